@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Benchmark of the paint -> FFT -> P(k) multipoles hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload at every N: BASELINE.json configs[1] ("C2") -- a lognormal mock of 1e8 particles in
+redshift space, TSC on a 512^3 mesh, P0/P2/P4 in kF-wide bins -- one independent realisation
+per GPU (weak scaling, no data-path collective; realisations are the unit the path shards on,
+as in configs[4]).  A "step" is one full pass particles -> mesh -> delta_k -> multipoles.
+
+  value  : whole-job Gparticles/s with the catalogue already resident in HBM
+  e2e    : the same through the public API with HOST (pinned) catalogues: H2D copy of the
+           particles and D2H read of the multipoles inside the timed region, every step
+  roofline / kernels : per-kernel device time from CUDA events recorded by the library around
+           each of its launches (second pass over the same K steps), algorithmic bytes from
+           DESIGN.md, peak from MEASURED_PEAKS.json
+  cpu_baseline : the C/NumPy restatement of the reference (oracle/) on the host cores, on a
+           bounded sample of the same workload, rank 0 only
+
+--impl reference times that CPU restatement as its own arm (JAX, and therefore the
+reference itself, cannot run offline on this image).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import socket
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "paint+FFT+P(k) multipoles end-to-end throughput"
+UNIT = "Gparticles/s"
+
+# ---- workload C2 (BASELINE.json configs[1])
+C2 = dict(name="C2", n_part=100_000_000, n_mesh=512, box=2000.0, order=3, seed=5, gen_grid=256)
+
+
+def k_edges_for(box, n_mesh):
+    kF = 2.0 * math.pi / box
+    return np.arange(kF, math.pi * n_mesh / box, kF).astype(np.float32)
+
+
+def config_dict(a, wl, n_gpus):
+    return {
+        "workload": (f"{wl['name']}: lognormal mock, {wl['n_part']:.3g} particles in redshift space (LOS z), "
+                     f"{ {2: 'CIC', 3: 'TSC', 4: 'PCS'}[wl['order']] } on {wl['n_mesh']}^3, box {wl['box']:g} Mpc/h, "
+                     f"P0/P2/P4 in kF-wide bins up to k_Nyquist"),
+        "n_part_per_gpu": wl["n_part"], "n_mesh": wl["n_mesh"], "box_size": wl["box"],
+        "mas_order": wl["order"], "n_kbins": int(len(k_edges_for(wl["box"], wl["n_mesh"])) - 1),
+        "paint_method": a.method,
+        "particle_order": "random (catalogue shuffled)",
+        "cache": f"inputs {12 * wl['n_part'] / 1e6:.0f} MB + mesh {4 * wl['n_mesh'] ** 3 / 1e6:.0f} MB per step, larger than the 126 MB L2 (no flush needed)",
+        "parallelism": f"{n_gpus} independent realisation(s), one per GPU; no data-path collective",
+    }
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampling of SM clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        # "under load": samples in the upper half of the power range
+        load = [s for s, p in zip(sm, pw) if pw and p >= 0.5 * max(pw)] or sm
+        return {"sm_mhz": statistics.median(load) if load else None,
+                "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------- CPU legs
+def cpu_reference_step(sample, wl, k_edges):
+    """One pass of the CPU restatement on `sample` particles; returns stage times (s)."""
+    from oracle import cport
+    x, y, z = sample
+    n, box = wl["n_mesh"], wl["box"]
+    t0 = time.perf_counter()
+    rho = cport.paint(np.zeros((n, n, n), np.float32), x, y, z, None, 0.0, 0.0, 0.0, box, n, True,
+                      order=wl["order"], compat="fixed")
+    t1 = time.perf_counter()
+    delta = rho / rho.mean() - np.float32(1.0)           # tests/correlations.py:49-50
+    t2 = time.perf_counter()
+    k3d, pk, nm = cport.powspec(delta, box, k_edges, mas_order=wl["order"], workers=-1)
+    t3 = time.perf_counter()
+    return {"paint_s": t1 - t0, "contrast_s": t2 - t1, "fft_bin_s": t3 - t2}, pk
+
+
+def cpu_sample_catalog(wl, n_sample):
+    import torch
+    from jax_powspec_b200.mocks import lognormal_catalog
+    x, y, z = lognormal_catalog(n_sample, wl["box"], n_grid=128, seed=wl["seed"], device="cpu")
+    return tuple(t.numpy() for t in (x, y, z))
+
+
+def cpu_throughput(times, wl, n_sample):
+    """Whole-workload Gparticles/s extrapolated from the bounded sample: painting scales with the
+    particle count, density contrast + FFT + binning are per-mesh costs paid once."""
+    full = times["paint_s"] * (wl["n_part"] / n_sample) + times["contrast_s"] + times["fft_bin_s"]
+    return wl["n_part"] / full / 1e9, full
+
+
+def run_reference_arm(a, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import build as obuild
+    obuild.build()
+    k_edges = k_edges_for(wl["box"], wl["n_mesh"])
+    n_sample = a.cpu_sample or 2_000_000
+    sample = cpu_sample_catalog(wl, n_sample)
+    for _ in range(a.warmup):
+        cpu_reference_step(sample, wl, k_edges)
+    acc = {"paint_s": 0.0, "contrast_s": 0.0, "fft_bin_s": 0.0}
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        t, _ = cpu_reference_step(sample, wl, k_edges)
+        for k in acc:
+            acc[k] += t[k] / a.steps
+    wall = (time.perf_counter() - t0) / a.steps
+    value, full_s = cpu_throughput(acc, wl, n_sample)
+    cores = len(os.sched_getaffinity(0))
+    sample_desc = (f"{n_sample:.3g} of {wl['n_part']:.3g} particles painted (serial float32 scatter, as XLA-CPU), "
+                   f"full {wl['n_mesh']}^3 density contrast + scipy rfftn ({cores} threads) + serial binning; "
+                   f"value = n_part / (paint_s * n_part/n_sample + contrast_s + fft_bin_s)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": wall * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(a, wl, a.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc,
+                         "stage_s": acc, "extrapolated_full_workload_s": full_s},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "JAX is not installable offline, so the reference's own JAX-on-CPU path cannot run; this arm "
+                "times oracle/ (C + NumPy restatement, pinned to the reference source run under oracle/jaxshim.py)",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------- GPU arm
+ALGO_BYTES = {
+    # kernel name -> algorithmic bytes per launch (DESIGN.md "Kernels"); np_ = particles, n = mesh side
+    "paint_atomic": lambda np_, n, w: np_ * (12 + 4 * w) + 4 * n ** 3,
+    "paint_tile": lambda np_, n, w: np_ * 16 + 4 * n ** 3,
+    "bucket_count": lambda np_, n, w: np_ * 12,
+    "bucket_scatter": lambda np_, n, w: np_ * (12 + 4 * w) + np_ * 16,
+    "pk_fold_bin": lambda np_, n, w: 8 * n * n * (n // 2 + 1),
+    "cufft_r2c": lambda np_, n, w: 24 * n ** 3,
+    "memset": lambda np_, n, w: 4 * n ** 3,
+}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_gpu_arm(a, wl):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import jax_powspec_b200 as jps
+    from jax_powspec_b200 import _lib
+    from jax_powspec_b200.mocks import lognormal_catalog
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n, box, npart, order = wl["n_mesh"], wl["box"], wl["n_part"], wl["order"]
+    k_edges = k_edges_for(box, n)
+    x, y, z = lognormal_catalog(npart, box, n_grid=wl["gen_grid"], seed=wl["seed"] + rank, device=dev)
+    torch.cuda.synchronize()
+    pipe = jps.PaintPowspec(n, box, k_edges, order=order, compat="fixed", method=a.method,
+                            n_part_max=npart, device=dev)
+
+    def step():
+        return pipe(x, y, z)
+
+    # ---- device-resident throughput
+    for _ in range(max(a.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.profile_enable(False)
+    _lib.profile_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / a.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    counts = _lib.profile_snapshot()
+    launches = sum(c for k, (c, _) in counts.items() if k not in _lib.LIBRARY_KERNELS)
+    result_pk = pipe.pk.clone()
+
+    # ---- per-kernel device time, same K steps, events recorded by the library around each launch
+    _lib.profile_reset()
+    _lib.profile_enable(True)
+    for _ in range(a.steps):
+        step()
+    torch.cuda.synchronize()
+    prof = _lib.profile_snapshot()
+    _lib.profile_enable(False)
+
+    # ---- end to end through the public API with host buffers
+    xh, yh, zh = (t.cpu().pin_memory() for t in (x, y, z))
+    del x, y, z
+    torch.cuda.empty_cache()
+    host = jps.HostPipeline(pipe, npart)
+    for _ in range(2):
+        host(xh, yh, zh)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        out = host(xh, yh, zh)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1) / a.steps)
+    h2d = 3 * npart * 4
+    d2h = int(sum(np.asarray(o).nbytes for o in out))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    kernels = {}
+    for name, (cnt, tot_ms) in prof.items():
+        per = tot_ms / cnt
+        entry = {"launches_per_step": cnt / a.steps, "ms_per_launch": per, "share_of_step": tot_ms / a.steps / ms}
+        if name in ALGO_BYTES:
+            b = ALGO_BYTES[name](npart, n, 0)
+            entry["algorithmic_bytes"] = b
+            entry["achieved_gbs"] = b / per / 1e6
+            entry["frac_of_peak"] = b / per / 1e6 / peak
+        kernels[name] = entry
+    ours = {k: v for k, v in kernels.items() if k not in _lib.LIBRARY_KERNELS and "algorithmic_bytes" in v}
+    dom = max(ours, key=lambda k: ours[k]["ms_per_launch"] * ours[k]["launches_per_step"]) if ours else None
+    roofline = None
+    if dom:
+        d = ours[dom]
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": d["frac_of_peak"], "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": d["algorithmic_bytes"], "ms_per_launch": d["ms_per_launch"]}
+
+    cpu = None
+    if world == 1 and not a.no_cpu:
+        from oracle import build as obuild
+        obuild.build()
+        n_sample = a.cpu_sample or 10_000_000
+        sample = tuple(t[:n_sample].numpy() for t in (xh, yh, zh))
+        times, pk_cpu = cpu_reference_step(sample, wl, k_edges)
+        v, full_s = cpu_throughput(times, wl, n_sample)
+        cores = len(os.sched_getaffinity(0))
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": (f"first {n_sample:.3g} of {npart:.3g} particles painted with the serial float32 C port "
+                          f"(1 thread, as XLA-CPU scatter), full {n}^3 density contrast + scipy rfftn ({cores} threads) "
+                          f"+ serial binning (1 thread); value extrapolates painting linearly to the full catalogue"),
+               "stage_s": times, "extrapolated_full_workload_s": full_s}
+
+    line = {
+        "metric": METRIC, "value": world * npart / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(a, wl, world),
+        "clocks": clocks,
+        "e2e": {"value": world * npart / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+        "check": {"P0_first_bins": [float(v) for v in result_pk[:3, 0].cpu()]},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--method", default="auto", choices=["auto", "atomic", "sorted"])
+    ap.add_argument("--n-part", type=float, default=None, help="override particles per GPU (smoke runs)")
+    ap.add_argument("--n-mesh", type=int, default=None)
+    ap.add_argument("--cpu-sample", type=int, default=None)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    wl = dict(C2)
+    if a.n_part:
+        wl["n_part"] = int(a.n_part)
+    if a.n_mesh:
+        wl["n_mesh"] = a.n_mesh
+    if a.impl == "reference":
+        return run_reference_arm(a, wl)
+    if a.gpus > 1 and "RANK" not in os.environ:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(free_port()), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_gpu_arm(a, wl)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,174 @@
+/*
+ * jps.h -- C ABI of libjps.so: the B200 (sm_100a) implementation of jax-powspec's
+ * mesh-painting + Fourier-space clustering hot path.
+ *
+ * This is the drop-in boundary.  Each entry point replaces one reference function
+ * (paths relative to the reference repository root):
+ *
+ *   jps_paint                 src/mas.py:88-153   cic_mas_vec   (variant JPS_VARIANT_VEC)
+ *                             src/mas.py:5-87     cic_mas       (variant JPS_VARIANT_SCAN)
+ *                             + TSC / PCS (order 3 / 4), absent from the reference
+ *   jps_powspec               src/correlations.py:7-56     powspec_vec
+ *   jps_powspec_fundamental   src/correlations.py:60-117   powspec_vec_fundamental
+ *   jps_xi                    src/correlations.py:120-187  xi_vec  (and the xi blocks :522-543, :689-710)
+ *   jps_xi_fundamental        src/correlations.py:191-261  xi_vec_fundamental
+ *   jps_bispec                src/correlations.py:334-462  bispec
+ *   jps_paint_powspec         tests/correlations.py:41-78  paint -> delta=rho/mean-1 -> powspec_vec
+ *
+ * The reference has no FFI of its own (it is pure Python on jax.numpy); these are the
+ * symbols a jax.ffi handler, a ctypes stub or any other host binds.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative JPS_ERR_* otherwise;
+ *     jps_last_error() returns a thread-local message for the last failure.
+ *   - all pointers documented "device" are CUDA device pointers BORROWED from the caller
+ *     (they must stay alive until `stream` reaches the operation); "host" pointers are
+ *     read before the call returns.
+ *   - all work is enqueued on the caller's `stream`; no call synchronises the device or
+ *     touches the default stream (exception: jps_plan_create, which builds cuFFT plans).
+ *   - no hidden device allocation: the caller passes the workspace whose size the
+ *     matching *_workspace_bytes() function reports.
+ *   - a plan is bound to the CUDA device current at creation and is not thread-safe;
+ *     distinct plans may be used concurrently from different threads / streams.
+ *   - `stream` is a cudaStream_t passed as void* so that this header needs no CUDA include.
+ */
+#ifndef JPS_H_
+#define JPS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JPS_VERSION 100
+
+#if defined(__GNUC__)
+#define JPS_API __attribute__((visibility("default")))
+#else
+#define JPS_API
+#endif
+
+/* error codes */
+#define JPS_OK                 0
+#define JPS_ERR_INVALID       -1   /* bad argument */
+#define JPS_ERR_CUDA          -2   /* CUDA runtime error */
+#define JPS_ERR_CUFFT         -3   /* cuFFT error */
+#define JPS_ERR_WORKSPACE     -4   /* workspace too small */
+#define JPS_ERR_UNSUPPORTED   -5   /* valid request this build cannot serve */
+
+/* mass-assignment order */
+#define JPS_ORDER_CIC 2
+#define JPS_ORDER_TSC 3
+#define JPS_ORDER_PCS 4
+
+/* compat: JPS_COMPAT_REFERENCE reproduces the reference bit-for-bit in semantics (SURVEY.md
+ * section 8 quirks Q1-Q3, Q18); JPS_COMPAT_FIXED uses the textbook weights, floor() cell
+ * choice and periodic wrap of every index. */
+#define JPS_COMPAT_REFERENCE 0
+#define JPS_COMPAT_FIXED     1
+
+/* which of the two reference painters' wrap handling to follow (only differs for wrap=0 and
+ * for particles outside the box) */
+#define JPS_VARIANT_VEC  0
+#define JPS_VARIANT_SCAN 1
+
+/* painter algorithm */
+#define JPS_PAINT_AUTO    0
+#define JPS_PAINT_ATOMIC  1   /* one thread per particle, global red.add (any order of particles) */
+#define JPS_PAINT_SORTED  2   /* bucket by mesh tile, deposit in shared memory, float4 flush */
+
+/* plan flags */
+#define JPS_PLAN_DEFAULT  0
+
+typedef struct jps_plan jps_plan_t;
+
+JPS_API int         jps_version(void);
+JPS_API const char* jps_last_error(void);
+
+/* ------------------------------------------------------------------ launch accounting */
+/* The library counts every kernel it launches, per kernel kind.  With profiling enabled each
+ * launch is also bracketed by CUDA events on the launching stream; jps_profile_get()
+ * synchronises on those events and returns the accumulated device time.  Used by bench.py
+ * for `gpu_launches` and the per-kernel roofline; off by default (zero overhead). */
+JPS_API int jps_profile_enable(int on);
+JPS_API int jps_profile_reset(void);
+JPS_API int jps_profile_num_kernels(void);
+JPS_API int jps_profile_get(int id, const char** name, unsigned long long* launches, double* ms);
+
+/* ------------------------------------------------------------------ plan ------------- */
+/* Bytes of device workspace a plan for an n_mesh^3 grid needs (delta_k buffer, cuFFT work
+ * area, lookup tables, accumulators).  n_shell_fields > 0 additionally reserves room for
+ * that many real-space shell fields (bispectrum); 0 for P(k)-only plans. */
+JPS_API int jps_plan_workspace_bytes(int n_mesh, int n_shell_fields, int flags, size_t* bytes);
+
+/* Build a plan on the current device.  `workspace` is device memory of at least
+ * jps_plan_workspace_bytes(...) bytes, 256-byte aligned, owned by the caller and kept
+ * alive until jps_plan_destroy. */
+JPS_API int jps_plan_create(int n_mesh, int n_shell_fields, int flags,
+                    void* workspace, size_t workspace_bytes, jps_plan_t** plan);
+JPS_API int jps_plan_destroy(jps_plan_t* plan);
+
+/* ------------------------------------------------------------------ painting --------- */
+/* Workspace for jps_paint (bucketed copy of the particles + tile offsets). */
+JPS_API int jps_paint_workspace_bytes(int n_mesh, int64_t n_part, int order, int method, size_t* bytes);
+
+/* mesh[n,n,n] (device, float32, C order) += deposit of n_part particles.
+ *   x,y,z,w : device float32; element i is at p[i*stride] (stride 1 = SoA arrays, 3 = the
+ *             columns of an (Np,3) row-major array); w may be NULL (unit weights, stride 1).
+ *   xmin..  : per-axis origin; box_size: cubic box; pos = (x-xmin) * (1/(box_size/n_mesh)) in
+ *             float32 exactly as src/mas.py:100-105.
+ *   wrap    : the reference's `wrap` argument. */
+JPS_API int jps_paint(int n_mesh,
+              const float* x, const float* y, const float* z, const float* w,
+              int64_t stride, int64_t n_part,
+              float xmin, float ymin, float zmin, float box_size,
+              int order, int wrap, int compat, int variant, int method,
+              float* mesh, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ P(k) ------------- */
+/* Power-spectrum multipoles of a mesh in user bins.
+ *   mesh       : device float32 [n,n,n]; not modified.
+ *   normalise  : 0 = mesh already holds delta (what powspec_vec receives);
+ *                1 = mesh holds rho: delta = rho/mean(rho) - 1 is applied in Fourier space
+ *                    through the DC mode (tests/correlations.py:49-50 folded in).
+ *   k_edges    : HOST float32 [nb+1], ascending, in h/Mpc; converted to grid units in float32
+ *                as src/correlations.py:42.
+ *   mas_order  : exponent p of the window deconvolution (1/sinc)^p per axis; the reference
+ *                hard-codes 2.
+ *   shot_noise : subtracted from P0 (the reference never does: pass 0).
+ * Outputs (device float32, as the reference returns): k3d[nb], pk3d[nb*3] row-major
+ * (P0,P2,P4), nmodes[nb].  Optional (may be NULL): sums[nb*3] float64 raw sums of
+ * |delta_k|^2 L_ell, counts[nb] int64 exact mode counts. */
+JPS_API int jps_powspec(jps_plan_t* plan, const float* mesh, int normalise, float box_size,
+                const float* k_edges, int nb, int mas_order, float shot_noise,
+                float* k3d, float* pk3d, float* nmodes,
+                double* sums, int64_t* counts, void* stream);
+
+/* Number of rows powspec_vec_fundamental returns for an n_mesh grid: floor(sqrt(3)*(n/2)). */
+JPS_API int jps_fundamental_nbins(int n_mesh);
+
+/* kF-wide integer bins, bin 0 dropped.  compat selects how k3d is formed (Q18). */
+JPS_API int jps_powspec_fundamental(jps_plan_t* plan, const float* mesh, int normalise, float box_size,
+                            int mas_order, int compat,
+                            float* k3d, float* pk3d, float* nmodes,
+                            double* sums, int64_t* counts, void* stream);
+
+/* ------------------------------------------------------------------ fused ------------ */
+/* paint (into the plan-owned mesh, zeroed first) -> R2C FFT -> multipoles; the call the
+ * benchmark times.  Arguments as jps_paint + jps_powspec(normalise=1, mas_order=order). */
+JPS_API int jps_paint_powspec(jps_plan_t* plan,
+                      const float* x, const float* y, const float* z, const float* w,
+                      int64_t stride, int64_t n_part,
+                      float xmin, float ymin, float zmin, float box_size,
+                      int order, int wrap, int compat, int method,
+                      const float* k_edges, int nb, float shot_noise,
+                      float* mesh, void* paint_workspace, size_t paint_workspace_bytes,
+                      float* k3d, float* pk3d, float* nmodes,
+                      double* sums, int64_t* counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JPS_H_ */

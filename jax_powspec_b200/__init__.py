@@ -1,0 +1,16 @@
+"""jax_powspec_b200 -- B200 (sm_100a) implementation of jax-powspec's mesh-painting and
+Fourier-space clustering hot path behind the reference's own function names.
+
+    from jax_powspec_b200.mas import cic_mas_vec
+    from jax_powspec_b200.correlations import powspec_vec
+
+Importing the package loads libjps.so and raises if it is missing (no CPU fallback).
+"""
+from . import _lib  # noqa: F401  (loads the CUDA library, fails loudly if absent)
+from .correlations import HostPipeline, PaintPowspec, paint_powspec, powspec_vec, powspec_vec_fundamental
+from .mas import cic_mas, cic_mas_vec, paint, pcs_mas_vec, tsc_mas_vec
+
+__all__ = [
+    "cic_mas", "cic_mas_vec", "tsc_mas_vec", "pcs_mas_vec", "paint",
+    "powspec_vec", "powspec_vec_fundamental", "paint_powspec", "PaintPowspec", "HostPipeline",
+]

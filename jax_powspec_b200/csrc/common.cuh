@@ -1,0 +1,143 @@
+// Shared declarations for libjps.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cufft.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/jps.h"
+
+namespace jps {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+
+#define JPS_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      jps::set_error("%s:%d CUDA error %d (%s) in %s", __FILE__, __LINE__, (int)e__,      \
+                     cudaGetErrorString(e__), #expr);                                     \
+      return JPS_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define JPS_CHECK_CUFFT(expr)                                                             \
+  do {                                                                                    \
+    cufftResult r__ = (expr);                                                             \
+    if (r__ != CUFFT_SUCCESS) {                                                           \
+      jps::set_error("%s:%d cuFFT error %d in %s", __FILE__, __LINE__, (int)r__, #expr);  \
+      return JPS_ERR_CUFFT;                                                               \
+    }                                                                                     \
+  } while (0)
+
+#define JPS_REQUIRE(cond, ...)                                                            \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      jps::set_error(__VA_ARGS__);                                                        \
+      return JPS_ERR_INVALID;                                                             \
+    }                                                                                     \
+  } while (0)
+
+#define JPS_CHECK_LAUNCH() JPS_CHECK_CUDA(cudaGetLastError())
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---------------------------------------------------------------- launch accounting
+// Every kernel launch of the library goes through a ScopedLaunch: it counts launches (always)
+// and, when profiling is enabled with jps_profile_enable(1), brackets the launch with CUDA
+// events on the launching stream so that bench.py can report per-kernel device time.
+enum KernelId {
+  K_PAINT_ATOMIC = 0,
+  K_BUCKET_COUNT,
+  K_BUCKET_SCAN,
+  K_BUCKET_SCATTER,
+  K_PAINT_TILE,
+  K_PK_FOLD_BIN,
+  K_PK_COUNT,
+  K_PK_FINALIZE,
+  K_FFT_R2C,        // cuFFT (library) -- timed, not counted as one of ours
+  K_FFT_C2R,
+  K_MEMSET,
+  K_SHELL_FILTER,
+  K_TRIPLE_REDUCE,
+  K_XI_BIN,
+  K_MISC,
+  K_NUM
+};
+
+struct ScopedLaunch {
+  ScopedLaunch(int id, cudaStream_t s);
+  ~ScopedLaunch();
+  int id;
+  cudaStream_t s;
+  cudaEvent_t e0, e1;
+  bool timed;
+};
+
+// ---------------------------------------------------------------- plan
+// Maximum number of distinct (reachable) k-bins the warp-private shared-memory
+// accumulators can hold; above it the binning kernel accumulates with global atomics.
+constexpr int kMaxSmemBins = 576;
+constexpr int kMaxUserBins = 1 << 20;
+
+struct BinTable {               // cached k^2 -> bin lookup for one set of edges
+  std::vector<float> key;       // edges in grid units (float32) that produced it (+ mode tag)
+  int nb = 0;                   // user bins
+  int nbc = 0;                  // compact (reachable) bins
+  bool valid = false;
+};
+
+}  // namespace jps
+
+struct jps_plan {
+  int n = 0;                    // mesh cells per side
+  int nz = 0;                   // n/2 + 1
+  int pitch = 0;                // complex elements per (kx,ky) row of delta_k
+  int device = 0;
+  int n_shell_fields = 0;
+  int64_t k2max = 0;            // 3 * (n/2)^2
+
+  cufftHandle r2c = 0;
+  bool r2c_ok = false;
+  cufftHandle c2r = 0;          // single inverse transform (xi, bispectrum shells)
+  bool c2r_ok = false;
+
+  // workspace partition (all device pointers inside the caller's workspace)
+  char* ws = nullptr;
+  size_t ws_bytes = 0;
+  float2* dk = nullptr;         // [n][n][pitch] complex64
+  void* fft_work = nullptr;
+  size_t fft_work_bytes = 0;
+  int32_t* lut = nullptr;       // [k2max+1]  k^2 -> compact bin (or -1)
+  int32_t* compact_to_bin = nullptr;   // [acc_cap] compact bin -> user bin
+  int32_t* bin_to_compact = nullptr;   // [kMaxUserBins] user bin -> compact bin or -1
+  float* edges = nullptr;       // [nb+1] bin edges in grid units (float32)
+  float* wlut = nullptr;        // [3][n] per-axis window factors for p = 2,3,4
+  double* acc = nullptr;        // [acc_cap][4] sums of the P0,P2,P4 weights (4th slot spare)
+  unsigned long long* cnt = nullptr;   // [acc_cap] mode counts             } geometry only:
+  double* ksum = nullptr;       // [acc_cap] sum of |k| (grid units) per bin  } cached with the
+  unsigned long long* lastidx = nullptr;  // [acc_cap] largest flat index per bin (Q18) } bin table
+  float* shell = nullptr;       // n_shell_fields real fields [n][n][2*pitch] (in-place C2R layout)
+  int acc_cap = 0;
+
+  jps::BinTable table;
+};
+
+namespace jps {
+
+// host side: window factors as the reference computes them in float32
+void host_window_axis(int n, int p, float* out);
+
+// powspec.cu
+int ensure_bin_table(jps_plan* plan, const float* kedges_grid, int nb, int mode, cudaStream_t s);
+
+}  // namespace jps

@@ -1,0 +1,253 @@
+// Plan object: cuFFT plans + partition of the caller's workspace.
+#include "common.cuh"
+
+#include <cmath>
+
+namespace jps {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---------------------------------------------------------------- launch accounting
+static const char* kKernelNames[K_NUM] = {
+    "paint_atomic", "bucket_count", "bucket_scan", "bucket_scatter", "paint_tile", "pk_fold_bin",
+    "pk_count_modes", "pk_finalize", "cufft_r2c", "cufft_c2r", "memset", "shell_filter",
+    "triple_reduce", "xi_bin", "misc"};
+
+struct Pending { int id; cudaEvent_t e0, e1; };
+static bool g_prof_on = false;
+static unsigned long long g_launches[K_NUM];
+static double g_ms[K_NUM];
+static std::vector<Pending> g_pending;
+static std::vector<cudaEvent_t> g_pool;
+
+static cudaEvent_t get_event() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+ScopedLaunch::ScopedLaunch(int id_, cudaStream_t s_) : id(id_), s(s_), e0(nullptr), e1(nullptr), timed(g_prof_on) {
+  ++g_launches[id];
+  if (timed) { e0 = get_event(); e1 = get_event(); cudaEventRecord(e0, s); }
+}
+
+ScopedLaunch::~ScopedLaunch() {
+  if (timed) { cudaEventRecord(e1, s); g_pending.push_back({id, e0, e1}); }
+}
+
+static void drain_pending() {
+  for (auto& p : g_pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(p.e1) == cudaSuccess && cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess)
+      g_ms[p.id] += ms;
+    g_pool.push_back(p.e0); g_pool.push_back(p.e1);
+  }
+  g_pending.clear();
+}
+
+// (1/sinc(pi k/N))^p per axis in float32, operation by operation as
+// /root/reference/src/correlations.py:15,20-21,32 evaluates it (Q13):
+//   prefact = pi/dims (Python double, cast when it meets the int32 k vector)
+//   x = prefact*k ; y = x/pi ; sinc(y) = sin(pi*y)/(pi*y), 1 at y == 0 ; (1/sinc)**p
+void host_window_axis(int n, int p, float* out) {
+  const float pref = (float)(M_PI / (double)n);
+  const float pi32 = (float)M_PI;
+  const int mid = n / 2;
+  for (int i = 0; i < n; ++i) {
+    const int ki = i > mid ? i - n : i;
+    const float x = pref * (float)ki;
+    const float y = x / pi32;
+    float s = 1.0f;
+    if (y != 0.0f) {
+      const float pix = pi32 * y;
+      s = sinf(pix) / pix;
+    }
+    const float r = 1.0f / s;
+    float v = r;
+    for (int j = 1; j < p; ++j) v = v * r;
+    out[i] = v;
+  }
+}
+
+struct Layout {
+  size_t dk, fft_work, lut, compact_to_bin, bin_to_compact, edges, wlut, acc, cnt, ksum, lastidx,
+      shell, total;
+  int cap;
+};
+
+static Layout make_layout(int n, int pitch, size_t fft_work_bytes, int n_shell_fields) {
+  Layout L;
+  const int mid = n / 2;
+  const int64_t k2max = 3LL * mid * mid;
+  L.cap = (int)std::min<int64_t>(k2max + 2, 262144);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  L.dk = take((size_t)n * n * pitch * sizeof(float2));
+  L.fft_work = take(fft_work_bytes);
+  L.lut = take((size_t)(k2max + 1) * 4);
+  L.compact_to_bin = take((size_t)L.cap * 4);
+  L.bin_to_compact = take((size_t)kMaxUserBins * 4);
+  L.edges = take((size_t)(kMaxUserBins + 1) * 4);
+  L.wlut = take((size_t)3 * n * 4);
+  L.acc = take((size_t)L.cap * 4 * 8);
+  L.cnt = take((size_t)L.cap * 8);
+  L.ksum = take((size_t)L.cap * 8);
+  L.lastidx = take((size_t)L.cap * 8);
+  L.shell = take((size_t)n_shell_fields * n * n * pitch * sizeof(float2));
+  L.total = off;
+  return L;
+}
+
+static int make_r2c(int n, int pitch, cufftHandle* h, size_t* work) {
+  JPS_CHECK_CUFFT(cufftCreate(h));
+  JPS_CHECK_CUFFT(cufftSetAutoAllocation(*h, 0));
+  long long dims[3] = {n, n, n};
+  long long inembed[3] = {n, n, n};
+  long long onembed[3] = {n, n, pitch};
+  JPS_CHECK_CUFFT(cufftMakePlanMany64(*h, 3, dims, inembed, 1, (long long)n * n * n, onembed, 1,
+                                      (long long)n * n * pitch, CUFFT_R2C, 1, work));
+  return JPS_OK;
+}
+
+static int make_c2r_inplace(int n, int pitch, cufftHandle* h, size_t* work) {
+  JPS_CHECK_CUFFT(cufftCreate(h));
+  JPS_CHECK_CUFFT(cufftSetAutoAllocation(*h, 0));
+  long long dims[3] = {n, n, n};
+  long long inembed[3] = {n, n, pitch};
+  long long onembed[3] = {n, n, 2LL * pitch};
+  JPS_CHECK_CUFFT(cufftMakePlanMany64(*h, 3, dims, inembed, 1, (long long)n * n * pitch, onembed, 1,
+                                      2LL * n * n * pitch, CUFFT_C2R, 1, work));
+  return JPS_OK;
+}
+
+static int pitch_for(int n) { return n / 2 + 1; }
+
+}  // namespace jps
+
+using namespace jps;
+
+extern "C" int jps_profile_enable(int on) {
+  drain_pending();
+  g_prof_on = on != 0;
+  return JPS_OK;
+}
+
+extern "C" int jps_profile_reset(void) {
+  drain_pending();
+  for (int i = 0; i < K_NUM; ++i) { g_launches[i] = 0; g_ms[i] = 0.0; }
+  return JPS_OK;
+}
+
+extern "C" int jps_profile_num_kernels(void) { return K_NUM; }
+
+extern "C" int jps_profile_get(int id, const char** name, unsigned long long* launches, double* ms) {
+  JPS_REQUIRE(id >= 0 && id < K_NUM, "jps_profile_get: id out of range");
+  drain_pending();                       // synchronises on the recorded events
+  if (name) *name = kKernelNames[id];
+  if (launches) *launches = g_launches[id];
+  if (ms) *ms = g_ms[id];
+  return JPS_OK;
+}
+
+extern "C" int jps_version(void) { return JPS_VERSION; }
+extern "C" const char* jps_last_error(void) { return g_err; }
+
+extern "C" int jps_plan_workspace_bytes(int n_mesh, int n_shell_fields, int flags, size_t* bytes) {
+  (void)flags;
+  JPS_REQUIRE(bytes != nullptr, "jps_plan_workspace_bytes: bytes is NULL");
+  JPS_REQUIRE(n_mesh >= 2 && n_mesh <= 4096, "jps_plan_workspace_bytes: n_mesh=%d out of range [2,4096]", n_mesh);
+  JPS_REQUIRE(n_shell_fields >= 0, "jps_plan_workspace_bytes: n_shell_fields < 0");
+  const int pitch = pitch_for(n_mesh);
+  cufftHandle h;
+  size_t w1 = 0, w2 = 0;
+  int rc = make_r2c(n_mesh, pitch, &h, &w1);
+  cufftDestroy(h);
+  if (rc) return rc;
+  rc = make_c2r_inplace(n_mesh, pitch, &h, &w2);
+  cufftDestroy(h);
+  if (rc) return rc;
+  *bytes = make_layout(n_mesh, pitch, std::max(w1, w2), n_shell_fields).total;
+  return JPS_OK;
+}
+
+extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* workspace,
+                               size_t workspace_bytes, jps_plan_t** out) {
+  (void)flags;
+  JPS_REQUIRE(out != nullptr, "jps_plan_create: plan is NULL");
+  *out = nullptr;
+  JPS_REQUIRE(n_mesh >= 2 && n_mesh <= 4096, "jps_plan_create: n_mesh=%d out of range [2,4096]", n_mesh);
+  JPS_REQUIRE(workspace != nullptr, "jps_plan_create: workspace is NULL");
+  JPS_REQUIRE(((uintptr_t)workspace & 255) == 0, "jps_plan_create: workspace must be 256-byte aligned");
+  jps_plan* p = new jps_plan();
+  p->n = n_mesh;
+  p->nz = n_mesh / 2 + 1;
+  p->pitch = pitch_for(n_mesh);
+  p->n_shell_fields = n_shell_fields;
+  p->k2max = 3LL * (n_mesh / 2) * (n_mesh / 2);
+  cudaError_t ce = cudaGetDevice(&p->device);
+  if (ce != cudaSuccess) { delete p; set_error("jps_plan_create: cudaGetDevice failed: %s", cudaGetErrorString(ce)); return JPS_ERR_CUDA; }
+  size_t w1 = 0, w2 = 0;
+  int rc = make_r2c(n_mesh, p->pitch, &p->r2c, &w1);
+  if (rc) { delete p; return rc; }
+  p->r2c_ok = true;
+  rc = make_c2r_inplace(n_mesh, p->pitch, &p->c2r, &w2);
+  if (rc) { cufftDestroy(p->r2c); delete p; return rc; }
+  p->c2r_ok = true;
+  Layout L = make_layout(n_mesh, p->pitch, std::max(w1, w2), n_shell_fields);
+  if (workspace_bytes < L.total) {
+    set_error("jps_plan_create: workspace has %zu bytes, %zu needed", workspace_bytes, L.total);
+    jps_plan_destroy(p);
+    return JPS_ERR_WORKSPACE;
+  }
+  char* ws = (char*)workspace;
+  p->ws = ws;
+  p->ws_bytes = workspace_bytes;
+  p->dk = (float2*)(ws + L.dk);
+  p->fft_work = ws + L.fft_work;
+  p->fft_work_bytes = std::max(w1, w2);
+  p->lut = (int32_t*)(ws + L.lut);
+  p->compact_to_bin = (int32_t*)(ws + L.compact_to_bin);
+  p->bin_to_compact = (int32_t*)(ws + L.bin_to_compact);
+  p->edges = (float*)(ws + L.edges);
+  p->wlut = (float*)(ws + L.wlut);
+  p->acc = (double*)(ws + L.acc);
+  p->cnt = (unsigned long long*)(ws + L.cnt);
+  p->ksum = (double*)(ws + L.ksum);
+  p->lastidx = (unsigned long long*)(ws + L.lastidx);
+  p->shell = (float*)(ws + L.shell);
+  p->acc_cap = L.cap;
+  cufftResult r = cufftSetWorkArea(p->r2c, p->fft_work);
+  if (r == CUFFT_SUCCESS) r = cufftSetWorkArea(p->c2r, p->fft_work);
+  if (r != CUFFT_SUCCESS) {
+    set_error("jps_plan_create: cufftSetWorkArea failed (%d)", (int)r);
+    jps_plan_destroy(p);
+    return JPS_ERR_CUFFT;
+  }
+  // window tables for p = 2, 3, 4 (tiny; synchronous copy at plan creation)
+  std::vector<float> w((size_t)3 * n_mesh);
+  for (int q = 0; q < 3; ++q) host_window_axis(n_mesh, q + 2, w.data() + (size_t)q * n_mesh);
+  ce = cudaMemcpy(p->wlut, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) {
+    set_error("jps_plan_create: window table upload failed: %s", cudaGetErrorString(ce));
+    jps_plan_destroy(p);
+    return JPS_ERR_CUDA;
+  }
+  *out = p;
+  return JPS_OK;
+}
+
+extern "C" int jps_plan_destroy(jps_plan_t* p) {
+  if (!p) return JPS_OK;
+  if (p->r2c_ok) cufftDestroy(p->r2c);
+  if (p->c2r_ok) cufftDestroy(p->c2r);
+  delete p;
+  return JPS_OK;
+}

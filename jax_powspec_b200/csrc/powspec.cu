@@ -1,0 +1,500 @@
+// P(k) multipoles: bin table, the fused streaming binning kernel (K4) and the API calls.
+//
+// Replaces /root/reference/src/correlations.py:25-54 (window multiply, |delta_k|^2, mu,
+// four jnp.histogram passes, normalisation) with ONE pass over delta_k.
+//
+// Design (B200): delta_k is read exactly once (8 B per stored mode, HBM bound).  All stored
+// modes (+-kx, +-ky) and (+-ky, +-kx) at the same kz share |k|, mu, the window factor, the
+// Legendre weights and the bin, so one warp owns a canonical pair (a <= b) = (|kx|,|ky|),
+// streams its <= 8 rows along kz with coalesced 8-byte loads, and folds them in registers
+// before any binning work.  Lanes that fall in the same bin are contiguous in kz (|k| is
+// monotone in kz), so a shuffle-based segmented reduction leaves one partial sum per
+// (warp, bin); those go to warp-private shared-memory accumulators with plain stores (no
+// atomics: shared-memory float atomics are CAS loops on sm_100a), are merged per block and
+// leave the SM as one float64 global red per (block, bin).
+//
+// Bin membership is decided with integers only: the float32 edges of jnp.histogram are
+// converted on the host into thresholds on k^2 = kx^2+ky^2+kz^2 (the smallest integer m
+// with sqrt_f32(m) >= edge), which reproduces searchsorted(kedges, sqrt_f32(k^2), 'right')
+// bit for bit -> mode counts are exact.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace jps {
+
+// ------------------------------------------------------------------ host: bin table
+// smallest integer m in [0, k2max+1] with sqrtf(m) >= e   (strict: > e)
+static int64_t edge_threshold(float e, bool strict, int64_t k2max) {
+  auto pass = [&](int64_t m) {
+    const float k = sqrtf((float)m);          // exact conversion: m < 2^24 for n <= 4096
+    return strict ? (k > e) : (k >= e);
+  };
+  if (std::isnan(e)) return k2max + 1;
+  if (pass(0)) return 0;
+  if (!pass(k2max)) return k2max + 1;
+  int64_t lo = 0, hi = k2max;                 // pass(lo) false, pass(hi) true; sqrtf is monotone
+  while (hi - lo > 1) {
+    const int64_t mid = lo + (hi - lo) / 2;
+    if (pass(mid)) hi = mid; else lo = mid;
+  }
+  return hi;
+}
+
+struct PairDecode {
+  int a, b;
+};
+
+__host__ __device__ inline PairDecode decode_pair(int p) {
+  int b = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+  while ((long long)(b + 1) * (b + 2) / 2 <= p) ++b;
+  while ((long long)b * (b + 1) / 2 > p) --b;
+  PairDecode d;
+  d.b = b;
+  d.a = p - (int)((long long)b * (b + 1) / 2);
+  return d;
+}
+
+// rows (ix,iy) of the half-space array whose (|kx|,|ky|) is {a,b} in either order
+struct RowSet {
+  int nrows;
+  int ix[8], iy[8];
+};
+
+__host__ __device__ inline RowSet make_rows(int a, int b, int n) {
+  RowSet r;
+  const int na = (a > 0 && 2 * a != n) ? 2 : 1;
+  const int nbb = (b > 0 && 2 * b != n) ? 2 : 1;
+  const int ia[2] = {a, n - a};
+  const int ib[2] = {b, n - b};
+  r.nrows = 0;
+  for (int i = 0; i < na; ++i)
+    for (int j = 0; j < nbb; ++j) {
+      r.ix[r.nrows] = ia[i]; r.iy[r.nrows] = ib[j]; ++r.nrows;
+    }
+  if (a != b) {
+    for (int i = 0; i < na; ++i)
+      for (int j = 0; j < nbb; ++j) {
+        r.ix[r.nrows] = ib[j]; r.iy[r.nrows] = ia[i]; ++r.nrows;
+      }
+  }
+  for (int q = r.nrows; q < 8; ++q) { r.ix[q] = 0; r.iy[q] = 0; }
+  return r;
+}
+
+// ------------------------------------------------------------------ device helpers
+// Segmented suffix sums over lanes; `heads` has a bit set for every lane that starts a segment.
+// After the call every head lane holds the sum of its segment.
+template <int NV>
+__device__ __forceinline__ void segmented_reduce(float (&v)[NV], unsigned heads, int lane) {
+  const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const bool ok = (lane + off < 32) && ((above & ((1u << off) - 1u)) == 0u);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float t = __shfl_down_sync(0xffffffffu, v[j], off);
+      if (ok) v[j] += t;
+    }
+  }
+}
+
+struct PkParams {
+  const float2* dk;
+  int n, nz, pitch;
+  const int32_t* lut;
+  const float* wl;         // [n] window factor per array index for the chosen order
+  int nbc;
+  double* acc;             // [nbc][4]
+  int normalise;
+  int npairs;
+};
+
+// K4: fold + bin.  SMEM = warp-private shared accumulators; otherwise global float64 reds.
+template <bool SMEM>
+__global__ void __launch_bounds__(256) pk_fold_bin_kernel(PkParams P) {
+  extern __shared__ float sacc[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int nacc = P.nbc * 3;
+  float* my = sacc + (size_t)warp * nacc;
+  if (SMEM) {
+    for (int i = lane; i < nacc; i += 32) my[i] = 0.0f;
+    __syncwarp();
+  }
+  float scale2 = 1.0f;
+  if (P.normalise) {
+    // delta_k = rho_k * N^3 / rho_0 for k != 0 (tests/correlations.py:49-50 in Fourier space)
+    const double dc = (double)P.dk[0].x;
+    const double s = (double)P.n * (double)P.n * (double)P.n / dc;
+    scale2 = (float)(s * s);
+  }
+  const int n = P.n, nz = P.nz;
+  const size_t pitch = (size_t)P.pitch;
+  for (int p = blockIdx.x * nwarps + warp; p < P.npairs; p += gridDim.x * nwarps) {
+    const PairDecode ab = decode_pair(p);
+    const RowSet rows = make_rows(ab.a, ab.b, n);
+    const float wab = P.wl[ab.a] * P.wl[ab.b];      // (c(kx)*c(ky)), symmetric in a<->b
+    const int k2ab = ab.a * ab.a + ab.b * ab.b;
+    const float2* rp[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      rp[r] = P.dk + ((size_t)rows.ix[r] * n + rows.iy[r]) * pitch;
+    for (int kz0 = 0; kz0 < nz; kz0 += 32) {
+      const int kz = kz0 + lane;
+      const bool active = kz < nz;
+      float v[3] = {0.0f, 0.0f, 0.0f};
+      int cb = -2;
+      if (active) {
+        float2 d[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          d[r] = (r < rows.nrows) ? __ldg(rp[r] + kz) : make_float2(0.0f, 0.0f);
+        const int k2 = k2ab + kz * kz;
+        cb = __ldg(P.lut + k2);
+        const float c = wab * P.wl[kz];             // (c(kx)*c(ky))*c(kz), correlations.py:32
+        float sum = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const float re = d[r].x * c, im = d[r].y * c;   // delta_k *= correction (:39)
+          sum += re * re + im * im;                       // (delta_k * conj(delta_k)).real (:40)
+        }
+        sum *= scale2;
+        float mu2 = 0.0f;
+        if (k2 > 0) mu2 = (float)(kz * kz) / (float)k2;   // mu = kz/|k| (:37-38), LOS = z (Q14)
+        else if (P.normalise) sum = 0.0f;                 // delta_0 = 0 after rho/mean - 1
+        v[0] = sum;
+        v[1] = sum * (3.0f * mu2 - 1.0f) * 0.5f;
+        v[2] = sum * (35.0f * mu2 * mu2 - 30.0f * mu2 + 3.0f) * 0.125f;
+      }
+      const int prev = __shfl_up_sync(0xffffffffu, cb, 1);
+      const bool head = (lane == 0) || (cb != prev);
+      const unsigned heads = __ballot_sync(0xffffffffu, head);
+      segmented_reduce<3>(v, heads, lane);
+      if (head && cb >= 0) {
+        if (SMEM) {
+          float* a = my + cb * 3;
+          a[0] += v[0]; a[1] += v[1]; a[2] += v[2];
+        } else {
+          double* a = P.acc + (size_t)cb * 4;
+          atomicAdd(a + 0, (double)v[0]);
+          atomicAdd(a + 1, (double)v[1]);
+          atomicAdd(a + 2, (double)v[2]);
+        }
+      }
+      if (SMEM) __syncwarp();
+    }
+  }
+  if (SMEM) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
+      double s = 0.0;
+      for (int w = 0; w < nwarps; ++w) s += (double)sacc[(size_t)w * nacc + i];
+      if (s != 0.0) atomicAdd(P.acc + (size_t)(i / 3) * 4 + (i % 3), s);
+    }
+  }
+}
+
+// Geometry only (no delta_k): exact mode counts, sum of |k| and largest C-order flat index per
+// bin (for the reference's k3D[.].set(...) in powspec_vec_fundamental, Q18).  Runs once per
+// bin table, results cached in the plan.
+struct CountParams {
+  int n, nz;
+  const int32_t* lut;
+  unsigned long long* cnt;
+  double* ksum;
+  unsigned long long* lastidx;
+  int npairs;
+};
+
+__global__ void __launch_bounds__(256) pk_count_kernel(CountParams P) {
+  const int n = P.n, nz = P.nz;
+  const long long total = (long long)P.npairs * nz;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(t / nz);
+    const int kz = (int)(t - (long long)p * nz);
+    const PairDecode ab = decode_pair(p);
+    const int k2 = ab.a * ab.a + ab.b * ab.b + kz * kz;
+    const int cb = P.lut[k2];
+    if (cb < 0) continue;
+    const RowSet rows = make_rows(ab.a, ab.b, n);
+    unsigned long long last = 0;
+    for (int r = 0; r < rows.nrows; ++r) {
+      const unsigned long long flat = ((unsigned long long)rows.ix[r] * n + rows.iy[r]) * nz + kz;
+      last = flat > last ? flat : last;
+    }
+    atomicAdd(P.cnt + cb, (unsigned long long)rows.nrows);
+    atomicAdd(P.ksum + cb, (double)rows.nrows * (double)sqrtf((float)k2));
+    atomicMax(P.lastidx + cb, last);
+  }
+}
+
+struct FinalizeParams {
+  int nb;                       // rows written
+  int first_bin;                // user bin of output row 0 (1 for the fundamental variant)
+  const int32_t* bin_to_compact;
+  const float* edges;           // grid units, may be null (fundamental)
+  const double* acc;
+  const unsigned long long* cnt;
+  const double* ksum;
+  const unsigned long long* lastidx;
+  int n, nz;
+  float kF;
+  double vol;                   // (box/N^2)^3 evaluated in float32 on the host
+  float shot_noise;
+  int kmode;                    // 0: bin centres (powspec_vec, Q10); 1: reference .set quirk (Q18); 2: mean k
+  float* k3d; float* pk3d; float* nmodes;
+  double* sums; int64_t* counts;
+};
+
+__global__ void pk_finalize_kernel(FinalizeParams F) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= F.nb) return;
+  const int bin = j + F.first_bin;
+  const int c = F.bin_to_compact[bin];
+  double s0 = 0, s2 = 0, s4 = 0, ks = 0;
+  unsigned long long cnt = 0, last = 0;
+  if (c >= 0) {
+    s0 = F.acc[(size_t)c * 4 + 0]; s2 = F.acc[(size_t)c * 4 + 1]; s4 = F.acc[(size_t)c * 4 + 2];
+    cnt = F.cnt[c]; ks = F.ksum[c]; last = F.lastidx[c];
+  }
+  const double nm = (double)(float)cnt;          // the reference's counts are float32 (Q8)
+  // empty bins: 0/0 -> NaN, as the reference (Q11)
+  F.pk3d[j * 3 + 0] = (float)(s0 / nm * F.vol - (double)F.shot_noise);
+  F.pk3d[j * 3 + 1] = (float)(s2 / nm * 5.0 * F.vol);
+  F.pk3d[j * 3 + 2] = (float)(s4 / nm * 9.0 * F.vol);
+  F.nmodes[j] = (float)cnt;
+  if (F.kmode == 0) {
+    F.k3d[j] = (0.5f * (F.edges[bin + 1] + F.edges[bin])) * F.kF;      // correlations.py:54
+  } else if (F.kmode == 1) {
+    // k3D.at[k_index].set(k): the last stored mode of the bin in C order wins, then /Nmodes*kF
+    float kl = 0.0f;
+    if (cnt > 0) {
+      const int kz = (int)(last % F.nz);
+      const unsigned long long xy = last / F.nz;
+      int iy = (int)(xy % F.n), ix = (int)(xy / F.n);
+      const int mid = F.n / 2;
+      const int kx = ix > mid ? ix - F.n : ix, ky = iy > mid ? iy - F.n : iy;
+      kl = sqrtf((float)(kx * kx + ky * ky + kz * kz));
+    }
+    F.k3d[j] = kl / (float)cnt * F.kF;
+  } else {
+    F.k3d[j] = (float)(ks / (double)cnt) * F.kF;
+  }
+  if (F.sums) { F.sums[j * 3 + 0] = s0; F.sums[j * 3 + 1] = s2; F.sums[j * 3 + 2] = s4; }
+  if (F.counts) F.counts[j] = (int64_t)cnt;
+}
+
+static int npairs_for(int n) {
+  const int m = n / 2 + 1;                     // |k| values 0..n/2
+  return m * (m + 1) / 2;
+}
+
+// mode 0: user edges (kedges_grid, nb).  mode 1: fundamental bins, bin = (int)sqrtf(k^2).
+int ensure_bin_table(jps_plan* plan, const float* kedges_grid, int nb, int mode, cudaStream_t s) {
+  BinTable& T = plan->table;
+  std::vector<float> key;
+  key.push_back((float)mode);
+  if (mode == 0) key.insert(key.end(), kedges_grid, kedges_grid + nb + 1);
+  if (T.valid && T.key.size() == key.size() &&
+      std::memcmp(T.key.data(), key.data(), key.size() * sizeof(float)) == 0)
+    return JPS_OK;
+  T.valid = false;
+  const int64_t k2max = plan->k2max;
+  std::vector<int32_t> lut((size_t)k2max + 1, -1);
+  if (mode == 0) {
+    JPS_REQUIRE(nb >= 1 && nb <= kMaxUserBins, "powspec: number of bins %d out of range [1,%d]", nb, kMaxUserBins);
+    for (int i = 0; i < nb; ++i)
+      JPS_REQUIRE(!(kedges_grid[i + 1] < kedges_grid[i]), "powspec: k_edges must be ascending");
+    // thresholds: T[i] = min m with sqrtf(m) >= e_i; last edge inclusive -> strict threshold
+    std::vector<int64_t> th(nb + 1);
+    for (int i = 0; i < nb; ++i) th[i] = edge_threshold(kedges_grid[i], false, k2max);
+    th[nb] = edge_threshold(kedges_grid[nb], true, k2max);
+    for (int i = 0; i < nb; ++i) {
+      // members of bin i: th[i] <= m < th[i+1] (for i < nb-1), and m < th[nb] for the last bin;
+      // searchsorted(...,'right') puts m in the LAST bin whose lower edge it reaches
+      const int64_t lo = th[i];
+      const int64_t hi = (i + 1 < nb) ? th[i + 1] : th[nb];
+      for (int64_t m = lo; m < hi && m <= k2max; ++m) lut[(size_t)m] = i;
+    }
+    // duplicates of the upper edge (k == e_nb exactly) belong to the last bin even if an
+    // earlier pass left them out: covered, th[nb] is strict.
+  } else {
+    nb = jps_fundamental_nbins(plan->n) + 1;
+    for (int64_t m = 0; m <= k2max; ++m) {
+      const int b = (int)sqrtf((float)m);
+      lut[(size_t)m] = (b < nb) ? b : -1;
+    }
+  }
+  // compact the reachable bins
+  std::vector<int32_t> b2c((size_t)nb, -1), c2b;
+  {
+    std::vector<char> seen((size_t)nb, 0);
+    for (int64_t m = 0; m <= k2max; ++m) if (lut[(size_t)m] >= 0) seen[(size_t)lut[(size_t)m]] = 1;
+    for (int i = 0; i < nb; ++i) if (seen[(size_t)i]) { b2c[(size_t)i] = (int32_t)c2b.size(); c2b.push_back(i); }
+    for (int64_t m = 0; m <= k2max; ++m) if (lut[(size_t)m] >= 0) lut[(size_t)m] = b2c[(size_t)lut[(size_t)m]];
+  }
+  const int nbc = (int)c2b.size();
+  if (nbc > plan->acc_cap) {
+    set_error("powspec: %d reachable bins exceed the plan capacity %d", nbc, plan->acc_cap);
+    return JPS_ERR_UNSUPPORTED;
+  }
+  JPS_CHECK_CUDA(cudaMemcpyAsync(plan->lut, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice, s));
+  JPS_CHECK_CUDA(cudaMemcpyAsync(plan->bin_to_compact, b2c.data(), b2c.size() * 4, cudaMemcpyHostToDevice, s));
+  if (nbc) JPS_CHECK_CUDA(cudaMemcpyAsync(plan->compact_to_bin, c2b.data(), c2b.size() * 4, cudaMemcpyHostToDevice, s));
+  if (mode == 0)
+    JPS_CHECK_CUDA(cudaMemcpyAsync(plan->edges, kedges_grid, (size_t)(nb + 1) * 4, cudaMemcpyHostToDevice, s));
+  // pageable sources are staged before cudaMemcpyAsync returns, so the vectors may die here
+  JPS_CHECK_CUDA(cudaMemsetAsync(plan->cnt, 0, (size_t)plan->acc_cap * 8, s));
+  JPS_CHECK_CUDA(cudaMemsetAsync(plan->ksum, 0, (size_t)plan->acc_cap * 8, s));
+  JPS_CHECK_CUDA(cudaMemsetAsync(plan->lastidx, 0, (size_t)plan->acc_cap * 8, s));
+  CountParams C;
+  C.n = plan->n; C.nz = plan->nz; C.lut = plan->lut; C.cnt = plan->cnt; C.ksum = plan->ksum;
+  C.lastidx = plan->lastidx; C.npairs = npairs_for(plan->n);
+  {
+    ScopedLaunch L(K_PK_COUNT, s);
+    pk_count_kernel<<<kNumSMs * 8, 256, 0, s>>>(C);
+  }
+  JPS_CHECK_LAUNCH();
+  T.key = key; T.nb = nb; T.nbc = nbc; T.valid = true;
+  return JPS_OK;
+}
+
+static int run_fft_and_bin(jps_plan* plan, const float* mesh, int normalise, int mas_order,
+                           cudaStream_t s) {
+  JPS_CHECK_CUFFT(cufftSetStream(plan->r2c, s));
+  {
+    ScopedLaunch L(K_FFT_R2C, s);
+    JPS_CHECK_CUFFT(cufftExecR2C(plan->r2c, (cufftReal*)mesh, (cufftComplex*)plan->dk));
+  }
+  const int nbc = plan->table.nbc;
+  JPS_CHECK_CUDA(cudaMemsetAsync(plan->acc, 0, (size_t)std::max(nbc, 1) * 4 * 8, s));
+  if (nbc == 0) return JPS_OK;
+  PkParams P;
+  P.dk = plan->dk; P.n = plan->n; P.nz = plan->nz; P.pitch = plan->pitch; P.lut = plan->lut;
+  P.wl = plan->wlut + (size_t)(mas_order - 2) * plan->n;
+  P.nbc = nbc; P.acc = plan->acc; P.normalise = normalise; P.npairs = npairs_for(plan->n);
+  const int threads = 256, warps = threads / 32;
+  if (nbc <= kMaxSmemBins) {
+    const size_t smem = (size_t)warps * nbc * 3 * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_fold_bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)((size_t)warps * kMaxSmemBins * 3 * sizeof(float))));
+      attr_set = true;
+    }
+    int per_sm = 1;
+    JPS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_fold_bin_kernel<true>, threads, smem));
+    per_sm = std::max(per_sm, 1);
+    const int want = (P.npairs + warps - 1) / warps;
+    const int blocks = std::min(want, kNumSMs * per_sm);
+    ScopedLaunch L(K_PK_FOLD_BIN, s);
+    pk_fold_bin_kernel<true><<<blocks, threads, smem, s>>>(P);
+  } else {
+    const int want = (P.npairs + warps - 1) / warps;
+    const int blocks = std::min(want, kNumSMs * 8);
+    ScopedLaunch L(K_PK_FOLD_BIN, s);
+    pk_fold_bin_kernel<false><<<blocks, threads, 0, s>>>(P);
+  }
+  JPS_CHECK_LAUNCH();
+  return JPS_OK;
+}
+
+static double ref_volume(float box_size, int n) {
+  const float t = box_size / (float)(n * n);    // (box_size/dims**2)**3 in float32, :50
+  return (double)(t * t * t);
+}
+
+static float ref_kF(float box_size) { return (float)(2.0 * M_PI) / box_size; }   // :12
+
+}  // namespace jps
+
+using namespace jps;
+
+extern "C" int jps_fundamental_nbins(int n_mesh) {
+  const int mid = n_mesh / 2;
+  return (int)sqrtf((float)(3 * mid * mid));   // jnp.int32(jnp.sqrt(3*middle**2)), :68
+}
+
+extern "C" int jps_powspec(jps_plan_t* plan, const float* mesh, int normalise, float box_size,
+                           const float* k_edges, int nb, int mas_order, float shot_noise,
+                           float* k3d, float* pk3d, float* nmodes, double* sums, int64_t* counts,
+                           void* stream) {
+  JPS_REQUIRE(plan && mesh && k_edges && k3d && pk3d && nmodes, "jps_powspec: NULL argument");
+  JPS_REQUIRE(nb >= 1 && nb <= kMaxUserBins, "jps_powspec: nb=%d out of range", nb);
+  JPS_REQUIRE(mas_order >= 2 && mas_order <= 4, "jps_powspec: mas_order must be 2, 3 or 4");
+  JPS_REQUIRE(box_size > 0.0f, "jps_powspec: box_size must be > 0");
+  cudaStream_t s = (cudaStream_t)stream;
+  const float kF = ref_kF(box_size);
+  std::vector<float> kg((size_t)nb + 1);
+  for (int i = 0; i <= nb; ++i) kg[(size_t)i] = k_edges[i] / kF;       // kedges = k_edges / kF, :42 (Q9)
+  int rc = ensure_bin_table(plan, kg.data(), nb, 0, s);
+  if (rc) return rc;
+  rc = run_fft_and_bin(plan, mesh, normalise, mas_order, s);
+  if (rc) return rc;
+  FinalizeParams F;
+  F.nb = nb; F.first_bin = 0; F.bin_to_compact = plan->bin_to_compact; F.edges = plan->edges;
+  F.acc = plan->acc; F.cnt = plan->cnt; F.ksum = plan->ksum; F.lastidx = plan->lastidx;
+  F.n = plan->n; F.nz = plan->nz; F.kF = kF; F.vol = ref_volume(box_size, plan->n);
+  F.shot_noise = shot_noise; F.kmode = 0;
+  F.k3d = k3d; F.pk3d = pk3d; F.nmodes = nmodes; F.sums = sums; F.counts = counts;
+  {
+    ScopedLaunch L(K_PK_FINALIZE, s);
+    pk_finalize_kernel<<<(nb + 127) / 128, 128, 0, s>>>(F);
+  }
+  JPS_CHECK_LAUNCH();
+  return JPS_OK;
+}
+
+extern "C" int jps_powspec_fundamental(jps_plan_t* plan, const float* mesh, int normalise,
+                                       float box_size, int mas_order, int compat, float* k3d,
+                                       float* pk3d, float* nmodes, double* sums, int64_t* counts,
+                                       void* stream) {
+  JPS_REQUIRE(plan && mesh && k3d && pk3d && nmodes, "jps_powspec_fundamental: NULL argument");
+  JPS_REQUIRE(mas_order >= 2 && mas_order <= 4, "jps_powspec_fundamental: mas_order must be 2, 3 or 4");
+  JPS_REQUIRE(box_size > 0.0f, "jps_powspec_fundamental: box_size must be > 0");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = ensure_bin_table(plan, nullptr, 0, 1, s);
+  if (rc) return rc;
+  rc = run_fft_and_bin(plan, mesh, normalise, mas_order, s);
+  if (rc) return rc;
+  const int kmax = jps_fundamental_nbins(plan->n);
+  if (kmax < 1) return JPS_OK;
+  FinalizeParams F;
+  F.nb = kmax; F.first_bin = 1; F.bin_to_compact = plan->bin_to_compact; F.edges = nullptr;
+  F.acc = plan->acc; F.cnt = plan->cnt; F.ksum = plan->ksum; F.lastidx = plan->lastidx;
+  F.n = plan->n; F.nz = plan->nz; F.kF = ref_kF(box_size); F.vol = ref_volume(box_size, plan->n);
+  F.shot_noise = 0.0f; F.kmode = (compat == JPS_COMPAT_REFERENCE) ? 1 : 2;
+  F.k3d = k3d; F.pk3d = pk3d; F.nmodes = nmodes; F.sums = sums; F.counts = counts;
+  {
+    ScopedLaunch L(K_PK_FINALIZE, s);
+    pk_finalize_kernel<<<(kmax + 127) / 128, 128, 0, s>>>(F);
+  }
+  JPS_CHECK_LAUNCH();
+  return JPS_OK;
+}
+
+extern "C" int jps_paint_powspec(jps_plan_t* plan, const float* x, const float* y, const float* z,
+                                 const float* w, int64_t stride, int64_t n_part, float xmin,
+                                 float ymin, float zmin, float box_size, int order, int wrap,
+                                 int compat, int method, const float* k_edges, int nb,
+                                 float shot_noise, float* mesh, void* paint_workspace,
+                                 size_t paint_workspace_bytes, float* k3d, float* pk3d,
+                                 float* nmodes, double* sums, int64_t* counts, void* stream) {
+  JPS_REQUIRE(plan && mesh, "jps_paint_powspec: NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n3 = (size_t)plan->n * plan->n * plan->n;
+  {
+    ScopedLaunch L(K_MEMSET, s);
+    JPS_CHECK_CUDA(cudaMemsetAsync(mesh, 0, n3 * sizeof(float), s));
+  }
+  int rc = jps_paint(plan->n, x, y, z, w, stride, n_part, xmin, ymin, zmin, box_size, order, wrap,
+                     compat, JPS_VARIANT_VEC, method, mesh, paint_workspace, paint_workspace_bytes,
+                     stream);
+  if (rc) return rc;
+  return jps_powspec(plan, mesh, 1, box_size, k_edges, nb, order, shot_noise, k3d, pk3d, nmodes,
+                     sums, counts, stream);
+}

@@ -1,0 +1,111 @@
+"""Plan cache and tensor plumbing (torch is used for device memory and streams only)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.JpsError(
+            "jax_powspec_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback"
+        )
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+class Plan:
+    """Owns the workspace tensor and the jps_plan_t* built on it."""
+
+    def __init__(self, n_mesh: int, n_shell_fields: int, device: torch.device):
+        self.n = int(n_mesh)
+        self.n_shell_fields = int(n_shell_fields)
+        self.device = device
+        nbytes = C.c_size_t(0)
+        with torch.cuda.device(device):
+            check(lib.jps_plan_workspace_bytes(self.n, self.n_shell_fields, 0, C.byref(nbytes)),
+                  "jps_plan_workspace_bytes")
+            self.workspace = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=device)
+            base = self.workspace.data_ptr()
+            aligned = (base + 255) // 256 * 256
+            handle = C.c_void_p(0)
+            check(lib.jps_plan_create(self.n, self.n_shell_fields, 0, C.c_void_p(aligned),
+                                      C.c_size_t(nbytes.value), C.byref(handle)), "jps_plan_create")
+        self.handle = handle
+        self.workspace_bytes = nbytes.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib.jps_plan_destroy(self.handle)
+            self.handle = None
+            self.workspace = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_PLANS: dict = {}
+
+
+def get_plan(n_mesh: int, device: torch.device, n_shell_fields: int = 0) -> Plan:
+    key = (int(n_mesh), device.index)
+    p = _PLANS.get(key)
+    if p is None or p.n_shell_fields < n_shell_fields:
+        if p is not None:
+            torch.cuda.synchronize(device)
+            p.close()
+        p = Plan(n_mesh, n_shell_fields, device)
+        _PLANS[key] = p
+    return p
+
+
+def clear_plans():
+    for p in list(_PLANS.values()):
+        p.close()
+    _PLANS.clear()
+
+
+# --------------------------------------------------------------------------- array plumbing
+class ArrayKind:
+    """Remembers what the caller passed so results come back the same way."""
+
+    def __init__(self, like):
+        self.is_torch = isinstance(like, torch.Tensor)
+        self.on_device = self.is_torch and like.is_cuda
+
+    def out(self, t: torch.Tensor):
+        if self.is_torch:
+            return t if self.on_device else t.cpu()
+        return t.cpu().numpy()
+
+
+def to_device_f32(a, device, *, allow_strided=False):
+    """float32 CUDA tensor for `a` (numpy array, host or device torch tensor).  Host data goes
+    through one host->device copy; device data is used in place (no copy) when it is float32
+    and contiguous (or a 1-d strided view when allow_strided)."""
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32)))
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    if not t.is_cuda:
+        t = t.to(device, non_blocking=True)
+    if not t.is_contiguous() and not (allow_strided and t.dim() == 1 and t.stride(0) >= 1):
+        t = t.contiguous()
+    return t

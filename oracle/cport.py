@@ -1,0 +1,70 @@
+"""ctypes wrapper of the C restatement (oracle/c/jps_oracle.c) -- TEST INFRASTRUCTURE.
+Used by tests and by bench.py's CPU legs (cpu_baseline / --impl reference)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import scipy.fft as sfft
+
+from . import build as _build
+from .correlations import grid_edges, k_fundamental
+
+F32 = np.float32
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.LIB if os.path.exists(_build.LIB) else _build.build()
+        _lib = C.CDLL(path)
+        fp = C.POINTER(C.c_float)
+        _lib.jpso_paint_cic_reference.argtypes = [fp, fp, fp, fp, fp, C.c_int64, C.c_float, C.c_float, C.c_float,
+                                                  C.c_float, C.c_int, C.c_int, C.c_int]
+        _lib.jpso_paint_bspline.argtypes = [fp, fp, fp, fp, fp, C.c_int64, C.c_float, C.c_float, C.c_float,
+                                            C.c_float, C.c_int, C.c_int, C.c_int]
+        _lib.jpso_pk_bin.argtypes = [fp, C.c_int, fp, C.c_int, C.c_int, fp, fp, fp, fp]
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def paint(mesh, x, y, z, w, xmin, ymin, zmin, box_size, n_bins, wrap=True, *, order=2,
+          compat="reference", variant="vec"):
+    """Serial float32 painter; accumulates into a copy of ``mesh``."""
+    n = int(n_bins)
+    out = np.ascontiguousarray(mesh, dtype=F32).copy()
+    x, y, z = (np.ascontiguousarray(a, dtype=F32) for a in (x, y, z))
+    w = None if w is None else np.ascontiguousarray(w, dtype=F32)
+    if order == 2 and compat == "reference":
+        rc = lib().jpso_paint_cic_reference(_p(out), _p(x), _p(y), _p(z), _p(w), len(x), xmin, ymin, zmin,
+                                            box_size, n, int(bool(wrap)), 1 if variant == "scan" else 0)
+    else:
+        rc = lib().jpso_paint_bspline(_p(out), _p(x), _p(y), _p(z), _p(w), len(x), xmin, ymin, zmin,
+                                      box_size, n, int(bool(wrap)), int(order))
+    if rc != 0:
+        raise RuntimeError("C oracle paint failed")
+    return out
+
+
+def powspec(delta, box_size, k_edges, *, mas_order=2, workers=-1):
+    """rfftn (scipy, all cores) + serial float32 binning.  Returns (k3D, Pk3D f32[nb,3], Nmodes f32)."""
+    delta = np.ascontiguousarray(delta, dtype=F32)
+    n = delta.shape[0]
+    dk = sfft.rfftn(delta, workers=workers).astype(np.complex64, copy=False)
+    dk = np.ascontiguousarray(dk)
+    kedges = grid_edges(k_edges, box_size)
+    nb = len(kedges) - 1
+    s0, s2, s4, cnt = (np.zeros(nb, F32) for _ in range(4))
+    rc = lib().jpso_pk_bin(_p(dk.view(F32)), n, _p(kedges), nb, int(mas_order), _p(s0), _p(s2), _p(s4), _p(cnt))
+    if rc != 0:
+        raise RuntimeError("C oracle binning failed")
+    vol = (F32(box_size) / F32(n * n)) ** 3
+    with np.errstate(invalid="ignore", divide="ignore"):
+        pk = np.stack([s0 / cnt * vol, s2 / cnt * F32(5.0) * vol, s4 / cnt * F32(9.0) * vol], axis=1)
+    k3d = (F32(0.5) * (kedges[1:] + kedges[:-1]) * k_fundamental(box_size)).astype(F32)
+    return k3d, pk, cnt

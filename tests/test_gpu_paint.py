@@ -1,0 +1,128 @@
+"""CUDA painters (through the C ABI) against the golden vectors and the f64 oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mas as om
+from tests.util import F32, clustered_particles
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def jps():
+    import jax_powspec_b200
+    return jax_powspec_b200
+
+
+def _mesh_close(got, want, n_per_cell_scale=1.0):
+    # float32 products + atomics in arbitrary order: error ~ few ulp of the cell value
+    want = np.asarray(want, dtype=np.float64)
+    tol = 4e-6 * np.maximum(np.abs(want), want.mean() * n_per_cell_scale) + 1e-7
+    bad = np.abs(np.asarray(got, dtype=np.float64) - want) > tol
+    assert not bad.any(), f"{bad.sum()} cells differ, max err {np.abs(got - want).max()}"
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+@pytest.mark.parametrize("variant", ["vec", "scan"])
+@pytest.mark.parametrize("wrap", [True, False])
+def test_golden_reference_compat(jps, golden_dir, tag, variant, wrap):
+    g = np.load(os.path.join(golden_dir, f"ref_paint_{tag}.npz"))
+    p, w, n, box, xmin = g["particles"], g["weights"], int(g["n"]), float(g["box"]), float(g["xmin"])
+    fn = jps.cic_mas_vec if variant == "vec" else jps.cic_mas
+    got = fn(np.zeros((n, n, n), F32), p[:, 0], p[:, 1], p[:, 2], w, len(p), xmin, xmin, xmin, box, n, wrap,
+             method="atomic")
+    assert isinstance(got, np.ndarray) and got.dtype == F32
+    _mesh_close(got, g[f"{variant}_wrap{int(wrap)}"])
+
+
+def test_golden_accumulate_and_functional(jps, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_paint_a.npz"))
+    p, w, n, box, xmin = g["particles"], g["weights"], int(g["n"]), float(g["box"]), float(g["xmin"])
+    pre = torch.from_numpy(g["pre"]).cuda()
+    keep = pre.clone()
+    pd = torch.from_numpy(p).cuda()
+    got = jps.cic_mas_vec(pre, pd[:, 0], pd[:, 1], pd[:, 2], torch.from_numpy(w).cuda(), len(p),
+                          xmin, xmin, xmin, box, n, True, method="atomic")
+    assert got.is_cuda and torch.equal(pre, keep), "input mesh must not be modified (functional API)"
+    _mesh_close(got.cpu().numpy(), g["vec_accumulate"])
+
+
+@pytest.mark.parametrize("order,compat", [(2, "reference"), (2, "fixed"), (3, "fixed"), (4, "fixed")])
+@pytest.mark.parametrize("wrap", [True, False])
+@pytest.mark.parametrize("method", ["atomic", "sorted"])
+def test_against_f64_oracle(jps, order, compat, wrap, method):
+    n, box, npart = 64, 1000.0, 300_000
+    p = clustered_particles(11 + order, npart, box)
+    w = (0.5 + np.random.default_rng(3).random(npart)).astype(F32)
+    want = om.paint(np.zeros((n, n, n)), p[:, 0], p[:, 1], p[:, 2], w, 0.0, 0.0, 0.0, box, n, wrap,
+                    order=order, compat=compat, precision="f64")
+    got = jps.paint(np.zeros((n, n, n), F32), p[:, 0], p[:, 1], p[:, 2], w, 0.0, 0.0, 0.0, box, n, wrap,
+                    order=order, compat=compat, method=method)
+    _mesh_close(got, want)
+    if compat == "fixed" and wrap:
+        assert abs(got.sum(dtype=np.float64) - w.sum(dtype=np.float64)) < 2e-6 * w.sum()   # mass conservation
+
+
+@pytest.mark.parametrize("method", ["atomic", "sorted"])
+def test_unweighted_strided_columns_nonpow2(jps, method):
+    n, box, npart = 50, 600.0, 100_000          # non power of two mesh (tests/void-model.py:69 uses 300)
+    p = clustered_particles(5, npart, box)
+    pd = torch.from_numpy(p).cuda()             # (Np,3) rows: x,y,z are stride-3 views, no copy
+    got = jps.paint(torch.zeros((n, n, n), device="cuda"), pd[:, 0], pd[:, 1], pd[:, 2], None,
+                    0.0, 0.0, 0.0, box, n, True, order=2, compat="reference", method=method)
+    want = om.paint(np.zeros((n, n, n)), p[:, 0], p[:, 1], p[:, 2], None, 0.0, 0.0, 0.0, box, n, True,
+                    order=2, compat="reference", precision="f64")
+    _mesh_close(got.cpu().numpy(), want)
+
+
+def test_known_answers(jps):
+    n, box = 8, 8.0
+    z = np.zeros((n, n, n), F32)
+    one = np.ones(1, F32)
+    # particle on a node -> one cell
+    m = jps.cic_mas_vec(z, np.array([3.0], F32), np.array([2.0], F32), np.array([5.0], F32), one, 1, 0., 0., 0., box, n, True)
+    assert m[3, 2, 5] == 1.0 and m.sum() == 1.0
+    # mid-cell: textbook 8 x 1/8; the reference's Q1 corner gets mdx*mdy*ddz = 1/8 as well at d=1/2
+    m = jps.cic_mas_vec(z, np.array([3.5], F32), np.array([2.5], F32), np.array([7.5], F32), one, 1, 0., 0., 0., box, n, True)
+    assert np.isclose(m.sum(), 1.0) and np.isclose(m[3, 2, 7], 0.125) and np.isclose(m[4, 3, 0], 0.125)  # z wraps
+    # Q1: off-centre particle, mass = 1 + mdx*ddz*(mdy-ddy)
+    dx, dy, dz = 0.25, 0.125, 0.75
+    m = jps.cic_mas_vec(z, np.array([1 + dx], F32), np.array([1 + dy], F32), np.array([1 + dz], F32), one, 1, 0., 0., 0., box, n, True)
+    assert np.isclose(m.sum(), 1 + (1 - dx) * dz * ((1 - dy) - dy), atol=1e-6)
+    m = jps.cic_mas_vec(z, np.array([1 + dx], F32), np.array([1 + dy], F32), np.array([1 + dz], F32), one, 1, 0., 0., 0., box, n, True, compat="fixed")
+    assert np.isclose(m.sum(), 1.0, atol=1e-6)
+    # TSC on a node: 3/4, 1/8, 1/8 per axis;  PCS on a node: 2/3, 1/6, 1/6
+    m = jps.tsc_mas_vec(z, np.array([4.0], F32), np.array([4.0], F32), np.array([4.0], F32), one, 1, 0., 0., 0., box, n, True)
+    assert np.isclose(m[4, 4, 4], 0.75 ** 3) and np.isclose(m[3, 4, 4], 0.125 * 0.75 ** 2) and np.isclose(m.sum(), 1.0)
+    m = jps.pcs_mas_vec(z, np.array([4.0], F32), np.array([4.0], F32), np.array([4.0], F32), one, 1, 0., 0., 0., box, n, True)
+    assert np.isclose(m[4, 4, 4], (2 / 3) ** 3) and np.isclose(m[5, 4, 4], (1 / 6) * (2 / 3) ** 2) and np.isclose(m.sum(), 1.0)
+    # empty input
+    m = jps.cic_mas_vec(z, np.zeros(0, F32), np.zeros(0, F32), np.zeros(0, F32), np.zeros(0, F32), 0, 0., 0., 0., box, n, True)
+    assert m.sum() == 0.0
+
+
+@pytest.mark.parametrize("order", [2, 3, 4])
+def test_translation_by_whole_cells(jps, order):
+    n, box, npart = 32, 320.0, 50_000
+    p = clustered_particles(21, npart, box)
+    cell = box / n
+    base = jps.paint(np.zeros((n, n, n), F32), p[:, 0], p[:, 1], p[:, 2], None, 0., 0., 0., box, n, True,
+                     order=order, compat="fixed", method="atomic")
+    # shifting the origin by whole cells rolls the mesh (xmin is per axis)
+    shifted = jps.paint(np.zeros((n, n, n), F32), p[:, 0], p[:, 1], p[:, 2], None, -3 * cell, 2 * cell, 0., box, n, True,
+                        order=order, compat="fixed", method="atomic")
+    np.testing.assert_allclose(shifted, np.roll(base, (3, -2), axis=(0, 1)), rtol=2e-4, atol=2e-4)
+
+
+def test_bad_arguments(jps):
+    z = np.zeros((8, 8, 8), F32)
+    a = np.zeros(4, F32)
+    with pytest.raises(ValueError):
+        jps.cic_mas_vec(z, a, a, a, a, 4, 0., 0., 0., 8.0, 16, True)        # n_bins != mesh shape
+    with pytest.raises(jps._lib.JpsError):
+        jps.paint(z, a, a, a, a, 0., 0., 0., 8.0, 8, True, order=5)
+    with pytest.raises(jps._lib.JpsError):
+        jps.paint(z, a, a, a, a, 0., 0., 0., -1.0, 8, True)
