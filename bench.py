@@ -66,51 +66,54 @@ def config_dict(a, wl, n_gpus):
 
 # ------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi sampling of SM clocks / throttle reasons DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """NVML sampling (5 ms period, own thread) of SM clock, power and throttle reasons DURING the
+    timed region -- the same fields as the nvidia-smi line in B200_PROFILING.md."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop_flag, self.thread, self.err = index, [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:                      # pragma: no cover
+            self.err = repr(e)
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, pw, rs))
+            except Exception as e:                  # pragma: no cover
+                self.err = repr(e)
+                break
+            time.sleep(0.005)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        # "under load": samples in the upper half of the power range
-        load = [s for s, p in zip(sm, pw) if pw and p >= 0.5 * max(pw)] or sm
-        return {"sm_mhz": statistics.median(load) if load else None,
-                "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
+        nv = self.nv
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80}
+        reasons = sorted({k for _, _, rs in self.rows for k, b in bits.items() if rs & b})
+        sm = [r[0] for r in self.rows]
+        pw = [r[1] for r in self.rows]
+        load = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm   # samples taken under load
+        return {"sm_mhz": statistics.median(load), "sm_mhz_min": min(load), "sm_max_mhz": self.max_sm,
+                "power_w_max": max(pw), "samples": len(sm), "samples_under_load": len(load), "reasons": reasons}
 
 
 # ------------------------------------------------------------------------------- CPU legs
@@ -255,16 +258,23 @@ def run_gpu_arm(a, wl):
     _lib.profile_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    torch.cuda.nvtx.range_push("jps_timed")
     e0.record()
     for _ in range(a.steps):
         step()
     e1.record()
     barrier()
+    torch.cuda.nvtx.range_pop()
     ms = max_over_ranks(e0.elapsed_time(e1) / a.steps)
     clocks = sampler.stop() if rank == 0 else None
     counts = _lib.profile_snapshot()
     launches = sum(c for k, (c, _) in counts.items() if k not in _lib.LIBRARY_KERNELS)
     result_pk = pipe.pk.clone()
+
+    if a.quick:                                   # profiler runs: only the timed region matters
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms, "gpu_launches": int(launches)}), flush=True)
+        return 0
 
     # ---- per-kernel device time, same K steps, events recorded by the library around each launch
     _lib.profile_reset()
@@ -369,6 +379,7 @@ def main():
     ap.add_argument("--n-mesh", type=int, default=None)
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="stop after the device-resident timed region (ncu runs)")
     a = ap.parse_args()
     wl = dict(C2)
     if a.n_part:

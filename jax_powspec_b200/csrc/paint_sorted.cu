@@ -1,18 +1,368 @@
-// Bucketed painter (K1 + K2) -- placeholder until the tile kernels land.
+// Bucketed painter: K1 (bucket_count / bucket_scan / bucket_scatter) + K2 (paint_tile).
+//
+// Why (measured on B200, tools/microbench.cu, profiles/r1_microbench.txt): a 512^3 mesh
+// (537 MB) does not fit the 126 MB L2, and random global reds then run at ~25 G/s (DRAM sector
+// read-modify-write) against ~190 G/s when the target is L2 resident and ~750 G/s for
+// shared-memory float atomics.  So particles are first bucketed by the 16^3-cell tile that
+// holds the lowest node of their stencil; one CTA per tile then deposits its bucket into a
+// shared-memory copy of the tile (+ (order-1) halo cells on the high side of each axis) and
+// flushes it once with 16-byte vector reds (red.global.add.v4.f32) -- every mesh cell is
+// touched by O(1) global operations instead of O(particles).
+//
+// Bucketed record = (px, py, pz, w): the float32 grid coordinate (x-xmin)*inv the reference
+// computes (src/mas.py:103-105) and the weight, so K2 needs no further per-catalogue scalars
+// and cell choice stays bit-identical to the reference's float32 arithmetic.
 #include "paint_common.cuh"
 
 namespace jps {
 
+constexpr int TILE = 16;                 // cells per tile side
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 8;
+
+struct TileGeom {
+  int n;        // mesh side
+  int nt;       // tiles per axis = ceil(n / TILE)
+  int ntiles;   // nt^3; bucket `ntiles` collects the particles the tile kernel cannot take
+};
+
+// Lowest stencil node of a particle along one axis, wrapped into [0, n); -1 if the particle
+// cannot be handled by the tile kernel (reference-compat CIC outside the box).
+template <int ORDER, bool REFCIC>
+__device__ __forceinline__ int anchor_axis(float pos, int n) {
+  if (REFCIC) {
+    const int i = (int)pos;              // truncation (Q3); in-box particles have 0 <= i < n
+    return (pos >= 0.0f && i < n) ? i : -1;
+  }
+  int base;
+  if (ORDER == 2) base = (int)floorf(pos);
+  else if (ORDER == 3) base = (int)floorf(pos + 0.5f) - 1;
+  else base = (int)floorf(pos) - 1;
+  return pymod(base, n);
+}
+
+template <int ORDER, bool REFCIC>
+__device__ __forceinline__ int tile_of(float px, float py, float pz, const TileGeom& g) {
+  const int ax = anchor_axis<ORDER, REFCIC>(px, g.n);
+  const int ay = anchor_axis<ORDER, REFCIC>(py, g.n);
+  const int az = anchor_axis<ORDER, REFCIC>(pz, g.n);
+  if ((ax | ay | az) < 0) return g.ntiles;
+  return ((ax / TILE) * g.nt + (ay / TILE)) * g.nt + (az / TILE);
+}
+
+// ---------------------------------------------------------------- K1a: histogram of tile ids
+template <int ORDER, bool REFCIC>
+__global__ void __launch_bounds__(256) bucket_count_kernel(PaintParams p, TileGeom g,
+                                                           unsigned* __restrict__ counts) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_part;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float px = (p.x[i * p.stride] - p.xmin) * p.inv;
+    const float py = (p.y[i * p.stride] - p.ymin) * p.inv;
+    const float pz = (p.z[i * p.stride] - p.zmin) * p.inv;
+    atomicAdd(counts + tile_of<ORDER, REFCIC>(px, py, pz, g), 1u);
+  }
+}
+
+// ---------------------------------------------------------------- K1b: exclusive scan (one CTA)
+// offsets[0..m] = exclusive prefix sums of counts[0..m-1]; cursor[i] = offsets[i]
+__global__ void __launch_bounds__(SCAN_THREADS) bucket_scan_kernel(const unsigned* __restrict__ counts,
+                                                                   unsigned* __restrict__ offsets,
+                                                                   unsigned* __restrict__ cursor, int m) {
+  __shared__ unsigned warp_tot[SCAN_THREADS / 32];
+  __shared__ unsigned carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < m; base += SCAN_THREADS * SCAN_ITEMS) {
+    unsigned v[SCAN_ITEMS];
+    unsigned tsum = 0;
+    const int i0 = base + tid * SCAN_ITEMS;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+      v[j] = (i0 + j < m) ? counts[i0 + j] : 0u;
+      tsum += v[j];
+    }
+    unsigned incl = tsum;                        // inclusive scan of thread sums within the warp
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned w = warp_tot[lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, w, off);
+        if (lane >= off) w += t;
+      }
+      warp_tot[lane] = w;                        // inclusive scan of warp totals
+    }
+    __syncthreads();
+    unsigned run = carry + (warp ? warp_tot[warp - 1] : 0u) + (incl - tsum);
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+      if (i0 + j < m) { offsets[i0 + j] = run; cursor[i0 + j] = run; }
+      run += v[j];
+    }
+    __syncthreads();
+    if (tid == SCAN_THREADS - 1) carry = run;    // last thread holds the running total
+    __syncthreads();
+  }
+  if (tid == 0) offsets[m] = carry;
+}
+
+// ---------------------------------------------------------------- K1c: scatter into buckets
+template <int ORDER, bool REFCIC>
+__global__ void __launch_bounds__(256) bucket_scatter_kernel(PaintParams p, TileGeom g,
+                                                             unsigned* __restrict__ cursor,
+                                                             float4* __restrict__ sorted) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_part;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float px = (p.x[i * p.stride] - p.xmin) * p.inv;
+    const float py = (p.y[i * p.stride] - p.ymin) * p.inv;
+    const float pz = (p.z[i * p.stride] - p.zmin) * p.inv;
+    const float w = p.w ? p.w[i] : 1.0f;
+    const unsigned slot = atomicAdd(cursor + tile_of<ORDER, REFCIC>(px, py, pz, g), 1u);
+    sorted[slot] = make_float4(px, py, pz, w);
+  }
+}
+
+// ---------------------------------------------------------------- K2: per-tile deposit
+__device__ __forceinline__ void red_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+// Per-axis local node offset (0..TILE-1 for the lowest node) and weights inside the tile.
+template <int ORDER>
+__device__ __forceinline__ void tile_axis(float pos, int n, int wrap, int origin, int& l0,
+                                          float (&w)[ORDER]) {
+  int idx[ORDER];
+  bspline_axis<ORDER>(pos, n, 1, idx, w);        // wrapped indices; idx[0] is the anchor
+  l0 = idx[0] - origin;
+  if (!wrap) {                                   // non-periodic: drop nodes outside the mesh
+    int base;
+    if (ORDER == 2) base = (int)floorf(pos);
+    else if (ORDER == 3) base = (int)floorf(pos + 0.5f) - 1;
+    else base = (int)floorf(pos) - 1;
+#pragma unroll
+    for (int s = 0; s < ORDER; ++s)
+      if (base + s < 0 || base + s >= n) w[s] = 0.0f;
+  }
+}
+
+template <int ORDER, bool REFCIC>
+__global__ void __launch_bounds__(256) paint_tile_kernel(const float4* __restrict__ sorted,
+                                                         const unsigned* __restrict__ offsets,
+                                                         TileGeom g, int wrap, int variant,
+                                                         int mesh_vec_ok, float* __restrict__ mesh) {
+  constexpr int L = TILE + ORDER - 1;            // local extent per axis (halo on the + side)
+  constexpr int LP = (L + 3) & ~3;               // z pitch: rows stay 16-byte aligned for the flush
+  __shared__ __align__(16) float tile[L * L * LP];
+  const int t = blockIdx.x;
+  const unsigned beg = offsets[t], end = offsets[t + 1];
+  if (beg == end) return;                        // empty tile: nothing to flush
+  const int tz = t % g.nt, ty = (t / g.nt) % g.nt, tx = t / (g.nt * g.nt);
+  const int ox = tx * TILE, oy = ty * TILE, oz = tz * TILE;
+  const int n = g.n;
+  for (int i = threadIdx.x; i < L * L * LP; i += blockDim.x) tile[i] = 0.0f;
+  __syncthreads();
+
+  for (unsigned i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    const float4 r = sorted[i];
+    if (REFCIC) {
+      int x0, x1, y0, y1, z0, z1;
+      float mdx, ddx, mdy, ddy, mdz, ddz;
+      cic_reference_axis(r.x, n, wrap, variant, x0, x1, mdx, ddx);
+      cic_reference_axis(r.y, n, wrap, variant, y0, y1, mdy, ddy);
+      cic_reference_axis(r.z, n, wrap, variant, z0, z1, mdz, ddz);
+      // in-box particles: x1 == (x0+1) mod n for every variant, i.e. local index +1
+      float* c = tile + ((x0 - ox) * L + (y0 - oy)) * LP + (z0 - oz);
+      const float wgt = r.w;
+      constexpr int SX = L * LP, SY = LP;
+      atomicAdd(c, ((mdx * mdy) * mdz) * wgt);
+      atomicAdd(c + SX, ((ddx * mdy) * mdz) * wgt);
+      atomicAdd(c + SY, ((mdx * ddy) * mdz) * wgt);
+      atomicAdd(c + 1, ((mdx * mdy) * ddz) * wgt);
+      atomicAdd(c + SX + SY, ((ddx * ddy) * mdz) * wgt);
+      atomicAdd(c + SX + 1, ((ddx * mdy) * ddz) * wgt);
+      atomicAdd(c + SY + 1, ((mdx * mdy) * ddz) * wgt);       // Q1 (reference weight)
+      atomicAdd(c + SX + SY + 1, ((ddx * ddy) * ddz) * wgt);
+    } else {
+      int lx, ly, lz;
+      float wx[ORDER], wy[ORDER], wz[ORDER];
+      tile_axis<ORDER>(r.x, n, wrap, ox, lx, wx);
+      tile_axis<ORDER>(r.y, n, wrap, oy, ly, wy);
+      tile_axis<ORDER>(r.z, n, wrap, oz, lz, wz);
+      float* c = tile + (lx * L + ly) * LP + lz;
+#pragma unroll
+      for (int a = 0; a < ORDER; ++a) {
+#pragma unroll
+        for (int b = 0; b < ORDER; ++b) {
+          const float wxy = wx[a] * wy[b];
+#pragma unroll
+          for (int cc = 0; cc < ORDER; ++cc)
+            atomicAdd(c + (a * L + b) * LP + cc, (wxy * wz[cc]) * r.w);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // flush: one (i,j) row of L floats at a time; 16-byte vector reds where the row segment is
+  // aligned and does not wrap, scalar reds for the halo tail.
+  const size_t n2 = (size_t)n * n;
+  const bool vec_ok = (n % 4 == 0) && mesh_vec_ok;
+  constexpr int NV = TILE / 4;                   // aligned float4 groups per row
+  constexpr int ROW_ITEMS = NV + (ORDER - 1);    // + scalar halo cells
+  for (int item = threadIdx.x; item < L * L * ROW_ITEMS; item += blockDim.x) {
+    const int q = item % ROW_ITEMS;
+    const int row = item / ROW_ITEMS;
+    const int j = row % L, i = row / L;
+    const int gx = (ox + i) % n, gy = (oy + j) % n;
+    float* grow = mesh + (size_t)gx * n2 + (size_t)gy * n;
+    const float* trow = tile + (i * L + j) * LP;
+    if (q < NV) {
+      const int k = q * 4;
+      const float4 v = *reinterpret_cast<const float4*>(trow + k) ;
+      if (v.x == 0.0f && v.y == 0.0f && v.z == 0.0f && v.w == 0.0f) continue;
+      const int gz = oz + k;
+      if (vec_ok && gz + 3 < n) {
+        red_v4(grow + gz, v.x, v.y, v.z, v.w);
+      } else {
+        if (v.x != 0.0f) atomicAdd(grow + (gz % n), v.x);
+        if (v.y != 0.0f) atomicAdd(grow + ((gz + 1) % n), v.y);
+        if (v.z != 0.0f) atomicAdd(grow + ((gz + 2) % n), v.z);
+        if (v.w != 0.0f) atomicAdd(grow + ((gz + 3) % n), v.w);
+      }
+    } else {
+      const int k = TILE + (q - NV);
+      const float v = trow[k];
+      if (v != 0.0f) atomicAdd(grow + ((oz + k) % n), v);
+    }
+  }
+}
+
+// Particles the tile kernel cannot take (reference-compat CIC outside the box): the last bucket,
+// painted with the general per-particle path straight from the bucketed records.
+__global__ void __launch_bounds__(256) paint_outliers_kernel(const float4* __restrict__ sorted,
+                                                             const unsigned* __restrict__ offsets,
+                                                             int bucket, int n, int wrap, int variant,
+                                                             float* __restrict__ mesh) {
+  const unsigned beg = offsets[bucket], end = offsets[bucket + 1];
+  const size_t n2 = (size_t)n * n;
+  for (unsigned i = beg + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
+    const float4 r = sorted[i];
+    int x0, x1, y0, y1, z0, z1;
+    float mdx, ddx, mdy, ddy, mdz, ddz;
+    cic_reference_axis(r.x, n, wrap, variant, x0, x1, mdx, ddx);
+    cic_reference_axis(r.y, n, wrap, variant, y0, y1, mdy, ddy);
+    cic_reference_axis(r.z, n, wrap, variant, z0, z1, mdz, ddz);
+#define JPS_CORNER(ix, iy, iz, wx, wy, wz)                                           \
+  if (((ix) | (iy) | (iz)) >= 0)                                                      \
+    atomicAdd(mesh + (size_t)(ix) * n2 + (size_t)(iy) * n + (iz), (((wx) * (wy)) * (wz)) * r.w);
+    JPS_CORNER(x0, y0, z0, mdx, mdy, mdz)
+    JPS_CORNER(x1, y0, z0, ddx, mdy, mdz)
+    JPS_CORNER(x0, y1, z0, mdx, ddy, mdz)
+    JPS_CORNER(x0, y0, z1, mdx, mdy, ddz)
+    JPS_CORNER(x1, y1, z0, ddx, ddy, mdz)
+    JPS_CORNER(x1, y0, z1, ddx, mdy, ddz)
+    JPS_CORNER(x0, y1, z1, mdx, mdy, ddz)
+    JPS_CORNER(x1, y1, z1, ddx, ddy, ddz)
+#undef JPS_CORNER
+  }
+}
+
+// ---------------------------------------------------------------- host side
+struct SortedLayout {
+  size_t sorted, counts, offsets, cursor, total;
+  int nbuckets;
+};
+
+static SortedLayout sorted_layout(int n, int64_t n_part) {
+  SortedLayout L;
+  const int nt = (n + TILE - 1) / TILE;
+  L.nbuckets = nt * nt * nt + 1;
+  size_t off = 0;
+  auto take = [&](size_t b) { size_t o = off; off = align_up(off + b, 256); return o; };
+  L.sorted = take((size_t)(n_part > 0 ? n_part : 1) * sizeof(float4));
+  L.counts = take((size_t)(L.nbuckets + 1) * 4);
+  L.offsets = take((size_t)(L.nbuckets + 1) * 4);
+  L.cursor = take((size_t)(L.nbuckets + 1) * 4);
+  L.total = off;
+  return L;
+}
+
 size_t paint_sorted_workspace(int n, int64_t n_part, int order) {
-  (void)n; (void)order;
-  return align_up((size_t)n_part * 16, 256) + ((size_t)1 << 20);
+  (void)order;
+  return sorted_layout(n, n_part).total;
+}
+
+template <int ORDER, bool REFCIC>
+static int run_sorted(const PaintParams& p, const TileGeom& g, const SortedLayout& L, char* ws,
+                      cudaStream_t s) {
+  unsigned* counts = (unsigned*)(ws + L.counts);
+  unsigned* offsets = (unsigned*)(ws + L.offsets);
+  unsigned* cursor = (unsigned*)(ws + L.cursor);
+  float4* sorted = (float4*)(ws + L.sorted);
+  const int threads = 256;
+  const int64_t want = (p.n_part + threads - 1) / threads;
+  const int blocks = (int)std::min<int64_t>(want, (int64_t)kNumSMs * 8 * 4);
+  {
+    ScopedLaunch T(K_MEMSET, s);
+    JPS_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)(L.nbuckets + 1) * 4, s));
+  }
+  {
+    ScopedLaunch T(K_BUCKET_COUNT, s);
+    bucket_count_kernel<ORDER, REFCIC><<<blocks, threads, 0, s>>>(p, g, counts);
+  }
+  JPS_CHECK_LAUNCH();
+  {
+    ScopedLaunch T(K_BUCKET_SCAN, s);
+    bucket_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(counts, offsets, cursor, L.nbuckets);
+  }
+  JPS_CHECK_LAUNCH();
+  {
+    ScopedLaunch T(K_BUCKET_SCATTER, s);
+    bucket_scatter_kernel<ORDER, REFCIC><<<blocks, threads, 0, s>>>(p, g, cursor, sorted);
+  }
+  JPS_CHECK_LAUNCH();
+  {
+    ScopedLaunch T(K_PAINT_TILE, s);
+    const int mesh_vec_ok = (((uintptr_t)p.mesh) & 15) == 0 ? 1 : 0;
+    paint_tile_kernel<ORDER, REFCIC><<<g.ntiles, 256, 0, s>>>(sorted, offsets, g, p.wrap, p.variant,
+                                                            mesh_vec_ok, p.mesh);
+  }
+  JPS_CHECK_LAUNCH();
+  if (REFCIC) {
+    ScopedLaunch T(K_PAINT_ATOMIC, s);
+    paint_outliers_kernel<<<kNumSMs, 256, 0, s>>>(sorted, offsets, g.ntiles, g.n, p.wrap, p.variant, p.mesh);
+    JPS_CHECK_LAUNCH();
+  }
+  return JPS_OK;
 }
 
 int paint_sorted(const PaintParams& p, int order, int compat, void* ws, size_t ws_bytes,
                  cudaStream_t s) {
-  (void)p; (void)order; (void)compat; (void)ws; (void)ws_bytes; (void)s;
-  set_error("jps_paint: JPS_PAINT_SORTED is not built yet");
-  return JPS_ERR_UNSUPPORTED;
+  if (p.n_part == 0) return JPS_OK;
+  JPS_REQUIRE(p.n_part < ((int64_t)1 << 32) - 1, "jps_paint: the sorted painter takes < 2^32 particles per call");
+  const SortedLayout L = sorted_layout(p.n, p.n_part);
+  if (ws == nullptr || ws_bytes < L.total) {
+    set_error("jps_paint: workspace has %zu bytes, %zu needed (jps_paint_workspace_bytes)", ws_bytes, L.total);
+    return JPS_ERR_WORKSPACE;
+  }
+  JPS_REQUIRE(((uintptr_t)ws & 15) == 0, "jps_paint: workspace must be 16-byte aligned");
+  TileGeom g;
+  g.n = p.n;
+  g.nt = (p.n + TILE - 1) / TILE;
+  g.ntiles = g.nt * g.nt * g.nt;
+  char* w = (char*)ws;
+  if (order == 2 && compat == JPS_COMPAT_REFERENCE) return run_sorted<2, true>(p, g, L, w, s);
+  if (order == 2) return run_sorted<2, false>(p, g, L, w, s);
+  if (order == 3) return run_sorted<3, false>(p, g, L, w, s);
+  return run_sorted<4, false>(p, g, L, w, s);
 }
 
 }  // namespace jps

