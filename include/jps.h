@@ -155,6 +155,46 @@ JPS_API int jps_powspec_fundamental(jps_plan_t* plan, const float* mesh, int nor
                             float* k3d, float* pk3d, float* nmodes,
                             double* sums, int64_t* counts, void* stream);
 
+/* ------------------------------------------------------------------ xi(s) ------------ */
+/* Configuration-space multipoles (needs a plan with n_shell_fields >= 1).
+ *   s_edges  : HOST float32 [nb+1] separations in Mpc/h; converted to grid units as
+ *              src/correlations.py:126,170.
+ *   guard_mu : 0 = xi_vec (mu = rz/|r| is NaN at r = 0, which poisons the first bin of xi2/xi4
+ *              when s_edges[0] == 0, quirk Q22); 1 = the composites' guarded mu (:527).
+ * Outputs (device float32): r3d[nb], xi3d[nb*3], nmodes[nb] (empty bins: inf, as the reference). */
+JPS_API int jps_xi(jps_plan_t* plan, const float* mesh, int normalise, float box_size,
+           const float* s_edges, int nb, int mas_order, int guard_mu,
+           float* r3d, float* xi3d, float* nmodes, double* sums, int64_t* counts, void* stream);
+
+/* Integer-lag bins, bin 0 dropped; jps_fundamental_nbins(n_mesh) rows. */
+JPS_API int jps_xi_fundamental(jps_plan_t* plan, const float* mesh, int normalise, float box_size,
+                       int mas_order, float* r3d, float* xi3d, float* nmodes,
+                       double* sums, int64_t* counts, void* stream);
+
+/* ------------------------------------------------------------------ bispectrum ------- */
+/* FFT bispectrum for fixed (k1, k2) and nbins opening angles (needs n_shell_fields >= 6).
+ *   theta : HOST float32 [nbins] radians.
+ * Outputs (device float32): k_all[nbins+2], pk[nbins+2] (P at every shell), B[nbins], Q[nbins]. */
+JPS_API int jps_bispec(jps_plan_t* plan, const float* mesh, int normalise, float box_size,
+               float k1, float k2, const float* theta, int nbins, int mas_order,
+               float* k_all, float* pk, float* B, float* Q, void* stream);
+
+/* ------------------------------------------------------------------ composites ------- */
+/* src/correlations.py:640-712: P(k) + xi(s) sharing ONE forward FFT (n_shell_fields >= 1). */
+JPS_API int jps_compute_2pt_correlations(jps_plan_t* plan, const float* mesh, int normalise, float box_size,
+                                 const float* s_edges, int ns, const float* k_edges, int nk, int mas_order,
+                                 float* k3d, float* pk3d, float* nmodes_pk,
+                                 float* r3d, float* xi3d, float* nmodes_xi, void* stream);
+
+/* src/correlations.py:464-637: P(k) + xi(s) + bispectrum sharing ONE forward FFT
+ * (n_shell_fields >= 6). */
+JPS_API int jps_compute_all_correlations(jps_plan_t* plan, const float* mesh, int normalise, float box_size,
+                                 const float* s_edges, int ns, const float* k_edges, int nk,
+                                 float k1, float k2, const float* theta, int nbins, int mas_order,
+                                 float* k3d, float* pk3d, float* nmodes_pk,
+                                 float* r3d, float* xi3d, float* nmodes_xi,
+                                 float* k_all, float* pk_shell, float* B, float* Q, void* stream);
+
 /* ------------------------------------------------------------------ fused ------------ */
 /* paint (into the plan-owned mesh, zeroed first) -> R2C FFT -> multipoles; the call the
  * benchmark times.  Arguments as jps_paint + jps_powspec(normalise=1, mas_order=order). */

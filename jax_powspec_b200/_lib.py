@@ -53,6 +53,13 @@ SIGNATURES = {
     "jps_powspec": (_i, [_vp, _vp, _i, _f, _fp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "jps_fundamental_nbins": (_i, [_i]),
     "jps_powspec_fundamental": (_i, [_vp, _vp, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "jps_xi": (_i, [_vp, _vp, _i, _f, _fp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "jps_xi_fundamental": (_i, [_vp, _vp, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "jps_bispec": (_i, [_vp, _vp, _i, _f, _f, _f, _fp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "jps_compute_2pt_correlations": (_i, [_vp, _vp, _i, _f, _fp, _i, _fp, _i, _i,
+                                          _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "jps_compute_all_correlations": (_i, [_vp, _vp, _i, _f, _fp, _i, _fp, _i, _f, _f, _fp, _i, _i,
+                                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "jps_paint_powspec": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _f, _f, _i, _i, _i, _i,
                                _fp, _i, _f, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

@@ -1,8 +1,10 @@
 """Fourier-space estimators with the reference's names and positional signatures.
 
 Drop-in for /root/reference/src/correlations.py: ``powspec_vec`` (:7-56),
-``powspec_vec_fundamental`` (:60-117) and the fused ``paint_powspec`` path the benchmark
-times (paint -> density contrast -> rfftn -> multipoles, tests/correlations.py:41-78).
+``powspec_vec_fundamental`` (:60-117), ``xi_vec`` (:120-187), ``xi_vec_fundamental`` (:191-261),
+``bispec`` (:334-462), ``compute_all_correlations`` (:464-637), ``compute_2pt_correlations``
+(:640-712), and the fused ``paint_powspec`` path the benchmark times (paint -> density contrast
+-> rfftn -> multipoles, tests/correlations.py:41-78).
 Results come back in the container kind of ``delta`` (NumPy in -> NumPy out, CUDA tensor in ->
 CUDA tensors out), float32 as the reference returns them.
 
@@ -20,7 +22,9 @@ from ._lib import check, lib
 from .mas import _common_stride, _paint_workspace
 from .plan import ArrayKind, get_plan, ptr, require_cuda, stream_ptr, to_device_f32
 
-__all__ = ["powspec_vec", "powspec_vec_fundamental", "paint_powspec", "PaintPowspec", "HostPipeline"]
+__all__ = ["powspec_vec", "powspec_vec_fundamental", "xi_vec", "xi_vec_fundamental", "xi_vec_coords",
+           "s_edges_conv", "bispec", "compute_2pt_correlations", "compute_all_correlations",
+           "paint_powspec", "PaintPowspec", "HostPipeline"]
 
 
 def _host_edges(k_edges):
@@ -90,6 +94,132 @@ def powspec_vec_fundamental(delta, box_size, *, mas_order=2, compat="reference",
     if return_raw:
         out = out + ((kind.out(sums), kind.out(counts)),)
     return out
+
+
+def _mesh_arg(delta, device):
+    mesh = to_device_f32(delta, device)
+    n = mesh.shape[0]
+    if mesh.dim() != 3 or tuple(mesh.shape) != (n, n, n):
+        raise ValueError("delta must be a cubic 3-d mesh")
+    return mesh, n
+
+
+def _f32(device, *shape):
+    return torch.empty(shape, dtype=torch.float32, device=device)
+
+
+def xi_vec(delta, box_size, s_edges, *, mas_order=2, normalise=False, guard_mu=False):
+    """xi_0,2,4(s): ``(r3D[nb], xi3D[nb,3], Nmodes3D[nb])`` like
+    /root/reference/src/correlations.py:121 (empty bins: Nmodes = inf, xi = 0; with
+    ``s_edges[0] == 0`` the first bin of xi2/xi4 is NaN exactly as in the reference, Q22 --
+    pass ``guard_mu=True`` for the composites' behaviour)."""
+    device = require_cuda()
+    kind = ArrayKind(delta)
+    mesh, n = _mesh_arg(delta, device)
+    e = _host_edges(s_edges)
+    nb = e.size - 1
+    plan = get_plan(n, device, n_shell_fields=1)
+    r3d, xi, nm = _f32(device, nb), _f32(device, nb, 3), _f32(device, nb)
+    check(lib.jps_xi(plan.handle, ptr(mesh), int(bool(normalise)), float(box_size), _edge_ptr(e), nb,
+                     int(mas_order), int(bool(guard_mu)), ptr(r3d), ptr(xi), ptr(nm), None, None,
+                     stream_ptr()), "jps_xi")
+    return kind.out(r3d), kind.out(xi), kind.out(nm)
+
+
+def xi_vec_fundamental(delta, box_size, *, mas_order=2, normalise=False):
+    """Integer-lag bins, bin 0 dropped (/root/reference/src/correlations.py:191)."""
+    device = require_cuda()
+    kind = ArrayKind(delta)
+    mesh, n = _mesh_arg(delta, device)
+    nb = lib.jps_fundamental_nbins(n)
+    plan = get_plan(n, device, n_shell_fields=1)
+    r3d, xi, nm = _f32(device, nb), _f32(device, nb, 3), _f32(device, nb)
+    check(lib.jps_xi_fundamental(plan.handle, ptr(mesh), int(bool(normalise)), float(box_size),
+                                 int(mas_order), ptr(r3d), ptr(xi), ptr(nm), None, None, stream_ptr()),
+          "jps_xi_fundamental")
+    return kind.out(r3d), kind.out(xi), kind.out(nm)
+
+
+def xi_vec_coords(dims, box_size, k_edges):
+    """/root/reference/src/correlations.py:263 -- bin centres in Mpc/h for grid-unit edges
+    (tiny 1-d host arithmetic, float32 like the reference)."""
+    kF = np.float32(2.0 * np.pi) / np.float32(box_size)
+    kedges = np.asarray(k_edges, dtype=np.float32) / kF
+    return np.float32(0.5) * (kedges[1:] + kedges[:-1]) * (np.float32(box_size) * np.float32(1.0) / np.float32(dims))
+
+
+def s_edges_conv(dims, box_size, s_edges):
+    """/root/reference/src/correlations.py:270."""
+    kF = np.float32(2.0 * np.pi) / np.float32(box_size)
+    return kF * np.asarray(s_edges, dtype=np.float32) * np.float32(dims) / np.float32(box_size)
+
+
+def _theta_arg(theta):
+    if isinstance(theta, torch.Tensor):
+        theta = theta.detach().cpu().numpy()
+    t = np.ascontiguousarray(np.asarray(theta, dtype=np.float32))
+    if t.ndim != 1 or t.size < 1:
+        raise ValueError("theta must be a non-empty 1-d array")
+    return t
+
+
+def bispec(delta, box_size, k1, k2, theta, *, mas_order=2, normalise=False):
+    """FFT bispectrum: ``(k_all[bins+2], Pk[bins+2], theta, B[bins], Q[bins])`` like
+    /root/reference/src/correlations.py:335."""
+    device = require_cuda()
+    kind = ArrayKind(delta)
+    mesh, n = _mesh_arg(delta, device)
+    t = _theta_arg(theta)
+    nb = t.size
+    plan = get_plan(n, device, n_shell_fields=6)
+    k_all, pk, B, Q = _f32(device, nb + 2), _f32(device, nb + 2), _f32(device, nb), _f32(device, nb)
+    check(lib.jps_bispec(plan.handle, ptr(mesh), int(bool(normalise)), float(box_size), float(k1), float(k2),
+                         _edge_ptr(t), nb, int(mas_order), ptr(k_all), ptr(pk), ptr(B), ptr(Q), stream_ptr()),
+          "jps_bispec")
+    th = torch.from_numpy(t).to(device) if kind.on_device else (torch.from_numpy(t) if kind.is_torch else t)
+    return kind.out(k_all), kind.out(pk), th, kind.out(B), kind.out(Q)
+
+
+def compute_2pt_correlations(delta, box_size, s_edges, k_edges, *, mas_order=2, normalise=False):
+    """``(k3D, Pk3D, Nmodes3D_pk, r3D, xi3D)`` with ONE forward FFT, like
+    /root/reference/src/correlations.py:641."""
+    device = require_cuda()
+    kind = ArrayKind(delta)
+    mesh, n = _mesh_arg(delta, device)
+    se, ke = _host_edges(s_edges), _host_edges(k_edges)
+    ns, nk = se.size - 1, ke.size - 1
+    plan = get_plan(n, device, n_shell_fields=1)
+    k3d, pk, nmk = _f32(device, nk), _f32(device, nk, 3), _f32(device, nk)
+    r3d, xi, nmx = _f32(device, ns), _f32(device, ns, 3), _f32(device, ns)
+    check(lib.jps_compute_2pt_correlations(plan.handle, ptr(mesh), int(bool(normalise)), float(box_size),
+                                           _edge_ptr(se), ns, _edge_ptr(ke), nk, int(mas_order),
+                                           ptr(k3d), ptr(pk), ptr(nmk), ptr(r3d), ptr(xi), ptr(nmx),
+                                           stream_ptr()), "jps_compute_2pt_correlations")
+    return tuple(kind.out(t) for t in (k3d, pk, nmk, r3d, xi))
+
+
+def compute_all_correlations(delta, box_size, s_edges, k_edges, k1, k2, theta, *, mas_order=2,
+                             normalise=False):
+    """The 11 outputs of /root/reference/src/correlations.py:465 with ONE forward FFT:
+    ``(k3D, Pk3D, Nmodes3D_pk, r3D, xi3D, Nmodes3D_xi, k_all, Pk, theta, B, Q)``."""
+    device = require_cuda()
+    kind = ArrayKind(delta)
+    mesh, n = _mesh_arg(delta, device)
+    se, ke, t = _host_edges(s_edges), _host_edges(k_edges), _theta_arg(theta)
+    ns, nk, nb = se.size - 1, ke.size - 1, t.size
+    plan = get_plan(n, device, n_shell_fields=6)
+    k3d, pk, nmk = _f32(device, nk), _f32(device, nk, 3), _f32(device, nk)
+    r3d, xi, nmx = _f32(device, ns), _f32(device, ns, 3), _f32(device, ns)
+    k_all, pks, B, Q = _f32(device, nb + 2), _f32(device, nb + 2), _f32(device, nb), _f32(device, nb)
+    check(lib.jps_compute_all_correlations(plan.handle, ptr(mesh), int(bool(normalise)), float(box_size),
+                                           _edge_ptr(se), ns, _edge_ptr(ke), nk, float(k1), float(k2),
+                                           _edge_ptr(t), nb, int(mas_order),
+                                           ptr(k3d), ptr(pk), ptr(nmk), ptr(r3d), ptr(xi), ptr(nmx),
+                                           ptr(k_all), ptr(pks), ptr(B), ptr(Q), stream_ptr()),
+          "jps_compute_all_correlations")
+    th = torch.from_numpy(t).to(device) if kind.on_device else (torch.from_numpy(t) if kind.is_torch else t)
+    o = kind.out
+    return o(k3d), o(pk), o(nmk), o(r3d), o(xi), o(nmx), o(k_all), o(pks), th, o(B), o(Q)
 
 
 class PaintPowspec:

@@ -1,0 +1,281 @@
+// FFT ("Scoccimarro") bispectrum: jps_bispec and the shared "from delta_k" stage.
+//
+// Replaces /root/reference/src/correlations.py:334-462 (bispec) and the bispectrum block of
+// compute_all_correlations (:557-632):
+//   shells j = (k1, k2, k3(theta_b)...), half-width kF, mask lo_j <= |k| < hi_j in grid units;
+//   d_j = irfftn(mask_j * delta_k), I_j = irfftn(mask_j);
+//   P_j = sum d_j^2 / sum I_j^2 * (box/N^2)^3
+//   B_b = sum d_0 d_1 d_{b+2} / sum I_0 I_1 I_{b+2} * (box^2/N^3)^3 ; Q_b = B_b/(P0P1+P0P3+P1P3)
+//
+// Here the [N,N,N/2+1,bins+2] boolean mask of the reference is never materialised: shell
+// membership is an integer test on k^2 against thresholds derived from the float32 shell bounds
+// (same construction as the P(k) bin edges), one kernel writes the masked delta_k AND the
+// indicator in a single read of delta_k, cuFFT C2R runs in place, and one fused kernel reads
+// the six real fields once to produce the four sums a triangle bin needs.  cuFFT's C2R is
+// unnormalised; the N^3 factors cancel in every ratio, exactly as the 1/N^3 of irfftn does in
+// the reference (Q20).
+#include "common.cuh"
+#include "fold.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace jps {
+
+__global__ void __launch_bounds__(256) shell_filter_kernel(const float2* __restrict__ dk, int n,
+                                                           int nz, int pitch,
+                                                           const float* __restrict__ wl,
+                                                           int normalise, int tlo, int thi,
+                                                           float2* __restrict__ out_delta,
+                                                           float2* __restrict__ out_ind) {
+  float scale = 1.0f;
+  if (normalise) scale = (float)((double)n * (double)n * (double)n / (double)dk[0].x);
+  const int mid = n / 2;
+  const long long rows = (long long)n * n;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int iy = (int)(row % n), ix = (int)(row / n);
+    const int kx = ix > mid ? ix - n : ix, ky = iy > mid ? iy - n : iy;
+    const int k2xy = kx * kx + ky * ky;
+    const float wxy = wl[ix] * wl[iy];
+    const float2* src = dk + (size_t)row * pitch;
+    float2* dd = out_delta + (size_t)row * pitch;
+    float2* di = out_ind + (size_t)row * pitch;
+    for (int kz = threadIdx.x; kz < pitch; kz += blockDim.x) {
+      float2 od = make_float2(0.0f, 0.0f), oi = make_float2(0.0f, 0.0f);
+      if (kz < nz) {
+        const int k2 = k2xy + kz * kz;
+        if (k2 >= tlo && k2 < thi) {
+          const float c = (wxy * wl[kz]) * scale;
+          const float2 d = src[kz];
+          od = make_float2(d.x * c, d.y * c);
+          if (normalise && k2 == 0) od = make_float2(0.0f, 0.0f);
+          oi.x = 1.0f;
+        }
+      }
+      dd[kz] = od;
+      di[kz] = oi;
+    }
+  }
+}
+
+// out[0] += sum d3^2, out[1] += sum i3^2, and when `triple`: out[2] += sum d0 d1 d3,
+// out[3] += sum i0 i1 i3.  Fields are [n][n][rowpitch] reals (in-place C2R layout).
+__global__ void __launch_bounds__(256) triple_reduce_kernel(const float* __restrict__ d0,
+                                                            const float* __restrict__ d1,
+                                                            const float* __restrict__ d3,
+                                                            const float* __restrict__ i0,
+                                                            const float* __restrict__ i1,
+                                                            const float* __restrict__ i3, int n,
+                                                            int rowpitch, int triple,
+                                                            double* __restrict__ out) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  const long long rows = (long long)n * n;
+  const int half = n / 2;                         // float2 loads (rows are 8-byte aligned, n even)
+  const bool vec = (n % 2 == 0);
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const size_t base = (size_t)row * rowpitch;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;   // float32 partials per row segment
+    if (vec) {
+      for (int j = threadIdx.x; j < half; j += blockDim.x) {
+        const float2 x3 = *reinterpret_cast<const float2*>(d3 + base + 2 * j);
+        const float2 y3 = *reinterpret_cast<const float2*>(i3 + base + 2 * j);
+        s0 += x3.x * x3.x + x3.y * x3.y;
+        s1 += y3.x * y3.x + y3.y * y3.y;
+        if (triple) {
+          const float2 x0 = *reinterpret_cast<const float2*>(d0 + base + 2 * j);
+          const float2 x1 = *reinterpret_cast<const float2*>(d1 + base + 2 * j);
+          const float2 y0 = *reinterpret_cast<const float2*>(i0 + base + 2 * j);
+          const float2 y1 = *reinterpret_cast<const float2*>(i1 + base + 2 * j);
+          s2 += x0.x * x1.x * x3.x + x0.y * x1.y * x3.y;
+          s3 += y0.x * y1.x * y3.x + y0.y * y1.y * y3.y;
+        }
+      }
+    } else {
+      for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const float x3 = d3[base + j], y3 = i3[base + j];
+        s0 += x3 * x3;
+        s1 += y3 * y3;
+        if (triple) {
+          s2 += d0[base + j] * d1[base + j] * x3;
+          s3 += i0[base + j] * i1[base + j] * y3;
+        }
+      }
+    }
+    a0 += (double)s0; a1 += (double)s1; a2 += (double)s2; a3 += (double)s3;
+  }
+  // block reduction in float64
+  __shared__ double red[4][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    a0 += __shfl_down_sync(0xffffffffu, a0, off);
+    a1 += __shfl_down_sync(0xffffffffu, a1, off);
+    a2 += __shfl_down_sync(0xffffffffu, a2, off);
+    a3 += __shfl_down_sync(0xffffffffu, a3, off);
+  }
+  if (lane == 0) { red[0][warp] = a0; red[1][warp] = a1; red[2][warp] = a2; red[3][warp] = a3; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
+    if (threadIdx.x < 2 || triple) atomicAdd(out + threadIdx.x, t);
+  }
+}
+
+// scal layout: [4*j + 0..3] for shell j: sum d^2, sum I^2, sum d0 d1 d_j, sum I0 I1 I_j
+__global__ void bispec_finalize_kernel(const double* __restrict__ scal, int nshell, double vol_p,
+                                       double vol_b, float* __restrict__ pk, float* __restrict__ B,
+                                       float* __restrict__ Q) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nshell) return;
+  const double pj = scal[4 * j] / scal[4 * j + 1] * vol_p;
+  pk[j] = (float)pj;
+  if (j >= 2) {
+    const double p0 = scal[0] / scal[1] * vol_p, p1 = scal[4] / scal[5] * vol_p;
+    const double b = scal[4 * j + 2] / scal[4 * j + 3] * vol_b;
+    B[j - 2] = (float)b;
+    Q[j - 2] = (float)(b / (p0 * p1 + p0 * pj + p1 * pj));
+  }
+}
+
+constexpr int kMaxShells = 250;      // 4 doubles per shell in the 1024-double scratch
+
+// Bispectrum stage given plan->dk.  Needs 6 shell fields: d0, d1, i0, i1 and a (d3, i3) pair.
+int bispec_from_dk(jps_plan* plan, int normalise, float box_size, float k1, float k2,
+                   const float* theta, int nbins, int mas_order, float* k_all_out, float* pk_out,
+                   float* B_out, float* Q_out, cudaStream_t s) {
+  if (plan->n_shell_fields < 6) {
+    set_error("bispec needs a plan created with n_shell_fields >= 6");
+    return JPS_ERR_WORKSPACE;
+  }
+  const int nshell = nbins + 2;
+  JPS_REQUIRE(nbins >= 1 && nshell <= kMaxShells, "bispec: number of theta bins %d out of range [1,%d]", nbins, kMaxShells - 2);
+  const int n = plan->n;
+  const float kF = ref_kF(box_size);
+  // k_all = [k1, k2, k3(theta)...] in float32, :347-357 (Q19)
+  std::vector<float> k_all((size_t)nshell);
+  k_all[0] = k1; k_all[1] = k2;
+  for (int b = 0; b < nbins; ++b) {
+    const float sn = k2 * sinf(theta[b]);
+    const float cs = k2 * cosf(theta[b]) + k1;
+    k_all[(size_t)b + 2] = sqrtf(sn * sn + cs * cs);
+  }
+  std::vector<int> tlo((size_t)nshell), thi((size_t)nshell);
+  for (int j = 0; j < nshell; ++j) {
+    const float lo = (k_all[(size_t)j] - kF) / kF, hi = (k_all[(size_t)j] + kF) / kF;
+    tlo[(size_t)j] = (int)edge_threshold(lo, false, plan->k2max);     // |k| >= lo
+    thi[(size_t)j] = (int)edge_threshold(hi, false, plan->k2max);     // |k| <  hi
+  }
+  JPS_CHECK_CUDA(cudaMemcpyAsync(k_all_out, k_all.data(), (size_t)nshell * 4, cudaMemcpyHostToDevice, s));
+  {
+    ScopedLaunch L(K_MEMSET, s);
+    JPS_CHECK_CUDA(cudaMemsetAsync(plan->scal, 0, 1024 * sizeof(double), s));
+  }
+  const size_t field_floats = (size_t)n * n * 2 * plan->pitch;
+  float* F[6];
+  for (int i = 0; i < 6; ++i) F[i] = plan->shell + (size_t)i * field_floats;
+  // F[0]=d0 F[1]=d1 F[2]=i0 F[3]=i1 F[4]=d3 F[5]=i3
+  const float* wl = plan->wlut + (size_t)(mas_order - 2) * n;
+  const int fblocks = (int)std::min<long long>((long long)n * n, (long long)kNumSMs * 16);
+  const int rblocks = (int)std::min<long long>((long long)n * n, (long long)kNumSMs * 8);
+  JPS_CHECK_CUFFT(cufftSetStream(plan->c2r, s));
+  for (int j = 0; j < nshell; ++j) {
+    float* dj = (j == 0) ? F[0] : (j == 1) ? F[1] : F[4];
+    float* ij = (j == 0) ? F[2] : (j == 1) ? F[3] : F[5];
+    {
+      ScopedLaunch L(K_SHELL_FILTER, s);
+      shell_filter_kernel<<<fblocks, 256, 0, s>>>(plan->dk, n, plan->nz, plan->pitch, wl, normalise,
+                                                  tlo[(size_t)j], thi[(size_t)j], (float2*)dj, (float2*)ij);
+    }
+    JPS_CHECK_LAUNCH();
+    {
+      ScopedLaunch L(K_FFT_C2R, s);
+      JPS_CHECK_CUFFT(cufftExecC2R(plan->c2r, (cufftComplex*)dj, (cufftReal*)dj));
+    }
+    {
+      ScopedLaunch L(K_FFT_C2R, s);
+      JPS_CHECK_CUFFT(cufftExecC2R(plan->c2r, (cufftComplex*)ij, (cufftReal*)ij));
+    }
+    {
+      ScopedLaunch L(K_TRIPLE_REDUCE, s);
+      triple_reduce_kernel<<<rblocks, 256, 0, s>>>(F[0], F[1], dj, F[2], F[3], ij, n, 2 * plan->pitch,
+                                                   j >= 2 ? 1 : 0, plan->scal + 4 * j);
+    }
+    JPS_CHECK_LAUNCH();
+  }
+  const float tp = box_size / (float)(n * n);                 // (box_size / dims**2)**3, :398
+  const float tb = (box_size * box_size) / (float)((long long)n * n * n);   // (box_size**2 / dims**3)**3, :451
+  {
+    ScopedLaunch L(K_PK_FINALIZE, s);
+    bispec_finalize_kernel<<<(nshell + 127) / 128, 128, 0, s>>>(plan->scal, nshell, (double)(tp * tp * tp),
+                                                               (double)(tb * tb * tb), pk_out, B_out, Q_out);
+  }
+  JPS_CHECK_LAUNCH();
+  return JPS_OK;
+}
+
+// xi.cu
+int xi_from_dk(jps_plan* plan, const BinTable& T, int normalise, int mas_order, int guard_mu, cudaStream_t s);
+int xi_finalize(jps_plan* plan, const BinTable& T, float box_size, int nb, int first_bin, int fundamental,
+                float* r3d, float* xi3d, float* nmodes, double* sums, int64_t* counts, cudaStream_t s);
+void xi_grid_edges(const float* s_edges, int nb, float box_size, int n, std::vector<float>& out);
+// powspec.cu
+int pk_from_dk(jps_plan* plan, float box_size, const float* k_edges, int nb, int normalise, int mas_order,
+               float shot_noise, float* k3d, float* pk3d, float* nmodes, double* sums, int64_t* counts,
+               cudaStream_t s);
+
+}  // namespace jps
+
+using namespace jps;
+
+extern "C" int jps_bispec(jps_plan_t* plan, const float* mesh, int normalise, float box_size,
+                          float k1, float k2, const float* theta, int nbins, int mas_order,
+                          float* k_all, float* pk, float* B, float* Q, void* stream) {
+  JPS_REQUIRE(plan && mesh && theta && k_all && pk && B && Q, "jps_bispec: NULL argument");
+  JPS_REQUIRE(mas_order >= 2 && mas_order <= 4, "jps_bispec: mas_order must be 2, 3 or 4");
+  JPS_REQUIRE(box_size > 0.0f, "jps_bispec: box_size must be > 0");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = forward_fft(plan, mesh, s);
+  if (rc) return rc;
+  return bispec_from_dk(plan, normalise, box_size, k1, k2, theta, nbins, mas_order, k_all, pk, B, Q, s);
+}
+
+extern "C" int jps_compute_2pt_correlations(jps_plan_t* plan, const float* mesh, int normalise,
+                                            float box_size, const float* s_edges, int ns,
+                                            const float* k_edges, int nk, int mas_order,
+                                            float* k3d, float* pk3d, float* nmodes_pk, float* r3d,
+                                            float* xi3d, float* nmodes_xi, void* stream) {
+  JPS_REQUIRE(plan && mesh && s_edges && k_edges && k3d && pk3d && nmodes_pk && r3d && xi3d && nmodes_xi,
+              "jps_compute_2pt_correlations: NULL argument");
+  JPS_REQUIRE(mas_order >= 2 && mas_order <= 4, "jps_compute_2pt_correlations: mas_order must be 2, 3 or 4");
+  JPS_REQUIRE(box_size > 0.0f && ns >= 1 && nk >= 1, "jps_compute_2pt_correlations: bad sizes");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = forward_fft(plan, mesh, s);                     // ONE rfftn shared by both estimators (:656)
+  if (rc) return rc;
+  rc = pk_from_dk(plan, box_size, k_edges, nk, normalise, mas_order, 0.0f, k3d, pk3d, nmodes_pk, nullptr, nullptr, s);
+  if (rc) return rc;
+  std::vector<float> kg;
+  xi_grid_edges(s_edges, ns, box_size, plan->n, kg);
+  BinTable* T = nullptr;
+  rc = ensure_bin_table(plan, kg.data(), ns, TABLE_XI_EDGES, s, &T);
+  if (rc) return rc;
+  rc = xi_from_dk(plan, *T, normalise, mas_order, /*guard_mu=*/1, s);        // composites guard mu (:527)
+  if (rc) return rc;
+  return xi_finalize(plan, *T, box_size, ns, 0, 0, r3d, xi3d, nmodes_xi, nullptr, nullptr, s);
+}
+
+extern "C" int jps_compute_all_correlations(jps_plan_t* plan, const float* mesh, int normalise,
+                                            float box_size, const float* s_edges, int ns,
+                                            const float* k_edges, int nk, float k1, float k2,
+                                            const float* theta, int nbins, int mas_order,
+                                            float* k3d, float* pk3d, float* nmodes_pk, float* r3d,
+                                            float* xi3d, float* nmodes_xi, float* k_all,
+                                            float* pk_shell, float* B, float* Q, void* stream) {
+  JPS_REQUIRE(theta && k_all && pk_shell && B && Q, "jps_compute_all_correlations: NULL argument");
+  int rc = jps_compute_2pt_correlations(plan, mesh, normalise, box_size, s_edges, ns, k_edges, nk,
+                                        mas_order, k3d, pk3d, nmodes_pk, r3d, xi3d, nmodes_xi, stream);
+  if (rc) return rc;
+  // delta_k from the shared forward FFT is still in the plan
+  return bispec_from_dk(plan, normalise, box_size, k1, k2, theta, nbins, mas_order, k_all, pk_shell,
+                        B, Q, (cudaStream_t)stream);
+}

@@ -87,13 +87,33 @@ struct ScopedLaunch {
 // Maximum number of distinct (reachable) k-bins the warp-private shared-memory
 // accumulators can hold; above it the binning kernel accumulates with global atomics.
 constexpr int kMaxSmemBins = 576;
-constexpr int kMaxUserBins = 1 << 20;
+constexpr int kMaxUserBins = 1 << 18;
 
-struct BinTable {               // cached k^2 -> bin lookup for one set of edges
-  std::vector<float> key;       // edges in grid units (float32) that produced it (+ mode tag)
+// bin-table kinds
+enum TableMode {
+  TABLE_PK_EDGES = 0,        // powspec_vec: user edges, half-space mode counts
+  TABLE_PK_FUNDAMENTAL = 1,  // powspec_vec_fundamental: bin = int(|k|)
+  TABLE_XI_EDGES = 2,        // xi_vec: user edges, full-grid pair counts
+  TABLE_XI_FUNDAMENTAL = 3   // xi_vec_fundamental
+};
+
+constexpr int kNumTables = 4;
+
+struct BinTable {               // cached k^2 -> bin lookup for one set of edges (one slot)
+  std::vector<float> key;       // mode tag + edges in grid units (float32) that produced it
+  int mode = 0;
   int nb = 0;                   // user bins
   int nbc = 0;                  // compact (reachable) bins
   bool valid = false;
+  unsigned long long stamp = 0; // LRU
+  // device storage (inside the plan workspace)
+  int32_t* lut = nullptr;              // [k2max+1]  k^2 -> compact bin (or -1)
+  int32_t* compact_to_bin = nullptr;   // [acc_cap]
+  int32_t* bin_to_compact = nullptr;   // [kMaxUserBins] user bin -> compact bin or -1
+  float* edges = nullptr;              // [nb+1] bin edges in grid units
+  unsigned long long* cnt = nullptr;   // [acc_cap] exact mode / cell counts   } geometry only,
+  double* ksum = nullptr;              // [acc_cap] sum of |k| (grid units)     } computed once
+  unsigned long long* lastidx = nullptr;  // [acc_cap] largest C-order flat index (Q18) } per table
 };
 
 }  // namespace jps
@@ -117,19 +137,14 @@ struct jps_plan {
   float2* dk = nullptr;         // [n][n][pitch] complex64
   void* fft_work = nullptr;
   size_t fft_work_bytes = 0;
-  int32_t* lut = nullptr;       // [k2max+1]  k^2 -> compact bin (or -1)
-  int32_t* compact_to_bin = nullptr;   // [acc_cap] compact bin -> user bin
-  int32_t* bin_to_compact = nullptr;   // [kMaxUserBins] user bin -> compact bin or -1
-  float* edges = nullptr;       // [nb+1] bin edges in grid units (float32)
   float* wlut = nullptr;        // [3][n] per-axis window factors for p = 2,3,4
-  double* acc = nullptr;        // [acc_cap][4] sums of the P0,P2,P4 weights (4th slot spare)
-  unsigned long long* cnt = nullptr;   // [acc_cap] mode counts             } geometry only:
-  double* ksum = nullptr;       // [acc_cap] sum of |k| (grid units) per bin  } cached with the
-  unsigned long long* lastidx = nullptr;  // [acc_cap] largest flat index per bin (Q18) } bin table
+  double* acc = nullptr;        // [acc_cap][4] per-call sums of the l=0,2,4 weights (4th slot spare)
+  double* scal = nullptr;       // [1024] small float64 scratch (bispectrum sums)
   float* shell = nullptr;       // n_shell_fields real fields [n][n][2*pitch] (in-place C2R layout)
   int acc_cap = 0;
 
-  jps::BinTable table;
+  jps::BinTable tables[jps::kNumTables];
+  unsigned long long stamp = 0;
 };
 
 namespace jps {
@@ -138,6 +153,11 @@ namespace jps {
 void host_window_axis(int n, int p, float* out);
 
 // powspec.cu
-int ensure_bin_table(jps_plan* plan, const float* kedges_grid, int nb, int mode, cudaStream_t s);
+int ensure_bin_table(jps_plan* plan, const float* kedges_grid, int nb, int mode, cudaStream_t s,
+                     BinTable** out);
+int64_t edge_threshold(float e, bool strict, int64_t k2max);
+int forward_fft(jps_plan* plan, const float* mesh, cudaStream_t s);
+double ref_volume(float box_size, int n);
+float ref_kF(float box_size);
 
 }  // namespace jps

@@ -77,9 +77,13 @@ void host_window_axis(int n, int p, float* out) {
   }
 }
 
+struct TableLayout {
+  size_t lut, compact_to_bin, bin_to_compact, edges, cnt, ksum, lastidx;
+};
+
 struct Layout {
-  size_t dk, fft_work, lut, compact_to_bin, bin_to_compact, edges, wlut, acc, cnt, ksum, lastidx,
-      shell, total;
+  size_t dk, fft_work, wlut, acc, scal, shell, total;
+  TableLayout t[kNumTables];
   int cap;
 };
 
@@ -92,15 +96,18 @@ static Layout make_layout(int n, int pitch, size_t fft_work_bytes, int n_shell_f
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   L.dk = take((size_t)n * n * pitch * sizeof(float2));
   L.fft_work = take(fft_work_bytes);
-  L.lut = take((size_t)(k2max + 1) * 4);
-  L.compact_to_bin = take((size_t)L.cap * 4);
-  L.bin_to_compact = take((size_t)kMaxUserBins * 4);
-  L.edges = take((size_t)(kMaxUserBins + 1) * 4);
+  for (int i = 0; i < kNumTables; ++i) {
+    L.t[i].lut = take((size_t)(k2max + 1) * 4);
+    L.t[i].compact_to_bin = take((size_t)L.cap * 4);
+    L.t[i].bin_to_compact = take((size_t)kMaxUserBins * 4);
+    L.t[i].edges = take((size_t)(kMaxUserBins + 1) * 4);
+    L.t[i].cnt = take((size_t)L.cap * 8);
+    L.t[i].ksum = take((size_t)L.cap * 8);
+    L.t[i].lastidx = take((size_t)L.cap * 8);
+  }
   L.wlut = take((size_t)3 * n * 4);
   L.acc = take((size_t)L.cap * 4 * 8);
-  L.cnt = take((size_t)L.cap * 8);
-  L.ksum = take((size_t)L.cap * 8);
-  L.lastidx = take((size_t)L.cap * 8);
+  L.scal = take((size_t)1024 * 8);
   L.shell = take((size_t)n_shell_fields * n * n * pitch * sizeof(float2));
   L.total = off;
   return L;
@@ -213,15 +220,19 @@ extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* 
   p->dk = (float2*)(ws + L.dk);
   p->fft_work = ws + L.fft_work;
   p->fft_work_bytes = std::max(w1, w2);
-  p->lut = (int32_t*)(ws + L.lut);
-  p->compact_to_bin = (int32_t*)(ws + L.compact_to_bin);
-  p->bin_to_compact = (int32_t*)(ws + L.bin_to_compact);
-  p->edges = (float*)(ws + L.edges);
+  for (int i = 0; i < kNumTables; ++i) {
+    BinTable& T = p->tables[i];
+    T.lut = (int32_t*)(ws + L.t[i].lut);
+    T.compact_to_bin = (int32_t*)(ws + L.t[i].compact_to_bin);
+    T.bin_to_compact = (int32_t*)(ws + L.t[i].bin_to_compact);
+    T.edges = (float*)(ws + L.t[i].edges);
+    T.cnt = (unsigned long long*)(ws + L.t[i].cnt);
+    T.ksum = (double*)(ws + L.t[i].ksum);
+    T.lastidx = (unsigned long long*)(ws + L.t[i].lastidx);
+  }
   p->wlut = (float*)(ws + L.wlut);
   p->acc = (double*)(ws + L.acc);
-  p->cnt = (unsigned long long*)(ws + L.cnt);
-  p->ksum = (double*)(ws + L.ksum);
-  p->lastidx = (unsigned long long*)(ws + L.lastidx);
+  p->scal = (double*)(ws + L.scal);
   p->shell = (float*)(ws + L.shell);
   p->acc_cap = L.cap;
   cufftResult r = cufftSetWorkArea(p->r2c, p->fft_work);

@@ -18,6 +18,7 @@
 // with sqrt_f32(m) >= edge), which reproduces searchsorted(kedges, sqrt_f32(k^2), 'right')
 // bit for bit -> mode counts are exact.
 #include "common.cuh"
+#include "fold.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -26,7 +27,7 @@ namespace jps {
 
 // ------------------------------------------------------------------ host: bin table
 // smallest integer m in [0, k2max+1] with sqrtf(m) >= e   (strict: > e)
-static int64_t edge_threshold(float e, bool strict, int64_t k2max) {
+int64_t edge_threshold(float e, bool strict, int64_t k2max) {
   auto pass = [&](int64_t m) {
     const float k = sqrtf((float)m);          // exact conversion: m < 2^24 for n <= 4096
     return strict ? (k > e) : (k >= e);
@@ -40,64 +41,6 @@ static int64_t edge_threshold(float e, bool strict, int64_t k2max) {
     if (pass(mid)) hi = mid; else lo = mid;
   }
   return hi;
-}
-
-struct PairDecode {
-  int a, b;
-};
-
-__host__ __device__ inline PairDecode decode_pair(int p) {
-  int b = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
-  while ((long long)(b + 1) * (b + 2) / 2 <= p) ++b;
-  while ((long long)b * (b + 1) / 2 > p) --b;
-  PairDecode d;
-  d.b = b;
-  d.a = p - (int)((long long)b * (b + 1) / 2);
-  return d;
-}
-
-// rows (ix,iy) of the half-space array whose (|kx|,|ky|) is {a,b} in either order
-struct RowSet {
-  int nrows;
-  int ix[8], iy[8];
-};
-
-__host__ __device__ inline RowSet make_rows(int a, int b, int n) {
-  RowSet r;
-  const int na = (a > 0 && 2 * a != n) ? 2 : 1;
-  const int nbb = (b > 0 && 2 * b != n) ? 2 : 1;
-  const int ia[2] = {a, n - a};
-  const int ib[2] = {b, n - b};
-  r.nrows = 0;
-  for (int i = 0; i < na; ++i)
-    for (int j = 0; j < nbb; ++j) {
-      r.ix[r.nrows] = ia[i]; r.iy[r.nrows] = ib[j]; ++r.nrows;
-    }
-  if (a != b) {
-    for (int i = 0; i < na; ++i)
-      for (int j = 0; j < nbb; ++j) {
-        r.ix[r.nrows] = ib[j]; r.iy[r.nrows] = ia[i]; ++r.nrows;
-      }
-  }
-  for (int q = r.nrows; q < 8; ++q) { r.ix[q] = 0; r.iy[q] = 0; }
-  return r;
-}
-
-// ------------------------------------------------------------------ device helpers
-// Segmented suffix sums over lanes; `heads` has a bit set for every lane that starts a segment.
-// After the call every head lane holds the sum of its segment.
-template <int NV>
-__device__ __forceinline__ void segmented_reduce(float (&v)[NV], unsigned heads, int lane) {
-  const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const bool ok = (lane + off < 32) && ((above & ((1u << off) - 1u)) == 0u);
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const float t = __shfl_down_sync(0xffffffffu, v[j], off);
-      if (ok) v[j] += t;
-    }
-  }
 }
 
 struct PkParams {
@@ -201,6 +144,7 @@ __global__ void __launch_bounds__(256) pk_fold_bin_kernel(PkParams P) {
 // bin (for the reference's k3D[.].set(...) in powspec_vec_fundamental, Q18).  Runs once per
 // bin table, results cached in the plan.
 struct CountParams {
+  int full_grid;            // 0: half-space (P(k)); 1: full n^3 grid (xi): z index folded like x,y
   int n, nz;
   const int32_t* lut;
   unsigned long long* cnt;
@@ -226,8 +170,11 @@ __global__ void __launch_bounds__(256) pk_count_kernel(CountParams P) {
       const unsigned long long flat = ((unsigned long long)rows.ix[r] * n + rows.iy[r]) * nz + kz;
       last = flat > last ? flat : last;
     }
-    atomicAdd(P.cnt + cb, (unsigned long long)rows.nrows);
-    atomicAdd(P.ksum + cb, (double)rows.nrows * (double)sqrtf((float)k2));
+    // full grid: +-kz are both stored (except 0 and the Nyquist index)
+    const int zmult = (P.full_grid && kz > 0 && 2 * kz != n) ? 2 : 1;
+    const unsigned long long mult = (unsigned long long)rows.nrows * zmult;
+    atomicAdd(P.cnt + cb, mult);
+    atomicAdd(P.ksum + cb, (double)mult * (double)sqrtf((float)k2));
     atomicMax(P.lastidx + cb, last);
   }
 }
@@ -288,40 +235,52 @@ __global__ void pk_finalize_kernel(FinalizeParams F) {
   if (F.counts) F.counts[j] = (int64_t)cnt;
 }
 
-static int npairs_for(int n) {
+int npairs_for(int n) {
   const int m = n / 2 + 1;                     // |k| values 0..n/2
   return m * (m + 1) / 2;
 }
 
-// mode 0: user edges (kedges_grid, nb).  mode 1: fundamental bins, bin = (int)sqrtf(k^2).
-int ensure_bin_table(jps_plan* plan, const float* kedges_grid, int nb, int mode, cudaStream_t s) {
-  BinTable& T = plan->table;
+// Find or build the k^2 -> bin table for (mode, edges).  Tables live in kNumTables LRU slots so
+// that P(k), xi(s) and the fundamental variants can alternate without rebuilding.
+int ensure_bin_table(jps_plan* plan, const float* kedges_grid, int nb, int mode, cudaStream_t s,
+                     BinTable** out) {
+  const bool user_edges = (mode == TABLE_PK_EDGES || mode == TABLE_XI_EDGES);
   std::vector<float> key;
   key.push_back((float)mode);
-  if (mode == 0) key.insert(key.end(), kedges_grid, kedges_grid + nb + 1);
-  if (T.valid && T.key.size() == key.size() &&
-      std::memcmp(T.key.data(), key.data(), key.size() * sizeof(float)) == 0)
-    return JPS_OK;
+  if (user_edges) key.insert(key.end(), kedges_grid, kedges_grid + nb + 1);
+  BinTable* slot = nullptr;
+  for (int i = 0; i < kNumTables; ++i) {
+    BinTable& T = plan->tables[i];
+    if (T.valid && T.key.size() == key.size() &&
+        std::memcmp(T.key.data(), key.data(), key.size() * sizeof(float)) == 0) {
+      T.stamp = ++plan->stamp;
+      *out = &T;
+      return JPS_OK;
+    }
+  }
+  for (int i = 0; i < kNumTables; ++i) {          // least recently used (or empty) slot
+    BinTable& T = plan->tables[i];
+    if (!slot || !T.valid || (slot->valid && T.stamp < slot->stamp)) slot = &T;
+    if (!T.valid) break;
+  }
+  BinTable& T = *slot;
   T.valid = false;
   const int64_t k2max = plan->k2max;
   std::vector<int32_t> lut((size_t)k2max + 1, -1);
-  if (mode == 0) {
-    JPS_REQUIRE(nb >= 1 && nb <= kMaxUserBins, "powspec: number of bins %d out of range [1,%d]", nb, kMaxUserBins);
+  if (user_edges) {
+    JPS_REQUIRE(nb >= 1 && nb <= kMaxUserBins, "number of bins %d out of range [1,%d]", nb, kMaxUserBins);
     for (int i = 0; i < nb; ++i)
-      JPS_REQUIRE(!(kedges_grid[i + 1] < kedges_grid[i]), "powspec: k_edges must be ascending");
-    // thresholds: T[i] = min m with sqrtf(m) >= e_i; last edge inclusive -> strict threshold
-    std::vector<int64_t> th(nb + 1);
-    for (int i = 0; i < nb; ++i) th[i] = edge_threshold(kedges_grid[i], false, k2max);
-    th[nb] = edge_threshold(kedges_grid[nb], true, k2max);
+      JPS_REQUIRE(!(kedges_grid[i + 1] < kedges_grid[i]), "bin edges must be ascending");
+    // thresholds: th[i] = min m with sqrtf(m) >= e_i; last edge inclusive -> strict threshold
+    std::vector<int64_t> th((size_t)nb + 1);
+    for (int i = 0; i < nb; ++i) th[(size_t)i] = edge_threshold(kedges_grid[i], false, k2max);
+    th[(size_t)nb] = edge_threshold(kedges_grid[nb], true, k2max);
     for (int i = 0; i < nb; ++i) {
-      // members of bin i: th[i] <= m < th[i+1] (for i < nb-1), and m < th[nb] for the last bin;
       // searchsorted(...,'right') puts m in the LAST bin whose lower edge it reaches
-      const int64_t lo = th[i];
-      const int64_t hi = (i + 1 < nb) ? th[i + 1] : th[nb];
+      const int64_t lo = th[(size_t)i];
+      const int64_t hi = th[(size_t)i + 1];
       for (int64_t m = lo; m < hi && m <= k2max; ++m) lut[(size_t)m] = i;
     }
-    // duplicates of the upper edge (k == e_nb exactly) belong to the last bin even if an
-    // earlier pass left them out: covered, th[nb] is strict.
   } else {
     nb = jps_fundamental_nbins(plan->n) + 1;
     for (int64_t m = 0; m <= k2max; ++m) {
@@ -339,42 +298,49 @@ int ensure_bin_table(jps_plan* plan, const float* kedges_grid, int nb, int mode,
   }
   const int nbc = (int)c2b.size();
   if (nbc > plan->acc_cap) {
-    set_error("powspec: %d reachable bins exceed the plan capacity %d", nbc, plan->acc_cap);
+    set_error("%d reachable bins exceed the plan capacity %d", nbc, plan->acc_cap);
     return JPS_ERR_UNSUPPORTED;
   }
-  JPS_CHECK_CUDA(cudaMemcpyAsync(plan->lut, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice, s));
-  JPS_CHECK_CUDA(cudaMemcpyAsync(plan->bin_to_compact, b2c.data(), b2c.size() * 4, cudaMemcpyHostToDevice, s));
-  if (nbc) JPS_CHECK_CUDA(cudaMemcpyAsync(plan->compact_to_bin, c2b.data(), c2b.size() * 4, cudaMemcpyHostToDevice, s));
-  if (mode == 0)
-    JPS_CHECK_CUDA(cudaMemcpyAsync(plan->edges, kedges_grid, (size_t)(nb + 1) * 4, cudaMemcpyHostToDevice, s));
+  JPS_CHECK_CUDA(cudaMemcpyAsync(T.lut, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice, s));
+  JPS_CHECK_CUDA(cudaMemcpyAsync(T.bin_to_compact, b2c.data(), b2c.size() * 4, cudaMemcpyHostToDevice, s));
+  if (nbc) JPS_CHECK_CUDA(cudaMemcpyAsync(T.compact_to_bin, c2b.data(), c2b.size() * 4, cudaMemcpyHostToDevice, s));
+  if (user_edges)
+    JPS_CHECK_CUDA(cudaMemcpyAsync(T.edges, kedges_grid, (size_t)(nb + 1) * 4, cudaMemcpyHostToDevice, s));
   // pageable sources are staged before cudaMemcpyAsync returns, so the vectors may die here
-  JPS_CHECK_CUDA(cudaMemsetAsync(plan->cnt, 0, (size_t)plan->acc_cap * 8, s));
-  JPS_CHECK_CUDA(cudaMemsetAsync(plan->ksum, 0, (size_t)plan->acc_cap * 8, s));
-  JPS_CHECK_CUDA(cudaMemsetAsync(plan->lastidx, 0, (size_t)plan->acc_cap * 8, s));
+  JPS_CHECK_CUDA(cudaMemsetAsync(T.cnt, 0, (size_t)plan->acc_cap * 8, s));
+  JPS_CHECK_CUDA(cudaMemsetAsync(T.ksum, 0, (size_t)plan->acc_cap * 8, s));
+  JPS_CHECK_CUDA(cudaMemsetAsync(T.lastidx, 0, (size_t)plan->acc_cap * 8, s));
   CountParams C;
-  C.n = plan->n; C.nz = plan->nz; C.lut = plan->lut; C.cnt = plan->cnt; C.ksum = plan->ksum;
-  C.lastidx = plan->lastidx; C.npairs = npairs_for(plan->n);
+  C.full_grid = (mode == TABLE_XI_EDGES || mode == TABLE_XI_FUNDAMENTAL) ? 1 : 0;
+  C.n = plan->n; C.nz = plan->nz; C.lut = T.lut; C.cnt = T.cnt; C.ksum = T.ksum;
+  C.lastidx = T.lastidx; C.npairs = npairs_for(plan->n);
   {
     ScopedLaunch L(K_PK_COUNT, s);
     pk_count_kernel<<<kNumSMs * 8, 256, 0, s>>>(C);
   }
   JPS_CHECK_LAUNCH();
-  T.key = key; T.nb = nb; T.nbc = nbc; T.valid = true;
+  T.key = key; T.mode = mode; T.nb = nb; T.nbc = nbc; T.valid = true; T.stamp = ++plan->stamp;
+  *out = &T;
   return JPS_OK;
 }
 
-static int run_fft_and_bin(jps_plan* plan, const float* mesh, int normalise, int mas_order,
-                           cudaStream_t s) {
+int forward_fft(jps_plan* plan, const float* mesh, cudaStream_t s) {
   JPS_CHECK_CUFFT(cufftSetStream(plan->r2c, s));
+  ScopedLaunch L(K_FFT_R2C, s);
+  JPS_CHECK_CUFFT(cufftExecR2C(plan->r2c, (cufftReal*)mesh, (cufftComplex*)plan->dk));
+  return JPS_OK;
+}
+
+// fold + bin plan->dk into plan->acc with table T
+static int bin_from_dk(jps_plan* plan, const BinTable& T, int normalise, int mas_order, cudaStream_t s) {
+  const int nbc = T.nbc;
   {
-    ScopedLaunch L(K_FFT_R2C, s);
-    JPS_CHECK_CUFFT(cufftExecR2C(plan->r2c, (cufftReal*)mesh, (cufftComplex*)plan->dk));
+    ScopedLaunch L(K_MEMSET, s);
+    JPS_CHECK_CUDA(cudaMemsetAsync(plan->acc, 0, (size_t)std::max(nbc, 1) * 4 * 8, s));
   }
-  const int nbc = plan->table.nbc;
-  JPS_CHECK_CUDA(cudaMemsetAsync(plan->acc, 0, (size_t)std::max(nbc, 1) * 4 * 8, s));
   if (nbc == 0) return JPS_OK;
   PkParams P;
-  P.dk = plan->dk; P.n = plan->n; P.nz = plan->nz; P.pitch = plan->pitch; P.lut = plan->lut;
+  P.dk = plan->dk; P.n = plan->n; P.nz = plan->nz; P.pitch = plan->pitch; P.lut = T.lut;
   P.wl = plan->wlut + (size_t)(mas_order - 2) * plan->n;
   P.nbc = nbc; P.acc = plan->acc; P.normalise = normalise; P.npairs = npairs_for(plan->n);
   const int threads = 256, warps = threads / 32;
@@ -403,12 +369,21 @@ static int run_fft_and_bin(jps_plan* plan, const float* mesh, int normalise, int
   return JPS_OK;
 }
 
-static double ref_volume(float box_size, int n) {
+double ref_volume(float box_size, int n) {
   const float t = box_size / (float)(n * n);    // (box_size/dims**2)**3 in float32, :50
   return (double)(t * t * t);
 }
 
-static float ref_kF(float box_size) { return (float)(2.0 * M_PI) / box_size; }   // :12
+float ref_kF(float box_size) { return (float)(2.0 * M_PI) / box_size; }   // :12
+
+int pk_from_dk(jps_plan* plan, float box_size, const float* k_edges, int nb, int normalise,
+               int mas_order, float shot_noise, float* k3d, float* pk3d, float* nmodes,
+               double* sums, int64_t* counts, cudaStream_t s);
+
+static void fill_finalize(FinalizeParams& F, jps_plan* plan, const BinTable& T) {
+  F.bin_to_compact = T.bin_to_compact; F.edges = T.edges; F.acc = plan->acc; F.cnt = T.cnt;
+  F.ksum = T.ksum; F.lastidx = T.lastidx; F.n = plan->n; F.nz = plan->nz;
+}
 
 }  // namespace jps
 
@@ -428,17 +403,28 @@ extern "C" int jps_powspec(jps_plan_t* plan, const float* mesh, int normalise, f
   JPS_REQUIRE(mas_order >= 2 && mas_order <= 4, "jps_powspec: mas_order must be 2, 3 or 4");
   JPS_REQUIRE(box_size > 0.0f, "jps_powspec: box_size must be > 0");
   cudaStream_t s = (cudaStream_t)stream;
+  int rc = forward_fft(plan, mesh, s);
+  if (rc) return rc;
+  return pk_from_dk(plan, box_size, k_edges, nb, normalise, mas_order, shot_noise, k3d, pk3d, nmodes,
+                    sums, counts, s);
+}
+
+namespace jps {
+// P(k) stage given plan->dk (forward FFT already done).
+int pk_from_dk(jps_plan* plan, float box_size, const float* k_edges, int nb, int normalise,
+               int mas_order, float shot_noise, float* k3d, float* pk3d, float* nmodes,
+               double* sums, int64_t* counts, cudaStream_t s) {
   const float kF = ref_kF(box_size);
   std::vector<float> kg((size_t)nb + 1);
   for (int i = 0; i <= nb; ++i) kg[(size_t)i] = k_edges[i] / kF;       // kedges = k_edges / kF, :42 (Q9)
-  int rc = ensure_bin_table(plan, kg.data(), nb, 0, s);
+  BinTable* T = nullptr;
+  int rc = ensure_bin_table(plan, kg.data(), nb, TABLE_PK_EDGES, s, &T);
   if (rc) return rc;
-  rc = run_fft_and_bin(plan, mesh, normalise, mas_order, s);
+  rc = bin_from_dk(plan, *T, normalise, mas_order, s);
   if (rc) return rc;
   FinalizeParams F;
-  F.nb = nb; F.first_bin = 0; F.bin_to_compact = plan->bin_to_compact; F.edges = plan->edges;
-  F.acc = plan->acc; F.cnt = plan->cnt; F.ksum = plan->ksum; F.lastidx = plan->lastidx;
-  F.n = plan->n; F.nz = plan->nz; F.kF = kF; F.vol = ref_volume(box_size, plan->n);
+  fill_finalize(F, plan, *T);
+  F.nb = nb; F.first_bin = 0; F.kF = kF; F.vol = ref_volume(box_size, plan->n);
   F.shot_noise = shot_noise; F.kmode = 0;
   F.k3d = k3d; F.pk3d = pk3d; F.nmodes = nmodes; F.sums = sums; F.counts = counts;
   {
@@ -448,6 +434,7 @@ extern "C" int jps_powspec(jps_plan_t* plan, const float* mesh, int normalise, f
   JPS_CHECK_LAUNCH();
   return JPS_OK;
 }
+}  // namespace jps
 
 extern "C" int jps_powspec_fundamental(jps_plan_t* plan, const float* mesh, int normalise,
                                        float box_size, int mas_order, int compat, float* k3d,
@@ -457,16 +444,19 @@ extern "C" int jps_powspec_fundamental(jps_plan_t* plan, const float* mesh, int 
   JPS_REQUIRE(mas_order >= 2 && mas_order <= 4, "jps_powspec_fundamental: mas_order must be 2, 3 or 4");
   JPS_REQUIRE(box_size > 0.0f, "jps_powspec_fundamental: box_size must be > 0");
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = ensure_bin_table(plan, nullptr, 0, 1, s);
+  BinTable* T = nullptr;
+  int rc = ensure_bin_table(plan, nullptr, 0, TABLE_PK_FUNDAMENTAL, s, &T);
   if (rc) return rc;
-  rc = run_fft_and_bin(plan, mesh, normalise, mas_order, s);
+  rc = forward_fft(plan, mesh, s);
+  if (rc) return rc;
+  rc = bin_from_dk(plan, *T, normalise, mas_order, s);
   if (rc) return rc;
   const int kmax = jps_fundamental_nbins(plan->n);
   if (kmax < 1) return JPS_OK;
   FinalizeParams F;
-  F.nb = kmax; F.first_bin = 1; F.bin_to_compact = plan->bin_to_compact; F.edges = nullptr;
-  F.acc = plan->acc; F.cnt = plan->cnt; F.ksum = plan->ksum; F.lastidx = plan->lastidx;
-  F.n = plan->n; F.nz = plan->nz; F.kF = ref_kF(box_size); F.vol = ref_volume(box_size, plan->n);
+  fill_finalize(F, plan, *T);
+  F.edges = nullptr;
+  F.nb = kmax; F.first_bin = 1; F.kF = ref_kF(box_size); F.vol = ref_volume(box_size, plan->n);
   F.shot_noise = 0.0f; F.kmode = (compat == JPS_COMPAT_REFERENCE) ? 1 : 2;
   F.k3d = k3d; F.pk3d = pk3d; F.nmodes = nmodes; F.sums = sums; F.counts = counts;
   {

@@ -141,5 +141,5 @@ def test_sorted_equals_atomic_large_mesh_properties(jps, order):
     b = jps.paint(zero, x, y, z, None, 0., 0., 0., box, n, True, order=order, compat="fixed", method="sorted")
     assert abs(b.sum(dtype=torch.float64).item() - npart) < 2e-6 * npart
     diff = (a - b).abs()
-    tol = 4e-6 * torch.maximum(a.abs(), torch.tensor(1.0, device="cuda")) + 1e-6
+    tol = 2e-5 * torch.maximum(a.abs(), torch.tensor(1.0, device="cuda")) + 1e-6      # two float32 summation orders
     assert bool((diff <= tol).all()), f"max diff {diff.max().item()}"
