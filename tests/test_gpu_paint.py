@@ -143,3 +143,24 @@ def test_sorted_equals_atomic_large_mesh_properties(jps, order):
     diff = (a - b).abs()
     tol = 2e-5 * torch.maximum(a.abs(), torch.tensor(1.0, device="cuda")) + 1e-6      # two float32 summation orders
     assert bool((diff <= tol).all()), f"max diff {diff.max().item()}"
+
+
+@pytest.mark.parametrize("order,compat", [(2, "reference"), (3, "fixed"), (4, "fixed")])
+@pytest.mark.parametrize("method", ["atomic", "sorted"])
+def test_float32_grid_position_is_not_fused(jps, order, compat, method):
+    """Regression: pos = (x-xmin)*inv must be rounded to float32 BEFORE the in-cell offset is
+    taken (the reference materialises it, Q4).  An FMA-contracted pos - floor(pos) shifts weights by
+    up to half an ulp of pos -- 1.5e-5 relative at grid coordinate ~250 -- so particles are placed
+    in the top planes of a 256^3 mesh where that is far above the 4e-6 tolerance."""
+    n, box, npart = 256, 2500.0, 400_000
+    rng = np.random.default_rng(123)
+    p = rng.random((npart, 3)).astype(F32)
+    p = (p * np.array([0.06, 1.0, 1.0], dtype=F32) + np.array([0.94, 0.0, 0.0], dtype=F32)) * F32(box)
+    p[p >= F32(box)] = 0.0
+    xmin = 0.0
+    want = om.paint(np.zeros((n, n, n)), p[:, 0], p[:, 1], p[:, 2], None, xmin, xmin, xmin, box, n, True,
+                    order=order, compat=compat, precision="f64")
+    got = jps.paint(np.zeros((n, n, n), F32), p[:, 0], p[:, 1], p[:, 2], None, xmin, xmin, xmin, box, n, True,
+                    order=order, compat=compat, method=method)
+    err = np.abs(got - want) / np.maximum(np.abs(want), 1.0)
+    assert err.max() < 2e-6, f"max error relative to max(|cell|,1): {err.max():.3e}"
