@@ -18,7 +18,7 @@ namespace jps {
 
 constexpr int TILE = 16;                 // cells per tile side
 constexpr int SCAN_THREADS = 1024;
-constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_ITEMS = 32;      // 32 K counters per iteration of the single scan CTA
 
 struct TileGeom {
   int n;        // mesh side
