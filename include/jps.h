@@ -80,9 +80,11 @@ extern "C" {
 #define JPS_PAINT_SORTED  2   /* bucket by mesh tile, deposit in shared memory, float4 flush */
 
 /* plan flags */
-#define JPS_PLAN_DEFAULT  0
+#define JPS_PLAN_DEFAULT      0
+#define JPS_PLAN_TABLES_ONLY  1   /* bin tables + accumulators only: no 3-D FFT plans, no delta_k buffer */
 
 typedef struct jps_plan jps_plan_t;
+typedef struct jps_slab_plan jps_slab_plan_t;
 
 JPS_API int         jps_version(void);
 JPS_API const char* jps_last_error(void);
@@ -126,6 +128,17 @@ JPS_API int jps_paint(int n_mesh,
               float xmin, float ymin, float zmin, float box_size,
               int order, int wrap, int compat, int variant, int method,
               float* mesh, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same deposit into an x-SLAB of the mesh: `mesh` is [nx_alloc, n, n] and its plane 0 holds global
+ * plane x0 (x0 may be negative: planes are taken mod n_mesh).  Stencil nodes whose plane is not in
+ * [x0, x0+nx_alloc) are dropped, so the caller sizes the slab with ghost planes and adds them to
+ * the neighbours (jax_powspec_b200/slab.py).  jps_paint is jps_paint_slab(x0=0, nx_alloc=n_mesh). */
+JPS_API int jps_paint_slab(int n_mesh, int x0, int nx_alloc,
+                   const float* x, const float* y, const float* z, const float* w,
+                   int64_t stride, int64_t n_part,
+                   float xmin, float ymin, float zmin, float box_size,
+                   int order, int wrap, int compat, int variant, int method,
+                   float* mesh, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ P(k) ------------- */
 /* Power-spectrum multipoles of a mesh in user bins.
@@ -194,6 +207,36 @@ JPS_API int jps_compute_all_correlations(jps_plan_t* plan, const float* mesh, in
                                  float* k3d, float* pk3d, float* nmodes_pk,
                                  float* r3d, float* xi3d, float* nmodes_xi,
                                  float* k_all, float* pk_shell, float* B, float* Q, void* stream);
+
+/* ------------------------------------------------------------------ slab-sharded mesh - */
+/* Per-rank compute stages of the distributed path (one process per GPU; rank r of nranks owns
+ * x-planes [r*n/nranks, (r+1)*n/nranks); n_mesh % nranks == 0).  The reference has no
+ * multi-device code: these have no reference counterpart; the host side that strings them
+ * together with the halo exchange, the all-to-all transpose and the allreduce of the bin sums is
+ * jax_powspec_b200/slab.py.  All buffers are caller-owned device memory:
+ *   slab      float32  [n/nranks][n][n]            owned planes of the painted mesh
+ *   yz        complex64 [n/nranks][n][n/2+1]       after jps_slab_fft_yz
+ *   packed    complex64 [nranks][n/nranks][n/nranks][n/2+1]   after jps_slab_pack (all-to-all send buffer)
+ *   dk        complex64 [n][n/nranks][n/2+1]       all-to-all receive buffer; jps_slab_fft_x in place;
+ *                                                  element (ix, yl, kz) is mode (kx(ix), ky(rank*n/nranks+yl), kz)
+ */
+JPS_API int jps_slab_plan_workspace_bytes(int n_mesh, int nranks, size_t* bytes);
+JPS_API int jps_slab_plan_create(int n_mesh, int nranks, int rank, void* workspace, size_t workspace_bytes,
+                         jps_slab_plan_t** plan);
+JPS_API int jps_slab_plan_destroy(jps_slab_plan_t* plan);
+JPS_API int jps_slab_fft_yz(jps_slab_plan_t* plan, const float* slab, void* yz, void* stream);
+JPS_API int jps_slab_pack(jps_slab_plan_t* plan, const void* yz, void* packed, void* stream);
+JPS_API int jps_slab_fft_x(jps_slab_plan_t* plan, void* dk, void* stream);
+/* This rank's partial sums of |delta_k|^2 L_l per user bin (sums[nb*3], float64, overwritten) and the
+ * GLOBAL exact mode counts (counts[nb], identical on every rank; may be NULL).  dc: device pointer to
+ * Re rho_hat(k=0) (lives on rank 0; broadcast it), used when normalise != 0. */
+JPS_API int jps_slab_powspec_partial(jps_slab_plan_t* plan, const void* dk, const float* dc, int normalise,
+                             float box_size, const float* k_edges, int nb, int mas_order,
+                             double* sums, int64_t* counts, void* stream);
+/* After the allreduce of sums: the reference's output arrays (src/correlations.py:49-54). */
+JPS_API int jps_slab_powspec_finalize(jps_slab_plan_t* plan, float box_size, const float* k_edges, int nb,
+                              const double* sums, const int64_t* counts, float shot_noise,
+                              float* k3d, float* pk3d, float* nmodes, void* stream);
 
 /* ------------------------------------------------------------------ fused ------------ */
 /* paint (into the plan-owned mesh, zeroed first) -> R2C FFT -> multipoles; the call the

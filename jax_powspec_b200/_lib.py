@@ -50,6 +50,8 @@ SIGNATURES = {
     "jps_paint_workspace_bytes": (_i, [_i, _i64, _i, _i, C.POINTER(_sz)]),
     "jps_paint": (_i, [_i, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _f, _f, _i, _i, _i, _i, _i,
                        _vp, _vp, _sz, _vp]),
+    "jps_paint_slab": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _f, _f, _i, _i, _i, _i, _i,
+                            _vp, _vp, _sz, _vp]),
     "jps_powspec": (_i, [_vp, _vp, _i, _f, _fp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "jps_fundamental_nbins": (_i, [_i]),
     "jps_powspec_fundamental": (_i, [_vp, _vp, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -60,6 +62,14 @@ SIGNATURES = {
                                           _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "jps_compute_all_correlations": (_i, [_vp, _vp, _i, _f, _fp, _i, _fp, _i, _f, _f, _fp, _i, _i,
                                           _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "jps_slab_plan_workspace_bytes": (_i, [_i, _i, C.POINTER(_sz)]),
+    "jps_slab_plan_create": (_i, [_i, _i, _i, _vp, _sz, C.POINTER(_vp)]),
+    "jps_slab_plan_destroy": (_i, [_vp]),
+    "jps_slab_fft_yz": (_i, [_vp, _vp, _vp, _vp]),
+    "jps_slab_pack": (_i, [_vp, _vp, _vp, _vp]),
+    "jps_slab_fft_x": (_i, [_vp, _vp, _vp]),
+    "jps_slab_powspec_partial": (_i, [_vp, _vp, _vp, _i, _f, _fp, _i, _i, _vp, _vp, _vp]),
+    "jps_slab_powspec_finalize": (_i, [_vp, _f, _fp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
     "jps_paint_powspec": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _f, _f, _i, _i, _i, _i,
                                _fp, _i, _f, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

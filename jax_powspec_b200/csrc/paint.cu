@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(256) paint_atomic_kernel(PaintParams p) {
       cic_reference_axis(py, n, p.wrap, p.variant, y0, y1, mdy, ddy);
       cic_reference_axis(pz, n, p.wrap, p.variant, z0, z1, mdz, ddz);
       // the 8 scatters of src/mas.py:142-151, weights multiplied left to right
+      x0 = local_plane(x0, p.x0, p.nx, n);
+      x1 = local_plane(x1, p.x0, p.nx, n);
 #define JPS_CORNER(ix, iy, iz, wx, wy, wz)                                          \
   if (((ix) | (iy) | (iz)) >= 0)                                                     \
     red_add(p.mesh + (size_t)(ix) * n2 + (size_t)(iy) * n + (iz), (((wx) * (wy)) * (wz)) * wgt);
@@ -48,10 +50,11 @@ __global__ void __launch_bounds__(256) paint_atomic_kernel(PaintParams p) {
       bspline_axis<ORDER>(pz, n, p.wrap, iz, wz);
 #pragma unroll
       for (int a = 0; a < ORDER; ++a) {
+        const int lx = local_plane(ix[a], p.x0, p.nx, n);
 #pragma unroll
         for (int b = 0; b < ORDER; ++b) {
-          if ((ix[a] | iy[b]) < 0) continue;
-          float* row = p.mesh + (size_t)ix[a] * n2 + (size_t)iy[b] * n;
+          if ((lx | iy[b]) < 0) continue;
+          float* row = p.mesh + (size_t)lx * n2 + (size_t)iy[b] * n;
           const float wxy = wx[a] * wy[b];
 #pragma unroll
           for (int c = 0; c < ORDER; ++c) {
@@ -105,6 +108,16 @@ extern "C" int jps_paint(int n_mesh, const float* x, const float* y, const float
                          float zmin, float box_size, int order, int wrap, int compat, int variant,
                          int method, float* mesh, void* workspace, size_t workspace_bytes,
                          void* stream) {
+  return jps_paint_slab(n_mesh, 0, n_mesh, x, y, z, w, stride, n_part, xmin, ymin, zmin, box_size, order,
+                        wrap, compat, variant, method, mesh, workspace, workspace_bytes, stream);
+}
+
+extern "C" int jps_paint_slab(int n_mesh, int x0, int nx_alloc, const float* x, const float* y,
+                              const float* z, const float* w, int64_t stride, int64_t n_part,
+                              float xmin, float ymin, float zmin, float box_size, int order, int wrap,
+                              int compat, int variant, int method, float* mesh, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  JPS_REQUIRE(nx_alloc >= 1 && nx_alloc <= n_mesh, "jps_paint_slab: nx_alloc=%d out of range [1,%d]", nx_alloc, n_mesh);
   JPS_REQUIRE(n_mesh >= 2 && n_mesh <= 4096, "jps_paint: n_mesh=%d out of range [2,4096]", n_mesh);
   JPS_REQUIRE(n_part >= 0, "jps_paint: n_part < 0");
   JPS_REQUIRE(order >= 2 && order <= 4, "jps_paint: order must be 2 (CIC), 3 (TSC) or 4 (PCS)");
@@ -116,6 +129,8 @@ extern "C" int jps_paint(int n_mesh, const float* x, const float* y, const float
   JPS_REQUIRE(box_size > 0.0f, "jps_paint: box_size must be > 0");
   PaintParams p;
   p.n = n_mesh;
+  p.x0 = x0;
+  p.nx = nx_alloc;
   p.wrap = wrap ? 1 : 0;
   p.variant = variant;
   p.xmin = xmin; p.ymin = ymin; p.zmin = zmin;
@@ -128,10 +143,10 @@ extern "C" int jps_paint(int n_mesh, const float* x, const float* y, const float
   cudaStream_t s = (cudaStream_t)stream;
   if (method == JPS_PAINT_AUTO) {
     // small meshes stay L2-resident: global reds are already local; few particles: not worth sorting
-    const size_t mesh_bytes = (size_t)n_mesh * n_mesh * n_mesh * 4;
+    const size_t mesh_bytes = (size_t)nx_alloc * n_mesh * n_mesh * 4;
     method = (mesh_bytes <= (size_t)48 << 20 || n_part < (int64_t)1 << 18) ? JPS_PAINT_ATOMIC
                                                                           : JPS_PAINT_SORTED;
-    if (method == JPS_PAINT_SORTED && workspace_bytes < paint_sorted_workspace(n_mesh, n_part, order))
+    if (method == JPS_PAINT_SORTED && workspace_bytes < paint_sorted_workspace(n_mesh, n_part, order))  // sized for a full mesh: always enough
       method = JPS_PAINT_ATOMIC;                       // caller gave no room: still correct
   }
   if (method == JPS_PAINT_ATOMIC) return launch_atomic(p, order, compat, s);

@@ -10,7 +10,9 @@
 namespace jps {
 
 struct PaintParams {
-  int n;
+  int n;                   // global mesh side
+  int x0;                  // global x-plane stored at local plane 0 (0 for a full mesh; may be < 0)
+  int nx;                  // allocated x-planes of `mesh` (n for a full mesh; slab + ghosts otherwise)
   int wrap;
   int variant;
   float xmin, ymin, zmin;
@@ -37,6 +39,15 @@ __device__ __forceinline__ int pymod(int a, int n) {
   int r = a % n;
   return r < 0 ? r + n : r;
 }
+
+// Global (already wrapped / validated, or -1) x-plane -> local plane of a [nx][n][n] slab mesh
+// that starts at global plane x0; -1 if the plane is not held locally.  Identity for a full mesh.
+__device__ __forceinline__ int local_plane(int gx, int x0, int nx, int n) {
+  if (gx < 0) return -1;
+  const int l = pymod(gx - x0, n);
+  return l < nx ? l : -1;
+}
+
 
 // JAX .at[] scatter index: negatives wrap once, what is still out of range is dropped (-1).
 __device__ __forceinline__ int scatter_norm(int i, int n) {

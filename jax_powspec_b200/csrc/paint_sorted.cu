@@ -21,9 +21,11 @@ constexpr int SCAN_THREADS = 1024;
 constexpr int SCAN_ITEMS = 32;      // 32 K counters per iteration of the single scan CTA
 
 struct TileGeom {
-  int n;        // mesh side
-  int nt;       // tiles per axis = ceil(n / TILE)
-  int ntiles;   // nt^3
+  int n;        // global mesh side
+  int x0, nx;   // local slab: global plane of local plane 0, allocated planes (0, n for a full mesh)
+  int nt;       // tiles per y / z axis = ceil(n / TILE)
+  int ntx;      // tiles along x = ceil(nx / TILE)
+  int ntiles;   // ntx * nt * nt
   int rep;      // counter replicas per tile (power of two): bucket = tile*rep + (block & (rep-1)).
                 // Same-address global atomics serialise in L2; with ~3000 particles per tile and
                 // ~3e5 threads in flight the single-counter version ran at half the red rate of
@@ -51,7 +53,7 @@ __device__ __forceinline__ int anchor_axis(float pos, int n) {
 // the same particle -> block mapping, so a particle sees the same replica in both)
 template <int ORDER, bool REFCIC>
 __device__ __forceinline__ int tile_of(float px, float py, float pz, const TileGeom& g, unsigned block) {
-  const int ax = anchor_axis<ORDER, REFCIC>(px, g.n);
+  const int ax = local_plane(anchor_axis<ORDER, REFCIC>(px, g.n), g.x0, g.nx, g.n);   // not held here -> dropped
   const int ay = anchor_axis<ORDER, REFCIC>(py, g.n);
   const int az = anchor_axis<ORDER, REFCIC>(pz, g.n);
   if ((ax | ay | az) < 0) return g.ntiles * g.rep;
@@ -179,13 +181,12 @@ __device__ __forceinline__ void red_v4(float* addr, float a, float b, float c, f
                : "memory");
 }
 
-// Per-axis local node offset (0..TILE-1 for the lowest node) and weights inside the tile.
+// Per-axis anchor (lowest node, wrapped global index) and weights.
 template <int ORDER>
-__device__ __forceinline__ void tile_axis(float pos, int n, int wrap, int origin, int& l0,
-                                          float (&w)[ORDER]) {
+__device__ __forceinline__ void tile_axis(float pos, int n, int wrap, int& anchor, float (&w)[ORDER]) {
   int idx[ORDER];
   bspline_axis<ORDER>(pos, n, 1, idx, w);        // wrapped indices; idx[0] is the anchor
-  l0 = idx[0] - origin;
+  anchor = idx[0];
   if (!wrap) {                                   // non-periodic: drop nodes outside the mesh
     int base;
     if (ORDER == 2) base = (int)floorf(pos);
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(256) paint_tile_kernel(const float4* __restric
   const unsigned beg = offsets[t * g.rep], end = offsets[(t + 1) * g.rep];
   if (beg == end) return;                        // empty tile: nothing to flush
   const int tz = t % g.nt, ty = (t / g.nt) % g.nt, tx = t / (g.nt * g.nt);
-  const int ox = tx * TILE, oy = ty * TILE, oz = tz * TILE;
+  const int ox = tx * TILE, oy = ty * TILE, oz = tz * TILE;     // ox is a LOCAL plane index
   const int n = g.n;
   for (int i = threadIdx.x; i < L * L * LP; i += blockDim.x) tile[i] = 0.0f;
   __syncthreads();
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(256) paint_tile_kernel(const float4* __restric
       cic_reference_axis(r.y, n, wrap, variant, y0, y1, mdy, ddy);
       cic_reference_axis(r.z, n, wrap, variant, z0, z1, mdz, ddz);
       // in-box particles: x1 == (x0+1) mod n for every variant, i.e. local index +1
-      float* c = tile + ((x0 - ox) * L + (y0 - oy)) * LP + (z0 - oz);
+      float* c = tile + ((local_plane(x0, g.x0, g.nx, n) - ox) * L + (y0 - oy)) * LP + (z0 - oz);
       const float wgt = r.w;
       constexpr int SX = L * LP, SY = LP;
       atomicAdd(c, ((mdx * mdy) * mdz) * wgt);
@@ -235,12 +236,12 @@ __global__ void __launch_bounds__(256) paint_tile_kernel(const float4* __restric
       atomicAdd(c + SY + 1, ((mdx * mdy) * ddz) * wgt);       // Q1 (reference weight)
       atomicAdd(c + SX + SY + 1, ((ddx * ddy) * ddz) * wgt);
     } else {
-      int lx, ly, lz;
+      int ax, ay, az;
       float wx[ORDER], wy[ORDER], wz[ORDER];
-      tile_axis<ORDER>(r.x, n, wrap, ox, lx, wx);
-      tile_axis<ORDER>(r.y, n, wrap, oy, ly, wy);
-      tile_axis<ORDER>(r.z, n, wrap, oz, lz, wz);
-      float* c = tile + (lx * L + ly) * LP + lz;
+      tile_axis<ORDER>(r.x, n, wrap, ax, wx);
+      tile_axis<ORDER>(r.y, n, wrap, ay, wy);
+      tile_axis<ORDER>(r.z, n, wrap, az, wz);
+      float* c = tile + ((local_plane(ax, g.x0, g.nx, n) - ox) * L + (ay - oy)) * LP + (az - oz);
 #pragma unroll
       for (int a = 0; a < ORDER; ++a) {
 #pragma unroll
@@ -265,7 +266,10 @@ __global__ void __launch_bounds__(256) paint_tile_kernel(const float4* __restric
     const int q = item % ROW_ITEMS;
     const int row = item / ROW_ITEMS;
     const int j = row % L, i = row / L;
-    const int gx = (ox + i) % n, gy = (oy + j) % n;
+    int gx = ox + i;                               // local plane
+    if (g.nx == n) gx %= n;                        // full mesh: periodic in x
+    else if (gx >= g.nx) continue;                 // slab: ghost planes are part of the allocation
+    const int gy = (oy + j) % n;
     float* grow = mesh + (size_t)gx * n2 + (size_t)gy * n;
     const float* trow = tile + (i * L + j) * LP;
     if (q < NV) {
@@ -293,8 +297,8 @@ __global__ void __launch_bounds__(256) paint_tile_kernel(const float4* __restric
 // painted with the general per-particle path straight from the bucketed records.
 __global__ void __launch_bounds__(256) paint_outliers_kernel(const float4* __restrict__ sorted,
                                                              const unsigned* __restrict__ offsets,
-                                                             int bucket, int n, int wrap, int variant,
-                                                             float* __restrict__ mesh) {
+                                                             int bucket, int n, int gx0, int nx, int wrap,
+                                                             int variant, float* __restrict__ mesh) {
   const unsigned beg = offsets[bucket], end = offsets[bucket + 1];
   const size_t n2 = (size_t)n * n;
   for (unsigned i = beg + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
@@ -304,6 +308,8 @@ __global__ void __launch_bounds__(256) paint_outliers_kernel(const float4* __res
     cic_reference_axis(r.x, n, wrap, variant, x0, x1, mdx, ddx);
     cic_reference_axis(r.y, n, wrap, variant, y0, y1, mdy, ddy);
     cic_reference_axis(r.z, n, wrap, variant, z0, z1, mdz, ddz);
+    x0 = local_plane(x0, gx0, nx, n);
+    x1 = local_plane(x1, gx0, nx, n);
 #define JPS_CORNER(ix, iy, iz, wx, wy, wz)                                           \
   if (((ix) | (iy) | (iz)) >= 0)                                                      \
     atomicAdd(mesh + (size_t)(ix) * n2 + (size_t)(iy) * n + (iz), (((wx) * (wy)) * (wz)) * r.w);
@@ -331,10 +337,10 @@ static int replicas_for(int ntiles) {
   return rep;
 }
 
-static SortedLayout sorted_layout(int n, int64_t n_part) {
+static SortedLayout sorted_layout(int n, int nx, int64_t n_part) {
   SortedLayout L;
-  const int nt = (n + TILE - 1) / TILE;
-  L.nbuckets = nt * nt * nt * replicas_for(nt * nt * nt) + 1;
+  const int nt = (n + TILE - 1) / TILE, ntx = (nx + TILE - 1) / TILE;
+  L.nbuckets = ntx * nt * nt * replicas_for(ntx * nt * nt) + 1;
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = off; off = align_up(off + b, 256); return o; };
   L.sorted = take((size_t)(n_part > 0 ? n_part : 1) * sizeof(float4));
@@ -347,7 +353,7 @@ static SortedLayout sorted_layout(int n, int64_t n_part) {
 
 size_t paint_sorted_workspace(int n, int64_t n_part, int order) {
   (void)order;
-  return sorted_layout(n, n_part).total;
+  return sorted_layout(n, n, n_part).total + 4096;   // a full mesh bounds every slab of it
 }
 
 template <int ORDER, bool REFCIC>
@@ -388,7 +394,8 @@ static int run_sorted(const PaintParams& p, const TileGeom& g, const SortedLayou
   JPS_CHECK_LAUNCH();
   if (REFCIC) {
     ScopedLaunch T(K_PAINT_ATOMIC, s);
-    paint_outliers_kernel<<<kNumSMs, 256, 0, s>>>(sorted, offsets, g.ntiles * g.rep, g.n, p.wrap, p.variant, p.mesh);
+    paint_outliers_kernel<<<kNumSMs, 256, 0, s>>>(sorted, offsets, g.ntiles * g.rep, g.n, g.x0, g.nx, p.wrap,
+                                                  p.variant, p.mesh);
     JPS_CHECK_LAUNCH();
   }
   return JPS_OK;
@@ -398,7 +405,7 @@ int paint_sorted(const PaintParams& p, int order, int compat, void* ws, size_t w
                  cudaStream_t s) {
   if (p.n_part == 0) return JPS_OK;
   JPS_REQUIRE(p.n_part < ((int64_t)1 << 32) - 1, "jps_paint: the sorted painter takes < 2^32 particles per call");
-  const SortedLayout L = sorted_layout(p.n, p.n_part);
+  const SortedLayout L = sorted_layout(p.n, p.nx, p.n_part);
   if (ws == nullptr || ws_bytes < L.total) {
     set_error("jps_paint: workspace has %zu bytes, %zu needed (jps_paint_workspace_bytes)", ws_bytes, L.total);
     return JPS_ERR_WORKSPACE;
@@ -406,8 +413,11 @@ int paint_sorted(const PaintParams& p, int order, int compat, void* ws, size_t w
   JPS_REQUIRE(((uintptr_t)ws & 15) == 0, "jps_paint: workspace must be 16-byte aligned");
   TileGeom g;
   g.n = p.n;
+  g.x0 = p.x0;
+  g.nx = p.nx;
   g.nt = (p.n + TILE - 1) / TILE;
-  g.ntiles = g.nt * g.nt * g.nt;
+  g.ntx = (p.nx + TILE - 1) / TILE;
+  g.ntiles = g.ntx * g.nt * g.nt;
   g.rep = replicas_for(g.ntiles);
   char* w = (char*)ws;
   if (order == 2 && compat == JPS_COMPAT_REFERENCE) return run_sorted<2, true>(p, g, L, w, s);

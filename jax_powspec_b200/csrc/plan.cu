@@ -87,14 +87,14 @@ struct Layout {
   int cap;
 };
 
-static Layout make_layout(int n, int pitch, size_t fft_work_bytes, int n_shell_fields) {
+static Layout make_layout(int n, int pitch, size_t fft_work_bytes, int n_shell_fields, bool tables_only = false) {
   Layout L;
   const int mid = n / 2;
   const int64_t k2max = 3LL * mid * mid;
   L.cap = (int)std::min<int64_t>(k2max + 2, 262144);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-  L.dk = take((size_t)n * n * pitch * sizeof(float2));
+  L.dk = take(tables_only ? 0 : (size_t)n * n * pitch * sizeof(float2));
   L.fft_work = take(fft_work_bytes);
   for (int i = 0; i < kNumTables; ++i) {
     L.t[i].lut = take((size_t)(k2max + 1) * 4);
@@ -168,11 +168,14 @@ extern "C" int jps_version(void) { return JPS_VERSION; }
 extern "C" const char* jps_last_error(void) { return g_err; }
 
 extern "C" int jps_plan_workspace_bytes(int n_mesh, int n_shell_fields, int flags, size_t* bytes) {
-  (void)flags;
   JPS_REQUIRE(bytes != nullptr, "jps_plan_workspace_bytes: bytes is NULL");
   JPS_REQUIRE(n_mesh >= 2 && n_mesh <= 4096, "jps_plan_workspace_bytes: n_mesh=%d out of range [2,4096]", n_mesh);
   JPS_REQUIRE(n_shell_fields >= 0, "jps_plan_workspace_bytes: n_shell_fields < 0");
   const int pitch = pitch_for(n_mesh);
+  if (flags & JPS_PLAN_TABLES_ONLY) {
+    *bytes = make_layout(n_mesh, pitch, 0, 0, true).total;
+    return JPS_OK;
+  }
   cufftHandle h;
   size_t w1 = 0, w2 = 0;
   int rc = make_r2c(n_mesh, pitch, &h, &w1);
@@ -187,7 +190,7 @@ extern "C" int jps_plan_workspace_bytes(int n_mesh, int n_shell_fields, int flag
 
 extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* workspace,
                                size_t workspace_bytes, jps_plan_t** out) {
-  (void)flags;
+  const bool tables_only = (flags & JPS_PLAN_TABLES_ONLY) != 0;
   JPS_REQUIRE(out != nullptr, "jps_plan_create: plan is NULL");
   *out = nullptr;
   JPS_REQUIRE(n_mesh >= 2 && n_mesh <= 4096, "jps_plan_create: n_mesh=%d out of range [2,4096]", n_mesh);
@@ -202,13 +205,16 @@ extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* 
   cudaError_t ce = cudaGetDevice(&p->device);
   if (ce != cudaSuccess) { delete p; set_error("jps_plan_create: cudaGetDevice failed: %s", cudaGetErrorString(ce)); return JPS_ERR_CUDA; }
   size_t w1 = 0, w2 = 0;
-  int rc = make_r2c(n_mesh, p->pitch, &p->r2c, &w1);
-  if (rc) { delete p; return rc; }
-  p->r2c_ok = true;
-  rc = make_c2r_inplace(n_mesh, p->pitch, &p->c2r, &w2);
-  if (rc) { cufftDestroy(p->r2c); delete p; return rc; }
-  p->c2r_ok = true;
-  Layout L = make_layout(n_mesh, p->pitch, std::max(w1, w2), n_shell_fields);
+  int rc = JPS_OK;
+  if (!tables_only) {
+    rc = make_r2c(n_mesh, p->pitch, &p->r2c, &w1);
+    if (rc) { delete p; return rc; }
+    p->r2c_ok = true;
+    rc = make_c2r_inplace(n_mesh, p->pitch, &p->c2r, &w2);
+    if (rc) { cufftDestroy(p->r2c); delete p; return rc; }
+    p->c2r_ok = true;
+  }
+  Layout L = make_layout(n_mesh, p->pitch, std::max(w1, w2), n_shell_fields, tables_only);
   if (workspace_bytes < L.total) {
     set_error("jps_plan_create: workspace has %zu bytes, %zu needed", workspace_bytes, L.total);
     jps_plan_destroy(p);
@@ -235,8 +241,11 @@ extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* 
   p->scal = (double*)(ws + L.scal);
   p->shell = (float*)(ws + L.shell);
   p->acc_cap = L.cap;
-  cufftResult r = cufftSetWorkArea(p->r2c, p->fft_work);
-  if (r == CUFFT_SUCCESS) r = cufftSetWorkArea(p->c2r, p->fft_work);
+  cufftResult r = CUFFT_SUCCESS;
+  if (!tables_only) {
+    r = cufftSetWorkArea(p->r2c, p->fft_work);
+    if (r == CUFFT_SUCCESS) r = cufftSetWorkArea(p->c2r, p->fft_work);
+  }
   if (r != CUFFT_SUCCESS) {
     set_error("jps_plan_create: cufftSetWorkArea failed (%d)", (int)r);
     jps_plan_destroy(p);

@@ -325,6 +325,10 @@ int ensure_bin_table(jps_plan* plan, const float* kedges_grid, int nb, int mode,
 }
 
 int forward_fft(jps_plan* plan, const float* mesh, cudaStream_t s) {
+  if (!plan->r2c_ok) {
+    set_error("this plan was created with JPS_PLAN_TABLES_ONLY: it has no 3-D FFT");
+    return JPS_ERR_UNSUPPORTED;
+  }
   JPS_CHECK_CUFFT(cufftSetStream(plan->r2c, s));
   ScopedLaunch L(K_FFT_R2C, s);
   JPS_CHECK_CUFFT(cufftExecR2C(plan->r2c, (cufftReal*)mesh, (cufftComplex*)plan->dk));

@@ -1,0 +1,347 @@
+// Slab-sharded mesh: the per-rank compute stages of the distributed paint -> FFT -> P(k) path
+// (the reference has no multi-device code).
+//
+// Decomposition: rank r of P owns x-planes [r*N/P, (r+1)*N/P).  The forward transform is
+//   (1) jps_slab_fft_yz : batched 2-D R2C over (y,z) of the owned planes   [nxl][N][N] -> [nxl][N][nz]
+//   (2) jps_slab_pack   : regroup by destination rank                       -> [P][nxl][nyl][nz]
+//       + ONE all-to-all of (P-1)/P^2 * 8 N^2 nz bytes per rank (host side: torch.distributed / NCCL)
+//   (3) jps_slab_fft_x  : strided batched 1-D C2C along x, in place          [N][nyl][nz]
+// and the spectrum stays y-sharded: the binning kernel only needs each element's (kx,ky,kz).
+//   (4) jps_slab_powspec_partial : fold +-kx, window, Legendre weights, k-bin sums of the local shard
+//       + allreduce of nb*3 float64 (host side), then jps_slab_powspec_finalize.
+// Exact mode counts are geometry only and are computed identically on every rank.
+#include "common.cuh"
+#include "fold.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+struct jps_slab_plan {
+  int n = 0, nz = 0, nranks = 1, rank = 0, nxl = 0, nyl = 0;
+  cufftHandle fft_yz = 0, fft_x = 0;
+  bool yz_ok = false, x_ok = false;
+  void* work = nullptr;
+  size_t work_bytes = 0;
+  jps_plan* tables = nullptr;     // bin tables + accumulators (no 3-D FFT inside)
+};
+
+namespace jps {
+
+static int make_fft_yz(int n, int nxl, cufftHandle* h, size_t* work) {
+  JPS_CHECK_CUFFT(cufftCreate(h));
+  JPS_CHECK_CUFFT(cufftSetAutoAllocation(*h, 0));
+  const int nz = n / 2 + 1;
+  long long dims[2] = {n, n};
+  long long inembed[2] = {n, n};
+  long long onembed[2] = {n, nz};
+  JPS_CHECK_CUFFT(cufftMakePlanMany64(*h, 2, dims, inembed, 1, (long long)n * n, onembed, 1,
+                                      (long long)n * nz, CUFFT_R2C, nxl, work));
+  return JPS_OK;
+}
+
+static int make_fft_x(int n, int nyl, cufftHandle* h, size_t* work) {
+  JPS_CHECK_CUFFT(cufftCreate(h));
+  JPS_CHECK_CUFFT(cufftSetAutoAllocation(*h, 0));
+  const int nz = n / 2 + 1;
+  long long dims[1] = {n};
+  long long embed[1] = {n};
+  const long long stride = (long long)nyl * nz;      // distance between consecutive x
+  JPS_CHECK_CUFFT(cufftMakePlanMany64(*h, 1, dims, embed, stride, 1, embed, stride, 1, CUFFT_C2C,
+                                      stride, work));
+  return JPS_OK;
+}
+
+struct SlabPkParams {
+  const float2* dk;      // [n][nyl][nz]
+  int n, nz, nyl, y0;
+  const int32_t* lut;
+  const float* wl;
+  int nbc;
+  double* acc;           // [nbc][4]
+  const float* dc;       // device: Re rho_hat(k=0) (used when normalise)
+  int normalise;
+};
+
+// One warp per (a = |kx|, local y): folds the rows ix = a and ix = n-a, lanes along kz.
+template <bool SMEM>
+__global__ void __launch_bounds__(256) pk_bin_ysharded_kernel(SlabPkParams P) {
+  extern __shared__ float sacc[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int nacc = P.nbc * 3;
+  float* my = sacc + (size_t)warp * nacc;
+  if (SMEM) {
+    for (int i = lane; i < nacc; i += 32) my[i] = 0.0f;
+    __syncwarp();
+  }
+  float scale2 = 1.0f;
+  if (P.normalise) {
+    const double s = (double)P.n * (double)P.n * (double)P.n / (double)P.dc[0];
+    scale2 = (float)(s * s);
+  }
+  const int n = P.n, nz = P.nz, mid = n / 2;
+  const long long items = (long long)(mid + 1) * P.nyl;
+  for (long long it = (long long)blockIdx.x * nwarps + warp; it < items; it += (long long)gridDim.x * nwarps) {
+    const int a = (int)(it / P.nyl), yl = (int)(it % P.nyl);
+    const int iy = P.y0 + yl;
+    const int ky = iy > mid ? iy - n : iy;
+    const bool two = (a > 0 && 2 * a != n);
+    const float2* r0 = P.dk + ((size_t)a * P.nyl + yl) * nz;
+    const float2* r1 = P.dk + ((size_t)(two ? n - a : a) * P.nyl + yl) * nz;
+    const float wab = P.wl[a] * P.wl[iy];
+    const int k2ab = a * a + ky * ky;
+    for (int kz0 = 0; kz0 < nz; kz0 += 32) {
+      const int kz = kz0 + lane;
+      float v[3] = {0.0f, 0.0f, 0.0f};
+      int cb = -2;
+      if (kz < nz) {
+        const float2 d0 = __ldg(r0 + kz);
+        const float2 d1 = two ? __ldg(r1 + kz) : make_float2(0.0f, 0.0f);
+        const int k2 = k2ab + kz * kz;
+        cb = __ldg(P.lut + k2);
+        const float c = wab * P.wl[kz];
+        float re = d0.x * c, im = d0.y * c;
+        float sum = re * re + im * im;
+        re = d1.x * c; im = d1.y * c;
+        sum += re * re + im * im;
+        sum *= scale2;
+        float mu2 = 0.0f;
+        if (k2 > 0) mu2 = (float)(kz * kz) / (float)k2;
+        else if (P.normalise) sum = 0.0f;
+        v[0] = sum;
+        v[1] = sum * (3.0f * mu2 - 1.0f) * 0.5f;
+        v[2] = sum * (35.0f * mu2 * mu2 - 30.0f * mu2 + 3.0f) * 0.125f;
+      }
+      const int prev = __shfl_up_sync(0xffffffffu, cb, 1);
+      const bool head = (lane == 0) || (cb != prev);
+      const unsigned heads = __ballot_sync(0xffffffffu, head);
+      segmented_reduce<3>(v, heads, lane);
+      if (head && cb >= 0) {
+        if (SMEM) {
+          float* q = my + cb * 3;
+          q[0] += v[0]; q[1] += v[1]; q[2] += v[2];
+        } else {
+          double* q = P.acc + (size_t)cb * 4;
+          atomicAdd(q + 0, (double)v[0]); atomicAdd(q + 1, (double)v[1]); atomicAdd(q + 2, (double)v[2]);
+        }
+      }
+      if (SMEM) __syncwarp();
+    }
+  }
+  if (SMEM) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
+      double s = 0.0;
+      for (int w = 0; w < nwarps; ++w) s += (double)sacc[(size_t)w * nacc + i];
+      if (s != 0.0) atomicAdd(P.acc + (size_t)(i / 3) * 4 + (i % 3), s);
+    }
+  }
+}
+
+// compact accumulators -> user-bin arrays
+__global__ void slab_expand_kernel(int nb, const int32_t* __restrict__ bin_to_compact,
+                                   const double* __restrict__ acc,
+                                   const unsigned long long* __restrict__ cnt,
+                                   double* __restrict__ sums, int64_t* __restrict__ counts) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nb) return;
+  const int c = bin_to_compact[j];
+  sums[j * 3 + 0] = c >= 0 ? acc[(size_t)c * 4 + 0] : 0.0;
+  sums[j * 3 + 1] = c >= 0 ? acc[(size_t)c * 4 + 1] : 0.0;
+  sums[j * 3 + 2] = c >= 0 ? acc[(size_t)c * 4 + 2] : 0.0;
+  if (counts) counts[j] = c >= 0 ? (int64_t)cnt[c] : 0;
+}
+
+__global__ void slab_finalize_kernel(int nb, const float* __restrict__ edges, const double* __restrict__ sums,
+                                     const int64_t* __restrict__ counts, float kF, double vol, float shot,
+                                     float* __restrict__ k3d, float* __restrict__ pk3d, float* __restrict__ nmodes) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nb) return;
+  const double nm = (double)(float)counts[j];
+  pk3d[j * 3 + 0] = (float)(sums[j * 3 + 0] / nm * vol - (double)shot);
+  pk3d[j * 3 + 1] = (float)(sums[j * 3 + 1] / nm * 5.0 * vol);
+  pk3d[j * 3 + 2] = (float)(sums[j * 3 + 2] / nm * 9.0 * vol);
+  nmodes[j] = (float)counts[j];
+  k3d[j] = (0.5f * (edges[j + 1] + edges[j])) * kF;
+}
+
+static size_t tables_bytes(int n) {
+  size_t b = 0;
+  return jps_plan_workspace_bytes(n, 0, JPS_PLAN_TABLES_ONLY, &b) == JPS_OK ? b : 0;
+}
+
+}  // namespace jps
+
+using namespace jps;
+
+extern "C" int jps_slab_plan_workspace_bytes(int n_mesh, int nranks, size_t* bytes) {
+  JPS_REQUIRE(bytes != nullptr, "jps_slab_plan_workspace_bytes: bytes is NULL");
+  JPS_REQUIRE(n_mesh >= 2 && n_mesh <= 4096, "jps_slab_plan_workspace_bytes: n_mesh out of range");
+  JPS_REQUIRE(nranks >= 1 && n_mesh % nranks == 0, "jps_slab_plan_workspace_bytes: n_mesh=%d must be divisible by nranks=%d", n_mesh, nranks);
+  cufftHandle h;
+  size_t w1 = 0, w2 = 0;
+  int rc = make_fft_yz(n_mesh, n_mesh / nranks, &h, &w1);
+  cufftDestroy(h);
+  if (rc) return rc;
+  rc = make_fft_x(n_mesh, n_mesh / nranks, &h, &w2);
+  cufftDestroy(h);
+  if (rc) return rc;
+  const size_t tb = tables_bytes(n_mesh);
+  JPS_REQUIRE(tb > 0, "jps_slab_plan_workspace_bytes: table sizing failed");
+  *bytes = align_up(std::max(w1, w2), 256) + align_up(tb, 256) + 512;
+  return JPS_OK;
+}
+
+extern "C" int jps_slab_plan_destroy(jps_slab_plan_t* p) {
+  if (!p) return JPS_OK;
+  if (p->yz_ok) cufftDestroy(p->fft_yz);
+  if (p->x_ok) cufftDestroy(p->fft_x);
+  if (p->tables) jps_plan_destroy(p->tables);
+  delete p;
+  return JPS_OK;
+}
+
+extern "C" int jps_slab_plan_create(int n_mesh, int nranks, int rank, void* workspace,
+                                    size_t workspace_bytes, jps_slab_plan_t** out) {
+  JPS_REQUIRE(out != nullptr, "jps_slab_plan_create: plan is NULL");
+  *out = nullptr;
+  JPS_REQUIRE(n_mesh >= 2 && n_mesh <= 4096, "jps_slab_plan_create: n_mesh out of range");
+  JPS_REQUIRE(nranks >= 1 && n_mesh % nranks == 0, "jps_slab_plan_create: n_mesh=%d must be divisible by nranks=%d", n_mesh, nranks);
+  JPS_REQUIRE(rank >= 0 && rank < nranks, "jps_slab_plan_create: bad rank");
+  JPS_REQUIRE(workspace && ((uintptr_t)workspace & 255) == 0, "jps_slab_plan_create: workspace must be 256-byte aligned");
+  jps_slab_plan* p = new jps_slab_plan();
+  p->n = n_mesh; p->nz = n_mesh / 2 + 1; p->nranks = nranks; p->rank = rank;
+  p->nxl = n_mesh / nranks; p->nyl = n_mesh / nranks;
+  size_t w1 = 0, w2 = 0;
+  int rc = make_fft_yz(n_mesh, p->nxl, &p->fft_yz, &w1);
+  if (rc) { delete p; return rc; }
+  p->yz_ok = true;
+  rc = make_fft_x(n_mesh, p->nyl, &p->fft_x, &w2);
+  if (rc) { jps_slab_plan_destroy(p); return rc; }
+  p->x_ok = true;
+  const size_t wb = align_up(std::max(w1, w2), 256);
+  const size_t tb = tables_bytes(n_mesh);
+  if (workspace_bytes < wb + align_up(tb, 256)) {
+    set_error("jps_slab_plan_create: workspace has %zu bytes, %zu needed", workspace_bytes, wb + align_up(tb, 256));
+    jps_slab_plan_destroy(p);
+    return JPS_ERR_WORKSPACE;
+  }
+  p->work = workspace; p->work_bytes = wb;
+  if (cufftSetWorkArea(p->fft_yz, p->work) != CUFFT_SUCCESS || cufftSetWorkArea(p->fft_x, p->work) != CUFFT_SUCCESS) {
+    set_error("jps_slab_plan_create: cufftSetWorkArea failed");
+    jps_slab_plan_destroy(p);
+    return JPS_ERR_CUFFT;
+  }
+  rc = jps_plan_create(n_mesh, 0, JPS_PLAN_TABLES_ONLY, (char*)workspace + wb, workspace_bytes - wb, &p->tables);
+  if (rc) { jps_slab_plan_destroy(p); return rc; }
+  *out = p;
+  return JPS_OK;
+}
+
+extern "C" int jps_slab_fft_yz(jps_slab_plan_t* p, const float* slab, void* out, void* stream) {
+  JPS_REQUIRE(p && slab && out, "jps_slab_fft_yz: NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  JPS_CHECK_CUFFT(cufftSetStream(p->fft_yz, s));
+  ScopedLaunch L(K_FFT_R2C, s);
+  JPS_CHECK_CUFFT(cufftExecR2C(p->fft_yz, (cufftReal*)slab, (cufftComplex*)out));
+  return JPS_OK;
+}
+
+extern "C" int jps_slab_pack(jps_slab_plan_t* p, const void* in, void* out, void* stream) {
+  JPS_REQUIRE(p && in && out, "jps_slab_pack: NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  // out[q][xl][yl][kz] = in[xl][q*nyl + yl][kz]: for each q a 2-D copy (rows = xl) of nyl*nz complex
+  const size_t row = (size_t)p->nyl * p->nz * sizeof(float2);
+  const size_t spitch = (size_t)p->n * p->nz * sizeof(float2);
+  for (int q = 0; q < p->nranks; ++q) {
+    ScopedLaunch L(K_MISC, s);
+    JPS_CHECK_CUDA(cudaMemcpy2DAsync((char*)out + (size_t)q * p->nxl * row, row,
+                                     (const char*)in + (size_t)q * row, spitch, row, (size_t)p->nxl,
+                                     cudaMemcpyDeviceToDevice, s));
+  }
+  return JPS_OK;
+}
+
+extern "C" int jps_slab_fft_x(jps_slab_plan_t* p, void* data, void* stream) {
+  JPS_REQUIRE(p && data, "jps_slab_fft_x: NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  JPS_CHECK_CUFFT(cufftSetStream(p->fft_x, s));
+  ScopedLaunch L(K_FFT_R2C, s);
+  JPS_CHECK_CUFFT(cufftExecC2C(p->fft_x, (cufftComplex*)data, (cufftComplex*)data, CUFFT_FORWARD));
+  return JPS_OK;
+}
+
+extern "C" int jps_slab_powspec_partial(jps_slab_plan_t* p, const void* dk, const float* dc,
+                                        int normalise, float box_size, const float* k_edges, int nb,
+                                        int mas_order, double* sums, int64_t* counts, void* stream) {
+  JPS_REQUIRE(p && dk && k_edges && sums, "jps_slab_powspec_partial: NULL argument");
+  JPS_REQUIRE(!normalise || dc, "jps_slab_powspec_partial: normalise needs the DC mode (dc)");
+  JPS_REQUIRE(nb >= 1 && nb <= kMaxUserBins, "jps_slab_powspec_partial: nb out of range");
+  JPS_REQUIRE(mas_order >= 2 && mas_order <= 4 && box_size > 0.0f, "jps_slab_powspec_partial: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  jps_plan* tp = p->tables;
+  const float kF = ref_kF(box_size);
+  std::vector<float> kg((size_t)nb + 1);
+  for (int i = 0; i <= nb; ++i) kg[(size_t)i] = k_edges[i] / kF;
+  BinTable* T = nullptr;
+  int rc = ensure_bin_table(tp, kg.data(), nb, TABLE_PK_EDGES, s, &T);
+  if (rc) return rc;
+  {
+    ScopedLaunch L(K_MEMSET, s);
+    JPS_CHECK_CUDA(cudaMemsetAsync(tp->acc, 0, (size_t)std::max(T->nbc, 1) * 4 * 8, s));
+  }
+  if (T->nbc > 0) {
+    SlabPkParams P;
+    P.dk = (const float2*)dk; P.n = p->n; P.nz = p->nz; P.nyl = p->nyl; P.y0 = p->rank * p->nyl;
+    P.lut = T->lut; P.wl = tp->wlut + (size_t)(mas_order - 2) * p->n; P.nbc = T->nbc; P.acc = tp->acc;
+    P.dc = dc; P.normalise = normalise;
+    const int threads = 256, warps = 8;
+    const long long items = (long long)(p->n / 2 + 1) * p->nyl;
+    const long long want = (items + warps - 1) / warps;
+    if (T->nbc <= kMaxSmemBins) {
+      const size_t smem = (size_t)warps * T->nbc * 3 * sizeof(float);
+      static bool attr_set = false;
+      if (!attr_set) {
+        JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)((size_t)warps * kMaxSmemBins * 3 * sizeof(float))));
+        attr_set = true;
+      }
+      int per_sm = 1;
+      JPS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_bin_ysharded_kernel<true>, threads, smem));
+      const int blocks = (int)std::min<long long>(want, (long long)kNumSMs * std::max(per_sm, 1));
+      ScopedLaunch L(K_PK_FOLD_BIN, s);
+      pk_bin_ysharded_kernel<true><<<blocks, threads, smem, s>>>(P);
+    } else {
+      const int blocks = (int)std::min<long long>(want, (long long)kNumSMs * 8);
+      ScopedLaunch L(K_PK_FOLD_BIN, s);
+      pk_bin_ysharded_kernel<false><<<blocks, threads, 0, s>>>(P);
+    }
+    JPS_CHECK_LAUNCH();
+  }
+  {
+    ScopedLaunch L(K_PK_FINALIZE, s);
+    slab_expand_kernel<<<(nb + 127) / 128, 128, 0, s>>>(nb, T->bin_to_compact, tp->acc, T->cnt, sums, counts);
+  }
+  JPS_CHECK_LAUNCH();
+  return JPS_OK;
+}
+
+extern "C" int jps_slab_powspec_finalize(jps_slab_plan_t* p, float box_size, const float* k_edges,
+                                         int nb, const double* sums, const int64_t* counts,
+                                         float shot_noise, float* k3d, float* pk3d, float* nmodes,
+                                         void* stream) {
+  JPS_REQUIRE(p && k_edges && sums && counts && k3d && pk3d && nmodes, "jps_slab_powspec_finalize: NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const float kF = ref_kF(box_size);
+  std::vector<float> kg((size_t)nb + 1);
+  for (int i = 0; i <= nb; ++i) kg[(size_t)i] = k_edges[i] / kF;
+  BinTable* T = nullptr;
+  int rc = ensure_bin_table(p->tables, kg.data(), nb, TABLE_PK_EDGES, s, &T);   // cached: gives the device edges
+  if (rc) return rc;
+  {
+    ScopedLaunch L(K_PK_FINALIZE, s);
+    slab_finalize_kernel<<<(nb + 127) / 128, 128, 0, s>>>(nb, T->edges, sums, counts, kF,
+                                                         ref_volume(box_size, p->n), shot_noise, k3d, pk3d, nmodes);
+  }
+  JPS_CHECK_LAUNCH();
+  return JPS_OK;
+}

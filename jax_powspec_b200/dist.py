@@ -1,0 +1,115 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed; NCCL on GPUs, gloo in CPU tests).
+
+The path shards without communication on *realisations* (BASELINE.json configs[4]: a covariance
+batch of independent mocks; also what ``bench.py --gpus N`` runs): rank r takes realisations
+r, r+W, r+2W, ...; the only exchange is the final gather of the (nbins x 3) multipole rows.
+The helpers below hold that host logic; they never touch the compute path, so they are testable
+with the gloo backend on CPU (tests/test_dist_cpu.py).
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def world() -> tuple[int, int]:
+    """(rank, world_size) from the initialised process group, else (0, 1)."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def init_from_env(backend: str | None = None, device: torch.device | None = None) -> tuple[int, int, int]:
+    """Initialise torch.distributed from RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun).
+    Returns (rank, world_size, local_rank).  No-op for a single process."""
+    w = int(os.environ.get("WORLD_SIZE", "1"))
+    r = int(os.environ.get("RANK", "0"))
+    lr = int(os.environ.get("LOCAL_RANK", "0"))
+    if w > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
+        dist.init_process_group(backend, rank=r, world_size=w, **kw)
+    return r, w, lr
+
+
+def shard_indices(n_items: int, rank: int | None = None, world_size: int | None = None) -> list[int]:
+    """Round-robin shard of range(n_items): rank r owns r, r+W, r+2W, ... (balanced to +-1)."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    return list(range(rank, n_items, world_size))
+
+
+def max_over_ranks(value: float, device: torch.device | str = "cpu") -> float:
+    """Device-time statistics are reported as the max over ranks (bench.py contract)."""
+    _, w = world()
+    if w == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def gather_rows(local_rows: torch.Tensor, n_items: int) -> torch.Tensor | None:
+    """Inverse of shard_indices: every rank passes its [n_local, ...] rows (in its shard order);
+    rank 0 gets the [n_items, ...] array in global order, other ranks get None."""
+    r, w = world()
+    if w == 1:
+        return local_rows
+    counts = [len(range(q, n_items, w)) for q in range(w)]
+    pad = max(counts)
+    shape = (pad,) + tuple(local_rows.shape[1:])
+    buf = torch.zeros(shape, dtype=local_rows.dtype, device=local_rows.device)
+    buf[: local_rows.shape[0]] = local_rows
+    out = [torch.empty_like(buf) for _ in range(w)]
+    dist.all_gather(out, buf)
+    if r != 0:
+        return None
+    full = torch.empty((n_items,) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype, device=local_rows.device)
+    for q in range(w):
+        full[q::w] = out[q][: counts[q]]
+    return full
+
+
+def sample_covariance(rows: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """Mean and unbiased sample covariance of realisation rows [n_real, n_features] (float64)."""
+    rows = np.asarray(rows, dtype=np.float64)
+    mean = rows.mean(axis=0)
+    d = rows - mean
+    cov = d.T @ d / max(rows.shape[0] - 1, 1)
+    return mean, cov
+
+
+def covariance_batch(seeds: Sequence[int], measure: Callable[[int], torch.Tensor]):
+    """BASELINE.json configs[4]: P(k) of many independent realisations, sharded over ranks.
+
+    ``measure(seed)`` returns that realisation's multipoles as a tensor [nbins, 3] (on any device);
+    it is called only for this rank's seeds.  Returns on rank 0 ``(pk_rows [n, nbins, 3] numpy,
+    mean [nbins*3], cov [nbins*3, nbins*3])`` and ``None`` elsewhere."""
+    seeds = list(seeds)
+    mine = shard_indices(len(seeds))
+    rows = [measure(seeds[i]).detach().to(torch.float32).reshape(1, -1) for i in mine]
+    ncol = None
+    if rows:
+        local = torch.cat(rows, dim=0)
+        ncol = local.shape[1]
+    r, w = world()
+    if w > 1:                                  # ranks with no work still need the row width
+        dev = rows[0].device if rows else (torch.device("cuda", torch.cuda.current_device())
+                                          if dist.get_backend() == "nccl" else torch.device("cpu"))
+        t = torch.tensor([ncol or 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ncol = int(t.item())
+        if not rows:
+            local = torch.zeros((0, ncol), dtype=torch.float32, device=dev)
+    full = gather_rows(local, len(seeds))
+    if full is None:
+        return None
+    arr = full.cpu().numpy()
+    mean, cov = sample_covariance(arr)
+    return arr.reshape(len(seeds), -1, 3), mean, cov

@@ -1,0 +1,258 @@
+"""Slab-sharded paint -> distributed R2C FFT -> P(k) multipoles (one process per GPU).
+
+SURVEY.md section 8e / BASELINE.json configs[3].  The reference has no multi-device code; this
+module is the host side that strings the per-rank C-ABI stages of include/jps.h
+("slab-sharded mesh") together with three exchanges done through torch.distributed (NCCL over
+NVLink on GPUs; gloo in the CPU choreography test):
+
+  paint   : every rank deposits ITS particles (x in its slab) into [1 + N/P + 2][N][N] planes
+            (one ghost plane below, two above: enough for CIC/TSC/PCS stencils anchored at their
+            lowest node)                                            -> ring halo exchange + add
+  FFT     : 2-D R2C of the owned planes, pack by destination, ONE all-to-all of
+            (P-1)/P^2 * 8 N^2 (N/2+1) bytes per rank, 1-D C2C along x -> delta_k stays y-sharded
+  binning : local fold/bin kernel                                   -> allreduce of nb*3 float64
+
+The exchange helpers are plain functions on tensors so that the choreography (who sends which
+block where) is unit-tested on CPU with gloo, independently of the CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check, lib
+from .correlations import _edge_ptr, _host_edges
+from .mas import _common_stride, _paint_workspace
+from .plan import ptr, stream_ptr
+
+GHOST_LO, GHOST_HI = 1, 2
+
+
+# --------------------------------------------------------------------------- exchanges
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def halo_exchange_add(mesh: torch.Tensor, nxl: int) -> None:
+    """mesh: [GHOST_LO + nxl + GHOST_HI, N, N].  Ring exchange: the low ghost plane is added to the
+    previous rank's last owned plane, the high ghost planes to the next rank's first owned planes."""
+    rank, world = _world()
+    lo = mesh[0:GHOST_LO]
+    hi = mesh[GHOST_LO + nxl: GHOST_LO + nxl + GHOST_HI]
+    own_first = mesh[GHOST_LO: GHOST_LO + GHOST_HI]
+    own_last = mesh[GHOST_LO + nxl - GHOST_LO: GHOST_LO + nxl]
+    if world == 1:
+        own_last += lo
+        own_first += hi
+        return
+    prev, nxt = (rank - 1) % world, (rank + 1) % world
+    from_next = torch.empty_like(lo)       # next rank's low ghost lands on my last owned plane
+    from_prev = torch.empty_like(hi)       # previous rank's high ghosts land on my first owned planes
+    ops = [dist.P2POp(dist.isend, lo.contiguous(), prev), dist.P2POp(dist.isend, hi.contiguous(), nxt),
+           dist.P2POp(dist.irecv, from_next, nxt), dist.P2POp(dist.irecv, from_prev, prev)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    own_last += from_next
+    own_first += from_prev
+
+
+def transpose_all_to_all(send: torch.Tensor, recv: torch.Tensor) -> None:
+    """send: [P][nxl][nyl][nz] (block q goes to rank q); recv: [P][nxl][nyl][nz] = [N][nyl][nz] with the
+    block of source rank q at x-planes [q*nxl, (q+1)*nxl)."""
+    _, world = _world()
+    if world == 1:
+        recv.copy_(send)
+        return
+    s = torch.view_as_real(send) if send.is_complex() else send
+    r = torch.view_as_real(recv) if recv.is_complex() else recv
+    dist.all_to_all_single(r.view(-1), s.reshape(-1))
+
+
+def pack_blocks_torch(yz: torch.Tensor, world: int) -> torch.Tensor:
+    """Reference implementation of jps_slab_pack with torch ops (used by the CPU choreography test):
+    [nxl][N][nz] -> [P][nxl][nyl][nz]."""
+    nxl, n, nz = yz.shape
+    nyl = n // world
+    return yz.reshape(nxl, world, nyl, nz).permute(1, 0, 2, 3).contiguous()
+
+
+def route_particles(x, y, z, w, box_size: float, n_mesh: int):
+    """Send every particle to the rank that owns floor(x/cell) (variable-size all-to-all).
+    Catalogues generated in place (BASELINE configs[3]) skip this."""
+    rank, world = _world()
+    if world == 1:
+        return x, y, z, w
+    nxl = n_mesh // world
+    cell = torch.floor(x * (n_mesh / box_size)).to(torch.int64).remainder_(n_mesh)
+    owner = torch.div(cell, nxl, rounding_mode="floor")
+    order = torch.argsort(owner)
+    counts = torch.bincount(owner, minlength=world)
+    recv_counts = torch.empty_like(counts)
+    dist.all_to_all_single(recv_counts, counts)
+    s_split, r_split = counts.tolist(), recv_counts.tolist()
+    out = []
+    for t in (x, y, z, w):
+        if t is None:
+            out.append(None)
+            continue
+        src = t[order].contiguous()
+        dst = torch.empty(int(sum(r_split)), dtype=t.dtype, device=t.device)
+        dist.all_to_all_single(dst, src, output_split_sizes=r_split, input_split_sizes=s_split)
+        out.append(dst)
+    return tuple(out)
+
+
+# --------------------------------------------------------------------------- pipeline
+class SlabPipeline:
+    """Per-rank object: owns the slab mesh, the two complex transpose buffers and the slab plan."""
+
+    def __init__(self, n_mesh, box_size, k_edges, *, order=2, compat="fixed", method="auto", wrap=True,
+                 shot_noise=0.0, rank=None, world=None, device=None):
+        r, w = _world()
+        self.rank = r if rank is None else rank
+        self.world = w if world is None else world
+        self.n, self.box = int(n_mesh), float(box_size)
+        if self.n % self.world:
+            raise ValueError(f"n_mesh={self.n} must be divisible by the number of ranks {self.world}")
+        self.nxl = self.n // self.world
+        if self.world > 1 and self.nxl < GHOST_HI:
+            raise ValueError("slab thinner than the stencil: use fewer ranks")
+        self.nz = self.n // 2 + 1
+        self.order, self.compat, self.method, self.wrap = int(order), compat, method, bool(wrap)
+        self.shot_noise = float(shot_noise)
+        self.edges = _host_edges(k_edges)
+        self.nb = self.edges.size - 1
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        d = self.device
+        self.single = self.world == 1
+        self.gl, self.gh = (0, 0) if self.single else (GHOST_LO, GHOST_HI)
+        self.nxa = self.nxl + self.gl + self.gh
+        self.x0 = self.rank * self.nxl - self.gl
+        self.mesh = torch.empty((self.nxa, self.n, self.n), dtype=torch.float32, device=d)
+        cshape = (self.world, self.nxl, self.nxl, self.nz)
+        self.buf_a = torch.empty(cshape, dtype=torch.complex64, device=d)     # yz-transformed / receive
+        self.buf_b = torch.empty(cshape, dtype=torch.complex64, device=d)     # packed send buffer
+        nbytes = C.c_size_t(0)
+        with torch.cuda.device(d):
+            check(lib.jps_slab_plan_workspace_bytes(self.n, self.world, C.byref(nbytes)))
+            self.ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=d)
+            base = (self.ws.data_ptr() + 255) // 256 * 256
+            h = C.c_void_p(0)
+            check(lib.jps_slab_plan_create(self.n, self.world, self.rank, C.c_void_p(base),
+                                           C.c_size_t(nbytes.value), C.byref(h)), "jps_slab_plan_create")
+        self.handle = h
+        self.sums = torch.zeros((self.nb, 3), dtype=torch.float64, device=d)
+        self.counts = torch.zeros(self.nb, dtype=torch.int64, device=d)
+        self.dc = torch.zeros(1, dtype=torch.float32, device=d)
+        self.k3d = torch.empty(self.nb, dtype=torch.float32, device=d)
+        self.pk = torch.empty((self.nb, 3), dtype=torch.float32, device=d)
+        self.nm = torch.empty(self.nb, dtype=torch.float32, device=d)
+        self.pws, self.pws_bytes = None, 0
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib.jps_slab_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- stages (each enqueues on the current stream; exchanges are separate so that a test can
+    #      drive several virtual ranks on one device)
+    def stage_paint(self, x, y, z, w=None, xmin=0.0, ymin=0.0, zmin=0.0):
+        x, y, z, stride = _common_stride(x, y, z)
+        npart = x.numel()
+        meth = _lib.METHOD[self.method]
+        need = C.c_size_t(0)
+        check(lib.jps_paint_workspace_bytes(self.n, npart, self.order, meth, C.byref(need)))
+        if need.value > self.pws_bytes:
+            self.pws, self.pws_bytes = _paint_workspace(self.n, npart, self.order, meth, self.device)
+        self.mesh.zero_()
+        check(lib.jps_paint_slab(self.n, self.x0, self.nxa, ptr(x), ptr(y), ptr(z), ptr(w), stride, npart,
+                                 float(xmin), float(ymin), float(zmin), self.box, self.order, int(self.wrap),
+                                 _lib.COMPAT[self.compat], _lib.VARIANT_VEC, meth, ptr(self.mesh), ptr(self.pws),
+                                 self.pws_bytes, stream_ptr()), "jps_paint_slab")
+
+    def owned(self):
+        return self.mesh[self.gl: self.gl + self.nxl]
+
+    def stage_fft_yz_pack(self):
+        check(lib.jps_slab_fft_yz(self.handle, ptr(self.owned()), ptr(self.buf_a), stream_ptr()), "jps_slab_fft_yz")
+        check(lib.jps_slab_pack(self.handle, ptr(self.buf_a), ptr(self.buf_b), stream_ptr()), "jps_slab_pack")
+
+    def stage_fft_x(self):
+        check(lib.jps_slab_fft_x(self.handle, ptr(self.buf_a), stream_ptr()), "jps_slab_fft_x")
+
+    def local_dc(self):
+        """Re rho_hat(0): element (ix=0, yl=0, kz=0) of rank 0's shard."""
+        return self.buf_a.view(-1)[0:1].real.to(torch.float32)
+
+    def stage_partial(self, normalise=True):
+        check(lib.jps_slab_powspec_partial(self.handle, ptr(self.buf_a), ptr(self.dc), int(bool(normalise)), self.box,
+                                           _edge_ptr(self.edges), self.nb, self.order, ptr(self.sums), ptr(self.counts),
+                                           stream_ptr()), "jps_slab_powspec_partial")
+
+    def stage_finalize(self):
+        check(lib.jps_slab_powspec_finalize(self.handle, self.box, _edge_ptr(self.edges), self.nb, ptr(self.sums),
+                                            ptr(self.counts), self.shot_noise, ptr(self.k3d), ptr(self.pk), ptr(self.nm),
+                                            stream_ptr()), "jps_slab_powspec_finalize")
+        return self.k3d, self.pk, self.nm
+
+    # ---- the distributed call
+    def __call__(self, x, y, z, w=None, xmin=0.0, ymin=0.0, zmin=0.0):
+        """x, y, z[, w]: this rank's particles (x inside its slab; use route_particles otherwise)."""
+        self.stage_paint(x, y, z, w, xmin, ymin, zmin)
+        if not self.single:
+            halo_exchange_add(self.mesh, self.nxl)
+        self.stage_fft_yz_pack()
+        transpose_all_to_all(self.buf_b, self.buf_a)
+        self.stage_fft_x()
+        if self.rank == 0:
+            self.dc.copy_(self.local_dc())
+        if self.world > 1:
+            dist.broadcast(self.dc, src=0)
+        self.stage_partial(normalise=True)
+        if self.world > 1:
+            dist.all_reduce(self.sums)
+        return self.stage_finalize()
+
+
+def run_virtual_ranks(pipes, catalogs, xmin=0.0):
+    """Drive P SlabPipeline objects that live on ONE device through the distributed algorithm,
+    doing the three exchanges with tensor copies (test harness for the per-rank kernels)."""
+    P = len(pipes)
+    for p, (x, y, z, w) in zip(pipes, catalogs):
+        p.stage_paint(x, y, z, w, xmin, xmin, xmin)
+    if P > 1:
+        los = [p.mesh[0:GHOST_LO].clone() for p in pipes]
+        his = [p.mesh[p.gl + p.nxl: p.gl + p.nxl + GHOST_HI].clone() for p in pipes]
+        for r, p in enumerate(pipes):
+            p.mesh[p.gl + p.nxl - GHOST_LO: p.gl + p.nxl] += los[(r + 1) % P]
+            p.mesh[p.gl: p.gl + GHOST_HI] += his[(r - 1) % P]
+    for p in pipes:
+        p.stage_fft_yz_pack()
+    for q, dst in enumerate(pipes):                      # all-to-all: block q of rank r -> rank q, slot r
+        for r, src in enumerate(pipes):
+            dst.buf_a[r].copy_(src.buf_b[q])
+    for p in pipes:
+        p.stage_fft_x()
+    dc = pipes[0].local_dc().clone()
+    total = torch.zeros_like(pipes[0].sums)
+    for p in pipes:
+        p.dc.copy_(dc)
+        p.stage_partial(normalise=True)
+        total += p.sums
+    outs = []
+    for p in pipes:
+        p.sums.copy_(total)
+        outs.append(tuple(t.clone() for t in p.stage_finalize()))
+    return outs
