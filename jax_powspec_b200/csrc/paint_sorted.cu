@@ -14,11 +14,11 @@
 // and cell choice stays bit-identical to the reference's float32 arithmetic.
 #include "paint_common.cuh"
 
+#include <cstdlib>
+
 namespace jps {
 
 constexpr int TILE = 16;                 // cells per tile side
-constexpr int SCAN_THREADS = 1024;
-constexpr int SCAN_ITEMS = 32;      // 32 K counters per iteration of the single scan CTA
 
 struct TileGeom {
   int n;        // global mesh side
@@ -89,54 +89,87 @@ __global__ void __launch_bounds__(256) bucket_count_kernel(PaintParams p, TileGe
   }
 }
 
-// ---------------------------------------------------------------- K1b: exclusive scan (one CTA)
-// offsets[0..m] = exclusive prefix sums of counts[0..m-1]; cursor[i] = offsets[i]
-__global__ void __launch_bounds__(SCAN_THREADS) bucket_scan_kernel(const unsigned* __restrict__ counts,
-                                                                   unsigned* __restrict__ offsets,
-                                                                   unsigned* __restrict__ cursor, int m) {
+// ---------------------------------------------------------------- K1b: exclusive scan
+// Three small launches: per-block totals (SCAN_BLOCK counters per CTA, coalesced), a one-CTA scan of
+// the block totals, and the per-block rescan that writes offsets[] and the scatter cursors.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ROUNDS = 8;
+constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ROUNDS;      // counters per CTA
+
+__device__ __forceinline__ unsigned block_exclusive_scan_256(unsigned v, unsigned* warp_tot, unsigned& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned incl = v;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += t;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  unsigned before = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+    const unsigned t = warp_tot[w];
+    if (w < warp) before += t;
+    tot += t;
+  }
+  __syncthreads();                                // warp_tot may be reused by the caller's next round
+  total = tot;
+  return before + incl - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_totals_kernel(const unsigned* __restrict__ counts,
+                                                                         unsigned* __restrict__ block_tot, int m) {
+  __shared__ unsigned warp_tot[SCAN_THREADS / 32];
+  const int base = blockIdx.x * SCAN_BLOCK;
+  unsigned v = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ROUNDS; ++j) {
+    const int i = base + j * SCAN_THREADS + threadIdx.x;
+    if (i < m) v += counts[i];
+  }
+  unsigned total;
+  block_exclusive_scan_256(v, warp_tot, total);
+  if (threadIdx.x == 0) block_tot[blockIdx.x] = total;
+}
+
+// in place: block_tot[b] <- sum of block_tot[0..b-1]; block_tot[nblocks] <- grand total
+__global__ void __launch_bounds__(SCAN_THREADS) scan_of_totals_kernel(unsigned* __restrict__ block_tot, int nblocks) {
   __shared__ unsigned warp_tot[SCAN_THREADS / 32];
   __shared__ unsigned carry;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) carry = 0;
+  if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  for (int base = 0; base < m; base += SCAN_THREADS * SCAN_ITEMS) {
-    unsigned v[SCAN_ITEMS];
-    unsigned tsum = 0;
-    const int i0 = base + tid * SCAN_ITEMS;
-#pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-      v[j] = (i0 + j < m) ? counts[i0 + j] : 0u;
-      tsum += v[j];
-    }
-    unsigned incl = tsum;                        // inclusive scan of thread sums within the warp
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const unsigned t = __shfl_up_sync(0xffffffffu, incl, off);
-      if (lane >= off) incl += t;
-    }
-    if (lane == 31) warp_tot[warp] = incl;
+  for (int base = 0; base < nblocks; base += SCAN_THREADS) {
+    const int i = base + threadIdx.x;
+    const unsigned v = i < nblocks ? block_tot[i] : 0u;
+    unsigned total;
+    const unsigned ex = block_exclusive_scan_256(v, warp_tot, total);
+    const unsigned c = carry;
+    if (i < nblocks) block_tot[i] = c + ex;
     __syncthreads();
-    if (warp == 0) {
-      unsigned w = warp_tot[lane];
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const unsigned t = __shfl_up_sync(0xffffffffu, w, off);
-        if (lane >= off) w += t;
-      }
-      warp_tot[lane] = w;                        // inclusive scan of warp totals
-    }
-    __syncthreads();
-    unsigned run = carry + (warp ? warp_tot[warp - 1] : 0u) + (incl - tsum);
-#pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-      if (i0 + j < m) { offsets[i0 + j] = run; cursor[i0 + j] = run; }
-      run += v[j];
-    }
-    __syncthreads();
-    if (tid == SCAN_THREADS - 1) carry = run;    // last thread holds the running total
+    if (threadIdx.x == 0) carry = c + total;
     __syncthreads();
   }
-  if (tid == 0) offsets[m] = carry;
+  if (threadIdx.x == 0) block_tot[nblocks] = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const unsigned* __restrict__ counts,
+                                                                  const unsigned* __restrict__ block_off,
+                                                                  unsigned* __restrict__ offsets,
+                                                                  unsigned* __restrict__ cursor, int m, int nblocks) {
+  __shared__ unsigned warp_tot[SCAN_THREADS / 32];
+  const int base = blockIdx.x * SCAN_BLOCK;
+  unsigned run = block_off[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < SCAN_ROUNDS; ++j) {
+    const int i = base + j * SCAN_THREADS + threadIdx.x;
+    const unsigned v = i < m ? counts[i] : 0u;
+    unsigned total;
+    const unsigned ex = block_exclusive_scan_256(v, warp_tot, total);
+    if (i < m) { offsets[i] = run + ex; cursor[i] = run + ex; }
+    run += total;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) offsets[m] = block_off[nblocks];
 }
 
 // ---------------------------------------------------------------- K1c: scatter into buckets
@@ -293,6 +326,185 @@ __global__ void __launch_bounds__(256) paint_tile_kernel(const float4* __restric
   }
 }
 
+// ---------------------------------------------------------------- K2 (v2): cell-ordered deposit
+// paint_tile (above) is bound by the shared-memory pipe: a warp-wide CAS-add on 32 random cells of
+// the tile costs ~13 wavefronts (bank conflicts on the read and on the CAS; ncu: 0.93 wavefronts
+// per clock per SM).  Here each chunk of <= CELL_CHUNK particles is first counting-sorted by anchor
+// cell inside shared memory (packed 16-bit counters, one native integer atomic per particle), so
+// that the 32 lanes of a warp deposit particles of consecutive cells: for a given stencil offset
+// their addresses are consecutive words of a few z-rows -> (almost) conflict free.
+constexpr int CELL_CHUNK = 2048;
+constexpr int CELL_PT = CELL_CHUNK / 256;          // particles per thread in the sort phases
+constexpr int CELLS = TILE * TILE * TILE;          // 4096 anchor cells per tile
+
+template <int ORDER, bool REFCIC>
+__device__ __forceinline__ int anchor_cell(const float4& r, const TileGeom& g, int ox, int oy, int oz) {
+  const int ax = local_plane(anchor_axis<ORDER, REFCIC>(r.x, g.n), g.x0, g.nx, g.n) - ox;
+  const int ay = anchor_axis<ORDER, REFCIC>(r.y, g.n) - oy;
+  const int az = anchor_axis<ORDER, REFCIC>(r.z, g.n) - oz;
+  return (ax * TILE + ay) * TILE + az;             // in [0, CELLS) for every particle of this bucket
+}
+
+template <int ORDER, bool REFCIC>
+__device__ __forceinline__ void deposit_to_tile(const float4& r, float* tile, const TileGeom& g, int wrap,
+                                                int variant, int ox, int oy, int oz) {
+  constexpr int L = TILE + ORDER - 1;
+  constexpr int LP = (L + 3) & ~3;
+  const int n = g.n;
+  if (REFCIC) {
+    int x0, x1, y0, y1, z0, z1;
+    float mdx, ddx, mdy, ddy, mdz, ddz;
+    cic_reference_axis(r.x, n, wrap, variant, x0, x1, mdx, ddx);
+    cic_reference_axis(r.y, n, wrap, variant, y0, y1, mdy, ddy);
+    cic_reference_axis(r.z, n, wrap, variant, z0, z1, mdz, ddz);
+    float* c = tile + ((local_plane(x0, g.x0, g.nx, n) - ox) * L + (y0 - oy)) * LP + (z0 - oz);
+    const float wgt = r.w;
+    constexpr int SX = L * LP, SY = LP;
+    atomicAdd(c, ((mdx * mdy) * mdz) * wgt);
+    atomicAdd(c + SX, ((ddx * mdy) * mdz) * wgt);
+    atomicAdd(c + SY, ((mdx * ddy) * mdz) * wgt);
+    atomicAdd(c + 1, ((mdx * mdy) * ddz) * wgt);
+    atomicAdd(c + SX + SY, ((ddx * ddy) * mdz) * wgt);
+    atomicAdd(c + SX + 1, ((ddx * mdy) * ddz) * wgt);
+    atomicAdd(c + SY + 1, ((mdx * mdy) * ddz) * wgt);       // Q1 (reference weight)
+    atomicAdd(c + SX + SY + 1, ((ddx * ddy) * ddz) * wgt);
+  } else {
+    int ax, ay, az;
+    float wx[ORDER], wy[ORDER], wz[ORDER];
+    tile_axis<ORDER>(r.x, n, wrap, ax, wx);
+    tile_axis<ORDER>(r.y, n, wrap, ay, wy);
+    tile_axis<ORDER>(r.z, n, wrap, az, wz);
+    float* c = tile + ((local_plane(ax, g.x0, g.nx, n) - ox) * L + (ay - oy)) * LP + (az - oz);
+#pragma unroll
+    for (int a = 0; a < ORDER; ++a) {
+#pragma unroll
+      for (int b = 0; b < ORDER; ++b) {
+        const float wxy = wx[a] * wy[b];
+#pragma unroll
+        for (int cc = 0; cc < ORDER; ++cc) atomicAdd(c + (a * L + b) * LP + cc, (wxy * wz[cc]) * r.w);
+      }
+    }
+  }
+}
+
+template <int ORDER>
+__device__ __forceinline__ void flush_tile(const float* tile, const TileGeom& g, int ox, int oy, int oz,
+                                           int mesh_vec_ok, float* __restrict__ mesh) {
+  constexpr int L = TILE + ORDER - 1;
+  constexpr int LP = (L + 3) & ~3;
+  const int n = g.n;
+  const size_t n2 = (size_t)n * n;
+  const bool vec_ok = (n % 4 == 0) && mesh_vec_ok;
+  constexpr int NV = TILE / 4;
+  constexpr int ROW_ITEMS = NV + (ORDER - 1);
+  for (int item = threadIdx.x; item < L * L * ROW_ITEMS; item += blockDim.x) {
+    const int q = item % ROW_ITEMS;
+    const int row = item / ROW_ITEMS;
+    const int j = row % L, i = row / L;
+    int gx = ox + i;
+    if (g.nx == n) gx %= n;
+    else if (gx >= g.nx) continue;
+    const int gy = (oy + j) % n;
+    float* grow = mesh + (size_t)gx * n2 + (size_t)gy * n;
+    const float* trow = tile + (i * L + j) * LP;
+    if (q < NV) {
+      const int k = q * 4;
+      const float4 v = *reinterpret_cast<const float4*>(trow + k);
+      if (v.x == 0.0f && v.y == 0.0f && v.z == 0.0f && v.w == 0.0f) continue;
+      const int gz = oz + k;
+      if (vec_ok && gz + 3 < n) {
+        red_v4(grow + gz, v.x, v.y, v.z, v.w);
+      } else {
+        if (v.x != 0.0f) atomicAdd(grow + (gz % n), v.x);
+        if (v.y != 0.0f) atomicAdd(grow + ((gz + 1) % n), v.y);
+        if (v.z != 0.0f) atomicAdd(grow + ((gz + 2) % n), v.z);
+        if (v.w != 0.0f) atomicAdd(grow + ((gz + 3) % n), v.w);
+      }
+    } else {
+      const int k = TILE + (q - NV);
+      const float v = trow[k];
+      if (v != 0.0f) atomicAdd(grow + ((oz + k) % n), v);
+    }
+  }
+}
+
+template <int ORDER, bool REFCIC>
+__global__ void __launch_bounds__(256) paint_tile_cellsort_kernel(const float4* __restrict__ sorted,
+                                                                  const unsigned* __restrict__ offsets,
+                                                                  TileGeom g, int wrap, int variant,
+                                                                  int mesh_vec_ok, float* __restrict__ mesh) {
+  constexpr int L = TILE + ORDER - 1;
+  constexpr int LP = (L + 3) & ~3;
+  __shared__ __align__(16) float tile[L * L * LP];
+  __shared__ unsigned cnt[CELLS / 2];              // two 16-bit counters per word
+  __shared__ unsigned short perm[CELL_CHUNK];
+  __shared__ unsigned warp_tot[8];
+  const int t = blockIdx.x;
+  const unsigned beg = offsets[t * g.rep], end = offsets[(t + 1) * g.rep];
+  if (beg == end) return;
+  const int tz = t % g.nt, ty = (t / g.nt) % g.nt, tx = t / (g.nt * g.nt);
+  const int ox = tx * TILE, oy = ty * TILE, oz = tz * TILE;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < L * L * LP; i += 256) tile[i] = 0.0f;
+  __syncthreads();
+
+  for (unsigned c0 = beg; c0 < end; c0 += CELL_CHUNK) {
+    const int m = (int)min((unsigned)CELL_CHUNK, end - c0);
+    if (m < 256) {                                 // not worth sorting
+      for (int j = tid; j < m; j += 256)
+        deposit_to_tile<ORDER, REFCIC>(sorted[c0 + j], tile, g, wrap, variant, ox, oy, oz);
+      __syncthreads();
+      continue;
+    }
+    for (int i = tid; i < CELLS / 2; i += 256) cnt[i] = 0u;
+    __syncthreads();
+    unsigned key[CELL_PT];
+#pragma unroll
+    for (int u = 0; u < CELL_PT; ++u) {
+      const int idx = u * 256 + tid;
+      key[u] = 0xffffffffu;
+      if (idx < m) {
+        const int cid = anchor_cell<ORDER, REFCIC>(sorted[c0 + idx], g, ox, oy, oz);
+        const int sh = (cid & 1) * 16;
+        const unsigned old = atomicAdd(&cnt[cid >> 1], 1u << sh);
+        key[u] = (unsigned)cid | (((old >> sh) & 0xffffu) << 12);
+      }
+    }
+    __syncthreads();
+    {                                              // exclusive scan of the 4096 counters, in place
+      unsigned w[8];
+      unsigned tot = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        w[q] = cnt[tid * 8 + q];
+        tot += (w[q] & 0xffffu) + (w[q] >> 16);
+      }
+      unsigned total;
+      unsigned run = block_exclusive_scan_256(tot, warp_tot, total);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const unsigned lo = w[q] & 0xffffu, hi = w[q] >> 16;
+        cnt[tid * 8 + q] = run | ((run + lo) << 16);
+        run += lo + hi;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < CELL_PT; ++u) {
+      if (key[u] != 0xffffffffu) {
+        const int cid = key[u] & 0xfff;
+        const unsigned start = (cnt[cid >> 1] >> ((cid & 1) * 16)) & 0xffffu;
+        perm[start + (key[u] >> 12)] = (unsigned short)(u * 256 + tid);
+      }
+    }
+    __syncthreads();
+    for (int j = tid; j < m; j += 256)
+      deposit_to_tile<ORDER, REFCIC>(sorted[c0 + perm[j]], tile, g, wrap, variant, ox, oy, oz);
+    __syncthreads();
+  }
+  flush_tile<ORDER>(tile, g, ox, oy, oz, mesh_vec_ok, mesh);
+}
+
 // Particles the tile kernel cannot take (reference-compat CIC outside the box): the last bucket,
 // painted with the general per-particle path straight from the bucketed records.
 __global__ void __launch_bounds__(256) paint_outliers_kernel(const float4* __restrict__ sorted,
@@ -327,7 +539,7 @@ __global__ void __launch_bounds__(256) paint_outliers_kernel(const float4* __res
 
 // ---------------------------------------------------------------- host side
 struct SortedLayout {
-  size_t sorted, counts, offsets, cursor, total;
+  size_t sorted, counts, offsets, cursor, block_tot, total;
   int nbuckets;
 };
 
@@ -347,6 +559,7 @@ static SortedLayout sorted_layout(int n, int nx, int64_t n_part) {
   L.counts = take((size_t)(L.nbuckets + 1) * 4);
   L.offsets = take((size_t)(L.nbuckets + 1) * 4);
   L.cursor = take((size_t)(L.nbuckets + 1) * 4);
+  L.block_tot = take((size_t)(L.nbuckets / 2048 + 4) * 4);
   L.total = off;
   return L;
 }
@@ -376,8 +589,11 @@ static int run_sorted(const PaintParams& p, const TileGeom& g, const SortedLayou
   }
   JPS_CHECK_LAUNCH();
   {
-    ScopedLaunch T(K_BUCKET_SCAN, s);
-    bucket_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(counts, offsets, cursor, L.nbuckets);
+    const int nsb = (L.nbuckets + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    unsigned* block_tot = (unsigned*)(ws + L.block_tot);
+    { ScopedLaunch T(K_BUCKET_SCAN, s); scan_block_totals_kernel<<<nsb, SCAN_THREADS, 0, s>>>(counts, block_tot, L.nbuckets); }
+    { ScopedLaunch T(K_BUCKET_SCAN, s); scan_of_totals_kernel<<<1, SCAN_THREADS, 0, s>>>(block_tot, nsb); }
+    { ScopedLaunch T(K_BUCKET_SCAN, s); scan_write_kernel<<<nsb, SCAN_THREADS, 0, s>>>(counts, block_tot, offsets, cursor, L.nbuckets, nsb); }
   }
   JPS_CHECK_LAUNCH();
   {
@@ -388,8 +604,13 @@ static int run_sorted(const PaintParams& p, const TileGeom& g, const SortedLayou
   {
     ScopedLaunch T(K_PAINT_TILE, s);
     const int mesh_vec_ok = (((uintptr_t)p.mesh) & 15) == 0 ? 1 : 0;
-    paint_tile_kernel<ORDER, REFCIC><<<g.ntiles, 256, 0, s>>>(sorted, offsets, g, p.wrap, p.variant,
-                                                            mesh_vec_ok, p.mesh);
+    static const bool plain = [] { const char* e = getenv("JPS_TILE_KERNEL"); return e && !strcmp(e, "plain"); }();
+    if (plain)
+      paint_tile_kernel<ORDER, REFCIC><<<g.ntiles, 256, 0, s>>>(sorted, offsets, g, p.wrap, p.variant,
+                                                              mesh_vec_ok, p.mesh);
+    else
+      paint_tile_cellsort_kernel<ORDER, REFCIC><<<g.ntiles, 256, 0, s>>>(sorted, offsets, g, p.wrap, p.variant,
+                                                                       mesh_vec_ok, p.mesh);
   }
   JPS_CHECK_LAUNCH();
   if (REFCIC) {
