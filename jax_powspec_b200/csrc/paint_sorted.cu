@@ -67,8 +67,10 @@ constexpr int BUCKET_UNROLL = 4;
 
 template <int ORDER, bool REFCIC>
 __global__ void __launch_bounds__(256) bucket_count_kernel(PaintParams p, TileGeom g,
-                                                           unsigned* __restrict__ counts) {
+                                                           unsigned* __restrict__ counts,
+                                                           unsigned* __restrict__ wmax_bits) {
   const int64_t T = (int64_t)gridDim.x * blockDim.x;
+  float wmax = p.w ? 0.0f : 1.0f;                  // max |w| (sets the fixed-point scale of K2)
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < p.n_part;
        i0 += BUCKET_UNROLL * T) {
     int tile[BUCKET_UNROLL];
@@ -81,12 +83,19 @@ __global__ void __launch_bounds__(256) bucket_count_kernel(PaintParams p, TileGe
         const float py = grid_pos(p.y[i * p.stride], p.ymin, p.inv);
         const float pz = grid_pos(p.z[i * p.stride], p.zmin, p.inv);
         tile[u] = tile_of<ORDER, REFCIC>(px, py, pz, g, blockIdx.x);
+        if (p.w) {
+          const float a = fabsf(p.w[i]);
+          if (a < 3.0e38f) wmax = fmaxf(wmax, a);     // ignores inf / NaN
+        }
       }
     }
 #pragma unroll
     for (int u = 0; u < BUCKET_UNROLL; ++u)
       if (tile[u] >= 0) atomicAdd(counts + tile[u], 1u);
   }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
+  if ((threadIdx.x & 31) == 0) atomicMax(wmax_bits, __float_as_uint(wmax));   // non-negative floats order as uints
 }
 
 // ---------------------------------------------------------------- K1b: exclusive scan
@@ -326,183 +335,143 @@ __global__ void __launch_bounds__(256) paint_tile_kernel(const float4* __restric
   }
 }
 
-// ---------------------------------------------------------------- K2 (v2): cell-ordered deposit
-// paint_tile (above) is bound by the shared-memory pipe: a warp-wide CAS-add on 32 random cells of
-// the tile costs ~13 wavefronts (bank conflicts on the read and on the CAS; ncu: 0.93 wavefronts
-// per clock per SM).  Here each chunk of <= CELL_CHUNK particles is first counting-sorted by anchor
-// cell inside shared memory (packed 16-bit counters, one native integer atomic per particle), so
-// that the 32 lanes of a warp deposit particles of consecutive cells: for a given stencil offset
-// their addresses are consecutive words of a few z-rows -> (almost) conflict free.
-constexpr int CELL_CHUNK = 2048;
-constexpr int CELL_PT = CELL_CHUNK / 256;          // particles per thread in the sort phases
-constexpr int CELLS = TILE * TILE * TILE;          // 4096 anchor cells per tile
-
-template <int ORDER, bool REFCIC>
-__device__ __forceinline__ int anchor_cell(const float4& r, const TileGeom& g, int ox, int oy, int oz) {
-  const int ax = local_plane(anchor_axis<ORDER, REFCIC>(r.x, g.n), g.x0, g.nx, g.n) - ox;
-  const int ay = anchor_axis<ORDER, REFCIC>(r.y, g.n) - oy;
-  const int az = anchor_axis<ORDER, REFCIC>(r.z, g.n) - oz;
-  return (ax * TILE + ay) * TILE + az;             // in [0, CELLS) for every particle of this bucket
-}
-
-template <int ORDER, bool REFCIC>
-__device__ __forceinline__ void deposit_to_tile(const float4& r, float* tile, const TileGeom& g, int wrap,
-                                                int variant, int ox, int oy, int oz) {
-  constexpr int L = TILE + ORDER - 1;
-  constexpr int LP = (L + 3) & ~3;
-  const int n = g.n;
-  if (REFCIC) {
-    int x0, x1, y0, y1, z0, z1;
-    float mdx, ddx, mdy, ddy, mdz, ddz;
-    cic_reference_axis(r.x, n, wrap, variant, x0, x1, mdx, ddx);
-    cic_reference_axis(r.y, n, wrap, variant, y0, y1, mdy, ddy);
-    cic_reference_axis(r.z, n, wrap, variant, z0, z1, mdz, ddz);
-    float* c = tile + ((local_plane(x0, g.x0, g.nx, n) - ox) * L + (y0 - oy)) * LP + (z0 - oz);
-    const float wgt = r.w;
-    constexpr int SX = L * LP, SY = LP;
-    atomicAdd(c, ((mdx * mdy) * mdz) * wgt);
-    atomicAdd(c + SX, ((ddx * mdy) * mdz) * wgt);
-    atomicAdd(c + SY, ((mdx * ddy) * mdz) * wgt);
-    atomicAdd(c + 1, ((mdx * mdy) * ddz) * wgt);
-    atomicAdd(c + SX + SY, ((ddx * ddy) * mdz) * wgt);
-    atomicAdd(c + SX + 1, ((ddx * mdy) * ddz) * wgt);
-    atomicAdd(c + SY + 1, ((mdx * mdy) * ddz) * wgt);       // Q1 (reference weight)
-    atomicAdd(c + SX + SY + 1, ((ddx * ddy) * ddz) * wgt);
-  } else {
-    int ax, ay, az;
-    float wx[ORDER], wy[ORDER], wz[ORDER];
-    tile_axis<ORDER>(r.x, n, wrap, ax, wx);
-    tile_axis<ORDER>(r.y, n, wrap, ay, wy);
-    tile_axis<ORDER>(r.z, n, wrap, az, wz);
-    float* c = tile + ((local_plane(ax, g.x0, g.nx, n) - ox) * L + (ay - oy)) * LP + (az - oz);
-#pragma unroll
-    for (int a = 0; a < ORDER; ++a) {
-#pragma unroll
-      for (int b = 0; b < ORDER; ++b) {
-        const float wxy = wx[a] * wy[b];
-#pragma unroll
-        for (int cc = 0; cc < ORDER; ++cc) atomicAdd(c + (a * L + b) * LP + cc, (wxy * wz[cc]) * r.w);
-      }
-    }
-  }
-}
-
+// ---------------------------------------------------------------- K2 (v3): fixed-point deposit
+// Shared-memory float atomicAdd is a compare-and-swap loop on sm_100a (ATOMS.CAST.SPIN); the only
+// native shared atomic add is the 32-bit integer one (ATOMS.ADD), measured 2x faster and immune to
+// same-address retries.  So the tile is accumulated in 64-bit fixed point held as two 32-bit words
+// per cell: lo += v_lo (native atomic, returns the old value -> carry), hi += v_hi + carry (native,
+// only when non-zero: ~4% of the updates).  Each contribution is the SAME float32 product the
+// reference forms, scaled by a power of two 2^(32-e) with 2^e >= max|w| (exact in float32) and
+// rounded to an integer, i.e. quantised at 2^-32 of the largest weight -- far below float32
+// resolution -- and integer addition is associative, so the tile sum is independent of the order
+// in which particles arrive (the float32 path is only reproducible to ~1e-7).
+// A cleverer ordering of the particles (in-tile counting sort by cell, tried in round 1) was
+// SLOWER with float CAS: adjacent lanes then hit the same cell and every collision costs a full
+// CAS retry; with native integer atomics ordering no longer matters.
 template <int ORDER>
-__device__ __forceinline__ void flush_tile(const float* tile, const TileGeom& g, int ox, int oy, int oz,
-                                           int mesh_vec_ok, float* __restrict__ mesh) {
-  constexpr int L = TILE + ORDER - 1;
-  constexpr int LP = (L + 3) & ~3;
-  const int n = g.n;
-  const size_t n2 = (size_t)n * n;
-  const bool vec_ok = (n % 4 == 0) && mesh_vec_ok;
-  constexpr int NV = TILE / 4;
-  constexpr int ROW_ITEMS = NV + (ORDER - 1);
-  for (int item = threadIdx.x; item < L * L * ROW_ITEMS; item += blockDim.x) {
-    const int q = item % ROW_ITEMS;
-    const int row = item / ROW_ITEMS;
-    const int j = row % L, i = row / L;
-    int gx = ox + i;
-    if (g.nx == n) gx %= n;
-    else if (gx >= g.nx) continue;
-    const int gy = (oy + j) % n;
-    float* grow = mesh + (size_t)gx * n2 + (size_t)gy * n;
-    const float* trow = tile + (i * L + j) * LP;
-    if (q < NV) {
-      const int k = q * 4;
-      const float4 v = *reinterpret_cast<const float4*>(trow + k);
-      if (v.x == 0.0f && v.y == 0.0f && v.z == 0.0f && v.w == 0.0f) continue;
-      const int gz = oz + k;
-      if (vec_ok && gz + 3 < n) {
-        red_v4(grow + gz, v.x, v.y, v.z, v.w);
-      } else {
-        if (v.x != 0.0f) atomicAdd(grow + (gz % n), v.x);
-        if (v.y != 0.0f) atomicAdd(grow + ((gz + 1) % n), v.y);
-        if (v.z != 0.0f) atomicAdd(grow + ((gz + 2) % n), v.z);
-        if (v.w != 0.0f) atomicAdd(grow + ((gz + 3) % n), v.w);
-      }
-    } else {
-      const int k = TILE + (q - NV);
-      const float v = trow[k];
-      if (v != 0.0f) atomicAdd(grow + ((oz + k) % n), v);
-    }
-  }
+struct TileDims {
+  static constexpr int L = TILE + ORDER - 1;
+  static constexpr int LP = (L + 3) & ~3;
+  static constexpr int CELLS = L * L * LP;
+};
+
+__device__ __forceinline__ void fx_add(unsigned* __restrict__ lo, unsigned* __restrict__ hi, int idx, float v) {
+  const long long q = __float2ll_rn(v);
+  if (q == 0) return;
+  const unsigned ql = (unsigned)q, qh = (unsigned)((unsigned long long)q >> 32);
+  const unsigned old = atomicAdd(lo + idx, ql);
+  const unsigned h = qh + ((old + ql) < old ? 1u : 0u);      // carry out of the low word
+  if (h) atomicAdd(hi + idx, h);
 }
 
 template <int ORDER, bool REFCIC>
-__global__ void __launch_bounds__(256) paint_tile_cellsort_kernel(const float4* __restrict__ sorted,
-                                                                  const unsigned* __restrict__ offsets,
-                                                                  TileGeom g, int wrap, int variant,
-                                                                  int mesh_vec_ok, float* __restrict__ mesh) {
-  constexpr int L = TILE + ORDER - 1;
-  constexpr int LP = (L + 3) & ~3;
-  __shared__ __align__(16) float tile[L * L * LP];
-  __shared__ unsigned cnt[CELLS / 2];              // two 16-bit counters per word
-  __shared__ unsigned short perm[CELL_CHUNK];
-  __shared__ unsigned warp_tot[8];
+__global__ void __launch_bounds__(256) paint_tile_fx_kernel(const float4* __restrict__ sorted,
+                                                            const unsigned* __restrict__ offsets,
+                                                            TileGeom g, int wrap, int variant,
+                                                            int mesh_vec_ok,
+                                                            const unsigned* __restrict__ wmax_bits,
+                                                            float* __restrict__ mesh) {
+  constexpr int L = TileDims<ORDER>::L, LP = TileDims<ORDER>::LP, NC = TileDims<ORDER>::CELLS;
+  extern __shared__ __align__(16) unsigned fx_smem[];
+  unsigned* lo = fx_smem;
+  unsigned* hi = fx_smem + NC;
   const int t = blockIdx.x;
   const unsigned beg = offsets[t * g.rep], end = offsets[(t + 1) * g.rep];
   if (beg == end) return;
   const int tz = t % g.nt, ty = (t / g.nt) % g.nt, tx = t / (g.nt * g.nt);
   const int ox = tx * TILE, oy = ty * TILE, oz = tz * TILE;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < L * L * LP; i += 256) tile[i] = 0.0f;
+  const int n = g.n;
+  for (int i = threadIdx.x; i < 2 * NC; i += blockDim.x) fx_smem[i] = 0u;
+  // power-of-two scale: 2^e >= max|w|  ->  |contribution| * 2^(32-e) <= 2^32
+  float wmax = __uint_as_float(*wmax_bits);
+  if (!(wmax > 0.0f) || !(wmax < 3.0e38f)) wmax = 1.0f;
+  int e;
+  frexpf(wmax, &e);
+  e = max(-90, min(90, e));
+  const float scale = ldexpf(1.0f, 32 - e);
   __syncthreads();
 
-  for (unsigned c0 = beg; c0 < end; c0 += CELL_CHUNK) {
-    const int m = (int)min((unsigned)CELL_CHUNK, end - c0);
-    if (m < 256) {                                 // not worth sorting
-      for (int j = tid; j < m; j += 256)
-        deposit_to_tile<ORDER, REFCIC>(sorted[c0 + j], tile, g, wrap, variant, ox, oy, oz);
-      __syncthreads();
-      continue;
-    }
-    for (int i = tid; i < CELLS / 2; i += 256) cnt[i] = 0u;
-    __syncthreads();
-    unsigned key[CELL_PT];
+  for (unsigned i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    const float4 r = sorted[i];
+    if (REFCIC) {
+      int x0, x1, y0, y1, z0, z1;
+      float mdx, ddx, mdy, ddy, mdz, ddz;
+      cic_reference_axis(r.x, n, wrap, variant, x0, x1, mdx, ddx);
+      cic_reference_axis(r.y, n, wrap, variant, y0, y1, mdy, ddy);
+      cic_reference_axis(r.z, n, wrap, variant, z0, z1, mdz, ddz);
+      const int c = ((local_plane(x0, g.x0, g.nx, n) - ox) * L + (y0 - oy)) * LP + (z0 - oz);
+      const float wgt = r.w;
+      constexpr int SX = L * LP, SY = LP;
+      // the float32 products of src/mas.py:142-151 (left to right), then the exact power-of-two scale
+      fx_add(lo, hi, c, (((mdx * mdy) * mdz) * wgt) * scale);
+      fx_add(lo, hi, c + SX, (((ddx * mdy) * mdz) * wgt) * scale);
+      fx_add(lo, hi, c + SY, (((mdx * ddy) * mdz) * wgt) * scale);
+      fx_add(lo, hi, c + 1, (((mdx * mdy) * ddz) * wgt) * scale);
+      fx_add(lo, hi, c + SX + SY, (((ddx * ddy) * mdz) * wgt) * scale);
+      fx_add(lo, hi, c + SX + 1, (((ddx * mdy) * ddz) * wgt) * scale);
+      fx_add(lo, hi, c + SY + 1, (((mdx * mdy) * ddz) * wgt) * scale);     // Q1 (reference weight)
+      fx_add(lo, hi, c + SX + SY + 1, (((ddx * ddy) * ddz) * wgt) * scale);
+    } else {
+      int ax, ay, az;
+      float wx[ORDER], wy[ORDER], wz[ORDER];
+      tile_axis<ORDER>(r.x, n, wrap, ax, wx);
+      tile_axis<ORDER>(r.y, n, wrap, ay, wy);
+      tile_axis<ORDER>(r.z, n, wrap, az, wz);
+      const int c = ((local_plane(ax, g.x0, g.nx, n) - ox) * L + (ay - oy)) * LP + (az - oz);
 #pragma unroll
-    for (int u = 0; u < CELL_PT; ++u) {
-      const int idx = u * 256 + tid;
-      key[u] = 0xffffffffu;
-      if (idx < m) {
-        const int cid = anchor_cell<ORDER, REFCIC>(sorted[c0 + idx], g, ox, oy, oz);
-        const int sh = (cid & 1) * 16;
-        const unsigned old = atomicAdd(&cnt[cid >> 1], 1u << sh);
-        key[u] = (unsigned)cid | (((old >> sh) & 0xffffu) << 12);
+      for (int a = 0; a < ORDER; ++a) {
+#pragma unroll
+        for (int b = 0; b < ORDER; ++b) {
+          const float wxy = wx[a] * wy[b];
+#pragma unroll
+          for (int cc = 0; cc < ORDER; ++cc)
+            fx_add(lo, hi, c + (a * L + b) * LP + cc, ((wxy * wz[cc]) * r.w) * scale);
+        }
       }
     }
-    __syncthreads();
-    {                                              // exclusive scan of the 4096 counters, in place
-      unsigned w[8];
-      unsigned tot = 0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        w[q] = cnt[tid * 8 + q];
-        tot += (w[q] & 0xffffu) + (w[q] >> 16);
-      }
-      unsigned total;
-      unsigned run = block_exclusive_scan_256(tot, warp_tot, total);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const unsigned lo = w[q] & 0xffffu, hi = w[q] >> 16;
-        cnt[tid * 8 + q] = run | ((run + lo) << 16);
-        run += lo + hi;
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < CELL_PT; ++u) {
-      if (key[u] != 0xffffffffu) {
-        const int cid = key[u] & 0xfff;
-        const unsigned start = (cnt[cid >> 1] >> ((cid & 1) * 16)) & 0xffffu;
-        perm[start + (key[u] >> 12)] = (unsigned short)(u * 256 + tid);
-      }
-    }
-    __syncthreads();
-    for (int j = tid; j < m; j += 256)
-      deposit_to_tile<ORDER, REFCIC>(sorted[c0 + perm[j]], tile, g, wrap, variant, ox, oy, oz);
-    __syncthreads();
   }
-  flush_tile<ORDER>(tile, g, ox, oy, oz, mesh_vec_ok, mesh);
+  __syncthreads();
+
+  // flush: fixed point -> float32 (one rounding), 16-byte vector reds where aligned
+  const double inv_scale = (double)ldexpf(1.0f, e - 32);
+  const size_t n2 = (size_t)n * n;
+  const bool vec_ok = (n % 4 == 0) && mesh_vec_ok;
+  constexpr int NV = TILE / 4;
+  constexpr int ROW_ITEMS = NV + (ORDER - 1);
+  auto cell = [&](int idx) -> float {
+    const unsigned l = lo[idx], h = hi[idx];
+    if ((l | h) == 0u) return 0.0f;
+    return (float)((double)(long long)(((unsigned long long)h << 32) | l) * inv_scale);
+  };
+  for (int item = threadIdx.x; item < L * L * ROW_ITEMS; item += blockDim.x) {
+    const int q = item % ROW_ITEMS;
+    const int row = item / ROW_ITEMS;
+    const int j = row % L, i = row / L;
+    int gx = ox + i;                               // local plane
+    if (g.nx == n) gx %= n;                        // full mesh: periodic in x
+    else if (gx >= g.nx) continue;                 // slab: ghost planes are part of the allocation
+    const int gy = (oy + j) % n;
+    float* grow = mesh + (size_t)gx * n2 + (size_t)gy * n;
+    const int tbase = (i * L + j) * LP;
+    if (q < NV) {
+      const int k = q * 4;
+      const float vx = cell(tbase + k), vy = cell(tbase + k + 1), vz = cell(tbase + k + 2), vw = cell(tbase + k + 3);
+      if (vx == 0.0f && vy == 0.0f && vz == 0.0f && vw == 0.0f) continue;
+      const int gz = oz + k;
+      if (vec_ok && gz + 3 < n) {
+        red_v4(grow + gz, vx, vy, vz, vw);
+      } else {
+        if (vx != 0.0f) atomicAdd(grow + (gz % n), vx);
+        if (vy != 0.0f) atomicAdd(grow + ((gz + 1) % n), vy);
+        if (vz != 0.0f) atomicAdd(grow + ((gz + 2) % n), vz);
+        if (vw != 0.0f) atomicAdd(grow + ((gz + 3) % n), vw);
+      }
+    } else {
+      const int k = TILE + (q - NV);
+      const float v = cell(tbase + k);
+      if (v != 0.0f) atomicAdd(grow + ((oz + k) % n), v);
+    }
+  }
 }
 
 // Particles the tile kernel cannot take (reference-compat CIC outside the box): the last bucket,
@@ -539,7 +508,7 @@ __global__ void __launch_bounds__(256) paint_outliers_kernel(const float4* __res
 
 // ---------------------------------------------------------------- host side
 struct SortedLayout {
-  size_t sorted, counts, offsets, cursor, block_tot, total;
+  size_t sorted, counts, offsets, cursor, block_tot, wmax, total;
   int nbuckets;
 };
 
@@ -560,6 +529,7 @@ static SortedLayout sorted_layout(int n, int nx, int64_t n_part) {
   L.offsets = take((size_t)(L.nbuckets + 1) * 4);
   L.cursor = take((size_t)(L.nbuckets + 1) * 4);
   L.block_tot = take((size_t)(L.nbuckets / 2048 + 4) * 4);
+  L.wmax = take(256);
   L.total = off;
   return L;
 }
@@ -579,13 +549,15 @@ static int run_sorted(const PaintParams& p, const TileGeom& g, const SortedLayou
   const int threads = 256;
   const int64_t want = (p.n_part + (int64_t)threads * BUCKET_UNROLL - 1) / ((int64_t)threads * BUCKET_UNROLL);
   const int blocks = (int)std::min<int64_t>(want, (int64_t)kNumSMs * 8 * 2);
+  unsigned* wmax_bits = (unsigned*)(ws + L.wmax);
   {
     ScopedLaunch T(K_MEMSET, s);
     JPS_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)(L.nbuckets + 1) * 4, s));
+    JPS_CHECK_CUDA(cudaMemsetAsync(wmax_bits, 0, 4, s));
   }
   {
     ScopedLaunch T(K_BUCKET_COUNT, s);
-    bucket_count_kernel<ORDER, REFCIC><<<blocks, threads, 0, s>>>(p, g, counts);
+    bucket_count_kernel<ORDER, REFCIC><<<blocks, threads, 0, s>>>(p, g, counts, wmax_bits);
   }
   JPS_CHECK_LAUNCH();
   {
@@ -605,12 +577,20 @@ static int run_sorted(const PaintParams& p, const TileGeom& g, const SortedLayou
     ScopedLaunch T(K_PAINT_TILE, s);
     const int mesh_vec_ok = (((uintptr_t)p.mesh) & 15) == 0 ? 1 : 0;
     static const bool plain = [] { const char* e = getenv("JPS_TILE_KERNEL"); return e && !strcmp(e, "plain"); }();
-    if (plain)
+    if (plain) {
       paint_tile_kernel<ORDER, REFCIC><<<g.ntiles, 256, 0, s>>>(sorted, offsets, g, p.wrap, p.variant,
                                                               mesh_vec_ok, p.mesh);
-    else
-      paint_tile_cellsort_kernel<ORDER, REFCIC><<<g.ntiles, 256, 0, s>>>(sorted, offsets, g, p.wrap, p.variant,
-                                                                       mesh_vec_ok, p.mesh);
+    } else {
+      constexpr int smem = 2 * TileDims<ORDER>::CELLS * (int)sizeof(unsigned);
+      static bool attr_set = false;
+      if (!attr_set) {
+        JPS_CHECK_CUDA(cudaFuncSetAttribute(paint_tile_fx_kernel<ORDER, REFCIC>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+      }
+      paint_tile_fx_kernel<ORDER, REFCIC><<<g.ntiles, 256, smem, s>>>(sorted, offsets, g, p.wrap, p.variant,
+                                                                    mesh_vec_ok, wmax_bits, p.mesh);
+    }
   }
   JPS_CHECK_LAUNCH();
   if (REFCIC) {
