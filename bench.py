@@ -43,6 +43,8 @@ UNIT = "Gparticles/s"
 
 # ---- workload C2 (BASELINE.json configs[1])
 C2 = dict(name="C2", n_part=100_000_000, n_mesh=512, box=2000.0, order=3, seed=5, gen_grid=256)
+# ---- workload C4 (BASELINE.json configs[3]): ONE mesh slab-sharded over the GPUs (strong scaling)
+C4 = dict(name="C4", n_part=1_000_000_000, n_mesh=2048, box=2000.0, order=4, seed=42)
 
 
 def k_edges_for(box, n_mesh):
@@ -362,6 +364,104 @@ def run_gpu_arm(a, wl):
     return 0
 
 
+def run_slab_arm(a, wl):
+    """--workload c4: 1e9 uniform particles, PCS on 2048^3, ONE mesh sharded in x-slabs over the ranks
+    (jax_powspec_b200/slab.py): halo exchange + all-to-all transpose + allreduce are inside the step."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from jax_powspec_b200 import _lib
+    from jax_powspec_b200.slab import SlabPipeline, halo_exchange_add, transpose_all_to_all
+    n, box, order = wl["n_mesh"], wl["box"], wl["order"]
+    nloc = wl["n_part"] // world
+    g = torch.Generator(device=dev)
+    g.manual_seed(wl["seed"] + rank)
+    w_slab = box / world
+    hi = float(np.nextafter(np.float32((rank + 1) * w_slab), np.float32(0)))
+    x = (torch.rand(nloc, generator=g, device=dev) * w_slab + rank * w_slab).clamp_(max=hi)
+    y = torch.rand(nloc, generator=g, device=dev) * box
+    z = torch.rand(nloc, generator=g, device=dev) * box
+    for t in (y, z):
+        t[t >= box] = 0.0
+    pipe = SlabPipeline(n, box, k_edges_for(box, n), order=order, compat="fixed", method=a.method)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        pipe(x, y, z)
+    sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.profile_enable(False); _lib.profile_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for _ in range(a.steps):
+        k3d, pk, nm = pipe(x, y, z)
+    e1.record()
+    sync()
+    t = torch.tensor([e0.elapsed_time(e1) / a.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    counts = _lib.profile_snapshot()
+    launches = sum(c for k, (c, _) in counts.items() if k not in _lib.LIBRARY_KERNELS and k != "misc")
+    stages = {}
+
+    def timed(name, fn):
+        sync()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(); fn(); s1.record(); sync()
+        tt = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        stages[name] = float(tt.item())
+
+    timed("paint", lambda: pipe.stage_paint(x, y, z))
+    if world > 1:
+        timed("halo_exchange", lambda: halo_exchange_add(pipe.mesh, pipe.nxl))
+    timed("fft_yz_pack", pipe.stage_fft_yz_pack)
+    if world > 1:
+        timed("all_to_all", lambda: transpose_all_to_all(pipe.buf_b, pipe.buf_a))
+    timed("fft_x", pipe.stage_fft_x)
+    timed("bin_partial", lambda: pipe.stage_partial(True))
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        a2a = (world - 1) / world ** 2 * 8 * n * n * (n // 2 + 1)
+        paint_bytes = 12 * nloc + 4 * n ** 3 / world
+        line = {
+            "metric": METRIC, "value": wl["n_part"] / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
+            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C4: {wl['n_part']:.3g} uniform particles generated per rank inside its x-slab, "
+                                   f"{ {2: 'CIC', 3: 'TSC', 4: 'PCS'}[order] } on {n}^3, slab-sharded paint + distributed R2C FFT "
+                                   f"(2-D local, NCCL all-to-all, 1-D local) + multipoles",
+                       "n_part_total": wl["n_part"], "n_mesh": n, "box_size": box, "mas_order": order,
+                       "parallelism": f"{world} x-slabs, halo ring exchange + all-to-all + allreduce per step"},
+            "clocks": clocks, "gpu_launches": int(launches), "stages_ms_max_over_ranks": stages,
+            "all_to_all": {"bytes_per_rank": a2a, "achieved_gbs_per_rank": (a2a / stages["all_to_all"] / 1e6) if world > 1 else None,
+                           "nvlink_peer_copy_ref_gbs": 770.0},
+            "roofline": {"kernel": "paint (bucket + tile deposit)", "bound": "hbm", "achieved": paint_bytes / stages["paint"] / 1e6,
+                         "peak": peak, "unit": "GB/s", "frac": paint_bytes / stages["paint"] / 1e6 / peak, "traffic": None,
+                         "peak_source": peak_src},
+            "check": {"P0_first_bins": [float(v) for v in pk[:3, 0].cpu()], "Nmodes_first_bins": [float(v) for v in nm[:3].cpu()]},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -380,8 +480,13 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="stop after the device-resident timed region (ncu runs)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+                    help="c2: one realisation per GPU (default, weak scaling); c4: one slab-sharded mesh (strong scaling)")
+    ap.add_argument("--order", type=int, default=None)
     a = ap.parse_args()
-    wl = dict(C2)
+    wl = dict(C4 if a.workload == "c4" else C2)
+    if a.order:
+        wl["order"] = a.order
     if a.n_part:
         wl["n_part"] = int(a.n_part)
     if a.n_mesh:
@@ -392,7 +497,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(free_port()), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
-    return run_gpu_arm(a, wl)
+    return run_slab_arm(a, wl) if a.workload == "c4" else run_gpu_arm(a, wl)
 
 
 if __name__ == "__main__":

@@ -267,21 +267,51 @@ class PaintPowspec:
                                     ptr(self.sums), ptr(self.counts), stream_ptr()), "jps_paint_powspec")
         return self.k3d, self.pk, self.nm
 
+    # ---- the same pipeline in pieces (HostPipeline streams the catalogue through these)
+    def paint_chunk(self, x, y, z, w=None, xmin=0.0, ymin=0.0, zmin=0.0):
+        """self.mesh += deposit of one piece of the catalogue (zero self.mesh before the first piece)."""
+        x, y, z, stride = _common_stride(x, y, z)
+        npart = x.numel()
+        need = C.c_size_t(0)
+        check(lib.jps_paint_workspace_bytes(self.n, npart, self.order, _lib.METHOD[self.method], C.byref(need)))
+        if need.value > self.ws_bytes:
+            self.reserve(npart)
+        check(lib.jps_paint(self.n, ptr(x), ptr(y), ptr(z), ptr(w), stride, npart, float(xmin), float(ymin),
+                            float(zmin), self.box, self.order, int(self.wrap), _lib.COMPAT[self.compat],
+                            _lib.VARIANT_VEC, _lib.METHOD[self.method], ptr(self.mesh), ptr(self.ws), self.ws_bytes,
+                            stream_ptr()), "jps_paint")
+
+    def finish(self):
+        """FFT + multipoles of self.mesh (density contrast folded in through the DC mode)."""
+        check(lib.jps_powspec(self.plan.handle, ptr(self.mesh), 1, self.box, _edge_ptr(self.edges), self.nb,
+                              self.order, self.shot_noise, ptr(self.k3d), ptr(self.pk), ptr(self.nm),
+                              ptr(self.sums), ptr(self.counts), stream_ptr()), "jps_powspec")
+        return self.k3d, self.pk, self.nm
+
 
 class HostPipeline:
-    """End-to-end call for catalogues that live in HOST memory (what a user of the reference
-    has after np.loadtxt, tests/correlations.py:29-31): host->device copy of x, y, z[, w],
-    the fused device pipeline, device->host copy of (k3D, Pk3D, Nmodes3D).  Device staging
-    buffers and pinned result buffers are allocated once."""
+    """End-to-end call for catalogues that live in HOST memory (what a user of the reference has
+    after np.loadtxt, tests/correlations.py:29-31): host->device copy of x, y, z[, w], paint,
+    FFT, multipoles, device->host copy of (k3D, Pk3D, Nmodes3D).
 
-    def __init__(self, pipe: PaintPowspec, n_part_max: int, weighted: bool = False):
+    The catalogue is streamed in ``n_chunks`` pieces: a copy stream moves piece c+1 over PCIe
+    while the compute stream buckets and paints piece c into the (accumulating) mesh, so the
+    step costs max(H2D, compute) instead of their sum.  Device staging buffers and pinned result
+    buffers are allocated once."""
+
+    def __init__(self, pipe: PaintPowspec, n_part_max: int, weighted: bool = False, n_chunks: int = 8):
         self.pipe = pipe
         d = pipe.device
         self.cap = int(n_part_max)
+        self.n_chunks = max(1, int(n_chunks))
         self.dev = [torch.empty(self.cap, dtype=torch.float32, device=d) for _ in range(4 if weighted else 3)]
         self.k3d = torch.empty(pipe.nb, dtype=torch.float32).pin_memory()
         self.pk = torch.empty((pipe.nb, 3), dtype=torch.float32).pin_memory()
         self.nm = torch.empty(pipe.nb, dtype=torch.float32).pin_memory()
+        self.copy_stream = torch.cuda.Stream(device=d)
+        self.paint_done = None                      # event: previous step no longer reads self.dev
+        chunk = -(-self.cap // self.n_chunks)
+        pipe.reserve(chunk)
 
     def __call__(self, x, y, z, w=None, xmin=0.0, ymin=0.0, zmin=0.0):
         """x, y, z[, w]: host arrays (NumPy or torch, ideally pinned).  Returns NumPy arrays."""
@@ -289,16 +319,36 @@ class HostPipeline:
         n = len(x)
         if n > self.cap or len(host) > len(self.dev):
             raise ValueError("HostPipeline: catalogue larger than the buffers it was built for")
-        dev = []
-        for h, d in zip(host, self.dev):
-            t = h if isinstance(h, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(h, dtype=np.float32))
-            d[:n].copy_(t, non_blocking=True)
-            dev.append(d[:n])
-        k3d, pk, nm = self.pipe(dev[0], dev[1], dev[2], dev[3] if w is not None else None, xmin, ymin, zmin)
+        host = [h if isinstance(h, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(h, dtype=np.float32))
+                for h in host]
+        p = self.pipe
+        compute = torch.cuda.current_stream(p.device)
+        nchunks = min(self.n_chunks, max(1, n // 65536))
+        bounds = [n * c // nchunks for c in range(nchunks + 1)]
+        ready = []
+        with torch.cuda.stream(self.copy_stream):
+            if self.paint_done is not None:
+                self.copy_stream.wait_event(self.paint_done)
+            for c in range(nchunks):
+                lo, hi = bounds[c], bounds[c + 1]
+                for h, d in zip(host, self.dev):
+                    d[lo:hi].copy_(h[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+                ready.append(ev)
+        p.mesh.zero_()
+        for c in range(nchunks):
+            lo, hi = bounds[c], bounds[c + 1]
+            compute.wait_event(ready[c])
+            wd = self.dev[3][lo:hi] if w is not None else None
+            p.paint_chunk(self.dev[0][lo:hi], self.dev[1][lo:hi], self.dev[2][lo:hi], wd, xmin, ymin, zmin)
+        self.paint_done = torch.cuda.Event()
+        self.paint_done.record(compute)
+        k3d, pk, nm = p.finish()
         self.k3d.copy_(k3d, non_blocking=True)
         self.pk.copy_(pk, non_blocking=True)
         self.nm.copy_(nm, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        compute.synchronize()
         return self.k3d.numpy(), self.pk.numpy(), self.nm.numpy()
 
 

@@ -137,7 +137,8 @@ class SlabPipeline:
         self.mesh = torch.empty((self.nxa, self.n, self.n), dtype=torch.float32, device=d)
         cshape = (self.world, self.nxl, self.nxl, self.nz)
         self.buf_a = torch.empty(cshape, dtype=torch.complex64, device=d)     # yz-transformed / receive
-        self.buf_b = torch.empty(cshape, dtype=torch.complex64, device=d)     # packed send buffer
+        # packed send buffer; with one rank pack + all-to-all are the identity and are skipped
+        self.buf_b = None if self.single else torch.empty(cshape, dtype=torch.complex64, device=d)
         nbytes = C.c_size_t(0)
         with torch.cuda.device(d):
             check(lib.jps_slab_plan_workspace_bytes(self.n, self.world, C.byref(nbytes)))
@@ -187,7 +188,8 @@ class SlabPipeline:
 
     def stage_fft_yz_pack(self):
         check(lib.jps_slab_fft_yz(self.handle, ptr(self.owned()), ptr(self.buf_a), stream_ptr()), "jps_slab_fft_yz")
-        check(lib.jps_slab_pack(self.handle, ptr(self.buf_a), ptr(self.buf_b), stream_ptr()), "jps_slab_pack")
+        if not self.single:
+            check(lib.jps_slab_pack(self.handle, ptr(self.buf_a), ptr(self.buf_b), stream_ptr()), "jps_slab_pack")
 
     def stage_fft_x(self):
         check(lib.jps_slab_fft_x(self.handle, ptr(self.buf_a), stream_ptr()), "jps_slab_fft_x")
@@ -214,7 +216,8 @@ class SlabPipeline:
         if not self.single:
             halo_exchange_add(self.mesh, self.nxl)
         self.stage_fft_yz_pack()
-        transpose_all_to_all(self.buf_b, self.buf_a)
+        if not self.single:
+            transpose_all_to_all(self.buf_b, self.buf_a)
         self.stage_fft_x()
         if self.rank == 0:
             self.dc.copy_(self.local_dc())
@@ -240,9 +243,10 @@ def run_virtual_ranks(pipes, catalogs, xmin=0.0):
             p.mesh[p.gl: p.gl + GHOST_HI] += his[(r - 1) % P]
     for p in pipes:
         p.stage_fft_yz_pack()
-    for q, dst in enumerate(pipes):                      # all-to-all: block q of rank r -> rank q, slot r
-        for r, src in enumerate(pipes):
-            dst.buf_a[r].copy_(src.buf_b[q])
+    if P > 1:
+        for q, dst in enumerate(pipes):                  # all-to-all: block q of rank r -> rank q, slot r
+            for r, src in enumerate(pipes):
+                dst.buf_a[r].copy_(src.buf_b[q])
     for p in pipes:
         p.stage_fft_x()
     dc = pipes[0].local_dc().clone()

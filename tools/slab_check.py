@@ -59,7 +59,7 @@ from jax_powspec_b200.slab import halo_exchange_add, transpose_all_to_all
 timed("paint", lambda: pipe.stage_paint(x, y, z))
 if world > 1: timed("halo", lambda: halo_exchange_add(pipe.mesh, pipe.nxl))
 timed("fft_yz_pack", pipe.stage_fft_yz_pack)
-timed("all_to_all", lambda: transpose_all_to_all(pipe.buf_b, pipe.buf_a))
+if world > 1: timed("all_to_all", lambda: transpose_all_to_all(pipe.buf_b, pipe.buf_a))
 timed("fft_x", pipe.stage_fft_x)
 timed("bin", lambda: pipe.stage_partial(True))
 res = {"n_gpus": world, "n_mesh": n, "n_part": npart, "order": a.order, "ms_per_step": ms,
