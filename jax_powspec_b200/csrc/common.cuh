@@ -87,6 +87,10 @@ struct ScopedLaunch {
 // Maximum number of distinct (reachable) k-bins the warp-private shared-memory
 // accumulators can hold; above it the binning kernel accumulates with global atomics.
 constexpr int kMaxSmemBins = 576;
+// Up to this many bins one shared accumulator set per CTA is used (shared atomics by segment
+// heads); above it the kernels fall back to global float64 reds.
+constexpr int kMaxBlockBins = 8192;
+enum AccMode { ACC_WARP = 0, ACC_BLOCK = 1, ACC_GLOBAL = 2 };
 constexpr int kMaxUserBins = 1 << 18;
 
 // bin-table kinds

@@ -54,18 +54,25 @@ struct PkParams {
   int npairs;
 };
 
-// K4: fold + bin.  SMEM = warp-private shared accumulators; otherwise global float64 reds.
-template <bool SMEM>
+// K4: fold + bin.  Accumulation MODE (chosen by the number of reachable bins):
+//   ACC_WARP   warp-private shared accumulators, plain += (no atomics)        nbc <= kMaxSmemBins
+//   ACC_BLOCK  one shared accumulator set per CTA, shared atomics by the few segment heads
+//   ACC_GLOBAL float64 global reds by the segment heads                      (huge bin counts)
+template <int MODE>
 __global__ void __launch_bounds__(256) pk_fold_bin_kernel(PkParams P) {
   extern __shared__ float sacc[];
+  constexpr bool SMEM = (MODE != ACC_GLOBAL);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
   const int nacc = P.nbc * 3;
-  float* my = sacc + (size_t)warp * nacc;
-  if (SMEM) {
+  float* my = sacc + (MODE == ACC_WARP ? (size_t)warp * nacc : 0);
+  if (MODE == ACC_WARP) {
     for (int i = lane; i < nacc; i += 32) my[i] = 0.0f;
     __syncwarp();
+  } else if (MODE == ACC_BLOCK) {
+    for (int i = threadIdx.x; i < nacc; i += blockDim.x) sacc[i] = 0.0f;
+    __syncthreads();
   }
   float scale2 = 1.0f;
   if (P.normalise) {
@@ -117,9 +124,12 @@ __global__ void __launch_bounds__(256) pk_fold_bin_kernel(PkParams P) {
       const unsigned heads = __ballot_sync(0xffffffffu, head);
       segmented_reduce<3>(v, heads, lane);
       if (head && cb >= 0) {
-        if (SMEM) {
+        if (MODE == ACC_WARP) {
           float* a = my + cb * 3;
           a[0] += v[0]; a[1] += v[1]; a[2] += v[2];
+        } else if (MODE == ACC_BLOCK) {
+          float* a = my + cb * 3;
+          atomicAdd(a + 0, v[0]); atomicAdd(a + 1, v[1]); atomicAdd(a + 2, v[2]);
         } else {
           double* a = P.acc + (size_t)cb * 4;
           atomicAdd(a + 0, (double)v[0]);
@@ -127,14 +137,15 @@ __global__ void __launch_bounds__(256) pk_fold_bin_kernel(PkParams P) {
           atomicAdd(a + 2, (double)v[2]);
         }
       }
-      if (SMEM) __syncwarp();
+      if (MODE == ACC_WARP) __syncwarp();
     }
   }
   if (SMEM) {
     __syncthreads();
+    const int nsets = (MODE == ACC_WARP) ? nwarps : 1;
     for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
       double s = 0.0;
-      for (int w = 0; w < nwarps; ++w) s += (double)sacc[(size_t)w * nacc + i];
+      for (int w = 0; w < nsets; ++w) s += (double)sacc[(size_t)w * nacc + i];
       if (s != 0.0) atomicAdd(P.acc + (size_t)(i / 3) * 4 + (i % 3), s);
     }
   }
@@ -348,26 +359,32 @@ static int bin_from_dk(jps_plan* plan, const BinTable& T, int normalise, int mas
   P.wl = plan->wlut + (size_t)(mas_order - 2) * plan->n;
   P.nbc = nbc; P.acc = plan->acc; P.normalise = normalise; P.npairs = npairs_for(plan->n);
   const int threads = 256, warps = threads / 32;
+  const int want = (P.npairs + warps - 1) / warps;
+  static bool attr_set = false;
+  if (!attr_set) {
+    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_fold_bin_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)((size_t)warps * kMaxSmemBins * 3 * sizeof(float))));
+    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_fold_bin_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)((size_t)kMaxBlockBins * 3 * sizeof(float))));
+    attr_set = true;
+  }
+  int per_sm = 1;
   if (nbc <= kMaxSmemBins) {
     const size_t smem = (size_t)warps * nbc * 3 * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-      JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_fold_bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)((size_t)warps * kMaxSmemBins * 3 * sizeof(float))));
-      attr_set = true;
-    }
-    int per_sm = 1;
-    JPS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_fold_bin_kernel<true>, threads, smem));
-    per_sm = std::max(per_sm, 1);
-    const int want = (P.npairs + warps - 1) / warps;
-    const int blocks = std::min(want, kNumSMs * per_sm);
+    JPS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_fold_bin_kernel<ACC_WARP>, threads, smem));
+    const int blocks = std::min(want, kNumSMs * std::max(per_sm, 1));
     ScopedLaunch L(K_PK_FOLD_BIN, s);
-    pk_fold_bin_kernel<true><<<blocks, threads, smem, s>>>(P);
+    pk_fold_bin_kernel<ACC_WARP><<<blocks, threads, smem, s>>>(P);
+  } else if (nbc <= kMaxBlockBins) {
+    const size_t smem = (size_t)nbc * 3 * sizeof(float);
+    JPS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_fold_bin_kernel<ACC_BLOCK>, threads, smem));
+    const int blocks = std::min(want, kNumSMs * std::max(per_sm, 1));
+    ScopedLaunch L(K_PK_FOLD_BIN, s);
+    pk_fold_bin_kernel<ACC_BLOCK><<<blocks, threads, smem, s>>>(P);
   } else {
-    const int want = (P.npairs + warps - 1) / warps;
     const int blocks = std::min(want, kNumSMs * 8);
     ScopedLaunch L(K_PK_FOLD_BIN, s);
-    pk_fold_bin_kernel<false><<<blocks, threads, 0, s>>>(P);
+    pk_fold_bin_kernel<ACC_GLOBAL><<<blocks, threads, 0, s>>>(P);
   }
   JPS_CHECK_LAUNCH();
   return JPS_OK;

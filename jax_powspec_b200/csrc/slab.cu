@@ -63,15 +63,19 @@ struct SlabPkParams {
 };
 
 // One warp per (a = |kx|, local y): folds the rows ix = a and ix = n-a, lanes along kz.
-template <bool SMEM>
+template <int MODE>
 __global__ void __launch_bounds__(256) pk_bin_ysharded_kernel(SlabPkParams P) {
   extern __shared__ float sacc[];
+  constexpr bool SMEM = (MODE != ACC_GLOBAL);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int nacc = P.nbc * 3;
-  float* my = sacc + (size_t)warp * nacc;
-  if (SMEM) {
+  float* my = sacc + (MODE == ACC_WARP ? (size_t)warp * nacc : 0);
+  if (MODE == ACC_WARP) {
     for (int i = lane; i < nacc; i += 32) my[i] = 0.0f;
     __syncwarp();
+  } else if (MODE == ACC_BLOCK) {
+    for (int i = threadIdx.x; i < nacc; i += blockDim.x) sacc[i] = 0.0f;
+    __syncthreads();
   }
   float scale2 = 1.0f;
   if (P.normalise) {
@@ -116,22 +120,26 @@ __global__ void __launch_bounds__(256) pk_bin_ysharded_kernel(SlabPkParams P) {
       const unsigned heads = __ballot_sync(0xffffffffu, head);
       segmented_reduce<3>(v, heads, lane);
       if (head && cb >= 0) {
-        if (SMEM) {
+        if (MODE == ACC_WARP) {
           float* q = my + cb * 3;
           q[0] += v[0]; q[1] += v[1]; q[2] += v[2];
+        } else if (MODE == ACC_BLOCK) {
+          float* q = my + cb * 3;
+          atomicAdd(q + 0, v[0]); atomicAdd(q + 1, v[1]); atomicAdd(q + 2, v[2]);
         } else {
           double* q = P.acc + (size_t)cb * 4;
           atomicAdd(q + 0, (double)v[0]); atomicAdd(q + 1, (double)v[1]); atomicAdd(q + 2, (double)v[2]);
         }
       }
-      if (SMEM) __syncwarp();
+      if (MODE == ACC_WARP) __syncwarp();
     }
   }
   if (SMEM) {
     __syncthreads();
+    const int nsets = (MODE == ACC_WARP) ? nwarps : 1;
     for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
       double s = 0.0;
-      for (int w = 0; w < nwarps; ++w) s += (double)sacc[(size_t)w * nacc + i];
+      for (int w = 0; w < nsets; ++w) s += (double)sacc[(size_t)w * nacc + i];
       if (s != 0.0) atomicAdd(P.acc + (size_t)(i / 3) * 4 + (i % 3), s);
     }
   }
@@ -297,23 +305,31 @@ extern "C" int jps_slab_powspec_partial(jps_slab_plan_t* p, const void* dk, cons
     const int threads = 256, warps = 8;
     const long long items = (long long)(p->n / 2 + 1) * p->nyl;
     const long long want = (items + warps - 1) / warps;
+    static bool attr_set = false;
+    if (!attr_set) {
+      JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)((size_t)warps * kMaxSmemBins * 3 * sizeof(float))));
+      JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)((size_t)kMaxBlockBins * 3 * sizeof(float))));
+      attr_set = true;
+    }
+    int per_sm = 1;
     if (T->nbc <= kMaxSmemBins) {
       const size_t smem = (size_t)warps * T->nbc * 3 * sizeof(float);
-      static bool attr_set = false;
-      if (!attr_set) {
-        JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)((size_t)warps * kMaxSmemBins * 3 * sizeof(float))));
-        attr_set = true;
-      }
-      int per_sm = 1;
-      JPS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_bin_ysharded_kernel<true>, threads, smem));
+      JPS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_bin_ysharded_kernel<ACC_WARP>, threads, smem));
       const int blocks = (int)std::min<long long>(want, (long long)kNumSMs * std::max(per_sm, 1));
       ScopedLaunch L(K_PK_FOLD_BIN, s);
-      pk_bin_ysharded_kernel<true><<<blocks, threads, smem, s>>>(P);
+      pk_bin_ysharded_kernel<ACC_WARP><<<blocks, threads, smem, s>>>(P);
+    } else if (T->nbc <= kMaxBlockBins) {
+      const size_t smem = (size_t)T->nbc * 3 * sizeof(float);
+      JPS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_bin_ysharded_kernel<ACC_BLOCK>, threads, smem));
+      const int blocks = (int)std::min<long long>(want, (long long)kNumSMs * std::max(per_sm, 1));
+      ScopedLaunch L(K_PK_FOLD_BIN, s);
+      pk_bin_ysharded_kernel<ACC_BLOCK><<<blocks, threads, smem, s>>>(P);
     } else {
       const int blocks = (int)std::min<long long>(want, (long long)kNumSMs * 8);
       ScopedLaunch L(K_PK_FOLD_BIN, s);
-      pk_bin_ysharded_kernel<false><<<blocks, threads, 0, s>>>(P);
+      pk_bin_ysharded_kernel<ACC_GLOBAL><<<blocks, threads, 0, s>>>(P);
     }
     JPS_CHECK_LAUNCH();
   }

@@ -104,6 +104,17 @@ def test_many_bins_global_accumulator_path(jps, field128):
     _check_pk(pk, nm, pk64, counts)
 
 
+def test_huge_bin_count_global_reds_path(jps, field128):
+    """> 8192 reachable bins: neither shared-memory accumulator layout fits, float64 global reds are used."""
+    n, box, p, rho, delta = field128
+    kF = 2 * np.pi / box
+    ke = np.arange(1e-4, 1.01 * np.sqrt(3) * np.pi * n / box, 0.004 * kF).astype(F32)
+    k3d, pk, nm = jps.powspec_vec(delta, box, ke)
+    assert (nm > 0).sum() > 8192
+    _, pk64, counts = oc.powspec(delta, box, ke, precision="f64")
+    _check_pk(pk, nm, pk64, counts)
+
+
 def test_normalise_folds_density_contrast(jps, field128):
     n, box, p, rho, delta = field128
     ke = np.arange(0.003, np.pi * n / box, 0.0025).astype(F32)          # tests/voids.py:55
