@@ -435,6 +435,11 @@ def run_slab_arm(a, wl):
         timed("all_to_all", lambda: transpose_all_to_all(pipe.buf_b, pipe.buf_a))
     timed("fft_x", pipe.stage_fft_x)
     timed("bin_partial", lambda: pipe.stage_partial(True))
+    _lib.profile_reset(); _lib.profile_enable(True)
+    pipe(x, y, z)
+    torch.cuda.synchronize()
+    prof = _lib.profile_snapshot()
+    _lib.profile_enable(False)
     if rank == 0:
         peak, peak_src = measured_peak()
         a2a = (world - 1) / world ** 2 * 8 * n * n * (n // 2 + 1)
@@ -449,6 +454,7 @@ def run_slab_arm(a, wl):
                        "n_part_total": wl["n_part"], "n_mesh": n, "box_size": box, "mas_order": order,
                        "parallelism": f"{world} x-slabs, halo ring exchange + all-to-all + allreduce per step"},
             "clocks": clocks, "gpu_launches": int(launches), "stages_ms_max_over_ranks": stages,
+            "kernels_ms_rank0": {k: round(ms_ / max(c, 1), 4) for k, (c, ms_) in prof.items()},
             "all_to_all": {"bytes_per_rank": a2a, "achieved_gbs_per_rank": (a2a / stages["all_to_all"] / 1e6) if world > 1 else None,
                            "nvlink_peer_copy_ref_gbs": 770.0},
             "roofline": {"kernel": "paint (bucket + tile deposit)", "bound": "hbm", "achieved": paint_bytes / stages["paint"] / 1e6,

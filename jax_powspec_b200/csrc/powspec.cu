@@ -92,52 +92,61 @@ __global__ void __launch_bounds__(256) pk_fold_bin_kernel(PkParams P) {
 #pragma unroll
     for (int r = 0; r < 8; ++r)
       rp[r] = P.dk + ((size_t)rows.ix[r] * n + rows.iy[r]) * pitch;
-    for (int kz0 = 0; kz0 < nz; kz0 += 32) {
-      const int kz = kz0 + lane;
-      const bool active = kz < nz;
-      float v[3] = {0.0f, 0.0f, 0.0f};
-      int cb = -2;
-      if (active) {
-        float2 d[8];
+    constexpr int UNR = 2;                         // kz chunks in flight: 8 rows x 2 chunks = 16 loads per lane
+    for (int kzb = 0; kzb < nz; kzb += 32 * UNR) {
+      float2 d[UNR][8];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int kz = kzb + 32 * u + lane;
 #pragma unroll
         for (int r = 0; r < 8; ++r)
-          d[r] = (r < rows.nrows) ? __ldg(rp[r] + kz) : make_float2(0.0f, 0.0f);
-        const int k2 = k2ab + kz * kz;
-        cb = __ldg(P.lut + k2);
-        const float c = wab * P.wl[kz];             // (c(kx)*c(ky))*c(kz), correlations.py:32
-        float sum = 0.0f;
+          d[u][r] = (r < rows.nrows && kz < nz) ? __ldg(rp[r] + kz) : make_float2(0.0f, 0.0f);
+      }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const float re = d[r].x * c, im = d[r].y * c;   // delta_k *= correction (:39)
-          sum += re * re + im * im;                       // (delta_k * conj(delta_k)).real (:40)
+      for (int u = 0; u < UNR; ++u) {
+        const int kz0 = kzb + 32 * u;
+        if (kz0 >= nz) break;                      // warp-uniform
+        const int kz = kz0 + lane;
+        float v[3] = {0.0f, 0.0f, 0.0f};
+        int cb = -2;
+        if (kz < nz) {
+          const int k2 = k2ab + kz * kz;
+          cb = __ldg(P.lut + k2);
+          const float c = wab * P.wl[kz];             // (c(kx)*c(ky))*c(kz), correlations.py:32
+          float sum = 0.0f;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const float re = d[u][r].x * c, im = d[u][r].y * c;   // delta_k *= correction (:39)
+            sum += re * re + im * im;                             // (delta_k * conj(delta_k)).real (:40)
+          }
+          sum *= scale2;
+          float mu2 = 0.0f;
+          if (k2 > 0) mu2 = (float)(kz * kz) / (float)k2;   // mu = kz/|k| (:37-38), LOS = z (Q14)
+          else if (P.normalise) sum = 0.0f;                 // delta_0 = 0 after rho/mean - 1
+          v[0] = sum;
+          v[1] = sum * (3.0f * mu2 - 1.0f) * 0.5f;
+          v[2] = sum * (35.0f * mu2 * mu2 - 30.0f * mu2 + 3.0f) * 0.125f;
         }
-        sum *= scale2;
-        float mu2 = 0.0f;
-        if (k2 > 0) mu2 = (float)(kz * kz) / (float)k2;   // mu = kz/|k| (:37-38), LOS = z (Q14)
-        else if (P.normalise) sum = 0.0f;                 // delta_0 = 0 after rho/mean - 1
-        v[0] = sum;
-        v[1] = sum * (3.0f * mu2 - 1.0f) * 0.5f;
-        v[2] = sum * (35.0f * mu2 * mu2 - 30.0f * mu2 + 3.0f) * 0.125f;
-      }
-      const int prev = __shfl_up_sync(0xffffffffu, cb, 1);
-      const bool head = (lane == 0) || (cb != prev);
-      const unsigned heads = __ballot_sync(0xffffffffu, head);
-      segmented_reduce<3>(v, heads, lane);
-      if (head && cb >= 0) {
-        if (MODE == ACC_WARP) {
-          float* a = my + cb * 3;
-          a[0] += v[0]; a[1] += v[1]; a[2] += v[2];
-        } else if (MODE == ACC_BLOCK) {
-          float* a = my + cb * 3;
-          atomicAdd(a + 0, v[0]); atomicAdd(a + 1, v[1]); atomicAdd(a + 2, v[2]);
-        } else {
-          double* a = P.acc + (size_t)cb * 4;
-          atomicAdd(a + 0, (double)v[0]);
-          atomicAdd(a + 1, (double)v[1]);
-          atomicAdd(a + 2, (double)v[2]);
+        const int prev = __shfl_up_sync(0xffffffffu, cb, 1);
+        const bool head = (lane == 0) || (cb != prev);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        segmented_reduce<3>(v, heads, lane);
+        if (head && cb >= 0) {
+          if (MODE == ACC_WARP) {
+            float* a = my + cb * 3;
+            a[0] += v[0]; a[1] += v[1]; a[2] += v[2];
+          } else if (MODE == ACC_BLOCK) {
+            float* a = my + cb * 3;
+            atomicAdd(a + 0, v[0]); atomicAdd(a + 1, v[1]); atomicAdd(a + 2, v[2]);
+          } else {
+            double* a = P.acc + (size_t)cb * 4;
+            atomicAdd(a + 0, (double)v[0]);
+            atomicAdd(a + 1, (double)v[1]);
+            atomicAdd(a + 2, (double)v[2]);
+          }
         }
+        if (MODE == ACC_WARP) __syncwarp();
       }
-      if (MODE == ACC_WARP) __syncwarp();
     }
   }
   if (SMEM) {

@@ -93,45 +93,56 @@ __global__ void __launch_bounds__(256) pk_bin_ysharded_kernel(SlabPkParams P) {
     const float2* r1 = P.dk + ((size_t)(two ? n - a : a) * P.nyl + yl) * nz;
     const float wab = P.wl[a] * P.wl[iy];
     const int k2ab = a * a + ky * ky;
-    for (int kz0 = 0; kz0 < nz; kz0 += 32) {
-      const int kz = kz0 + lane;
-      float v[3] = {0.0f, 0.0f, 0.0f};
-      int cb = -2;
-      if (kz < nz) {
-        const float2 d0 = __ldg(r0 + kz);
-        const float2 d1 = two ? __ldg(r1 + kz) : make_float2(0.0f, 0.0f);
-        const int k2 = k2ab + kz * kz;
-        cb = __ldg(P.lut + k2);
-        const float c = wab * P.wl[kz];
-        float re = d0.x * c, im = d0.y * c;
-        float sum = re * re + im * im;
-        re = d1.x * c; im = d1.y * c;
-        sum += re * re + im * im;
-        sum *= scale2;
-        float mu2 = 0.0f;
-        if (k2 > 0) mu2 = (float)(kz * kz) / (float)k2;
-        else if (P.normalise) sum = 0.0f;
-        v[0] = sum;
-        v[1] = sum * (3.0f * mu2 - 1.0f) * 0.5f;
-        v[2] = sum * (35.0f * mu2 * mu2 - 30.0f * mu2 + 3.0f) * 0.125f;
+    constexpr int UNR = 4;                         // kz chunks in flight: 2 rows x 4 chunks = 8 loads per lane
+    for (int kzb = 0; kzb < nz; kzb += 32 * UNR) {
+      float2 d0[UNR], d1[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int kz = kzb + 32 * u + lane;
+        d0[u] = (kz < nz) ? __ldg(r0 + kz) : make_float2(0.0f, 0.0f);
+        d1[u] = (two && kz < nz) ? __ldg(r1 + kz) : make_float2(0.0f, 0.0f);
       }
-      const int prev = __shfl_up_sync(0xffffffffu, cb, 1);
-      const bool head = (lane == 0) || (cb != prev);
-      const unsigned heads = __ballot_sync(0xffffffffu, head);
-      segmented_reduce<3>(v, heads, lane);
-      if (head && cb >= 0) {
-        if (MODE == ACC_WARP) {
-          float* q = my + cb * 3;
-          q[0] += v[0]; q[1] += v[1]; q[2] += v[2];
-        } else if (MODE == ACC_BLOCK) {
-          float* q = my + cb * 3;
-          atomicAdd(q + 0, v[0]); atomicAdd(q + 1, v[1]); atomicAdd(q + 2, v[2]);
-        } else {
-          double* q = P.acc + (size_t)cb * 4;
-          atomicAdd(q + 0, (double)v[0]); atomicAdd(q + 1, (double)v[1]); atomicAdd(q + 2, (double)v[2]);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int kz0 = kzb + 32 * u;
+        if (kz0 >= nz) break;                      // warp-uniform
+        const int kz = kz0 + lane;
+        float v[3] = {0.0f, 0.0f, 0.0f};
+        int cb = -2;
+        if (kz < nz) {
+          const int k2 = k2ab + kz * kz;
+          cb = __ldg(P.lut + k2);
+          const float c = wab * P.wl[kz];
+          float re = d0[u].x * c, im = d0[u].y * c;
+          float sum = re * re + im * im;
+          re = d1[u].x * c; im = d1[u].y * c;
+          sum += re * re + im * im;
+          sum *= scale2;
+          float mu2 = 0.0f;
+          if (k2 > 0) mu2 = (float)(kz * kz) / (float)k2;
+          else if (P.normalise) sum = 0.0f;
+          v[0] = sum;
+          v[1] = sum * (3.0f * mu2 - 1.0f) * 0.5f;
+          v[2] = sum * (35.0f * mu2 * mu2 - 30.0f * mu2 + 3.0f) * 0.125f;
         }
+        const int prev = __shfl_up_sync(0xffffffffu, cb, 1);
+        const bool head = (lane == 0) || (cb != prev);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        segmented_reduce<3>(v, heads, lane);
+        if (head && cb >= 0) {
+          if (MODE == ACC_WARP) {
+            float* q = my + cb * 3;
+            q[0] += v[0]; q[1] += v[1]; q[2] += v[2];
+          } else if (MODE == ACC_BLOCK) {
+            float* q = my + cb * 3;
+            atomicAdd(q + 0, v[0]); atomicAdd(q + 1, v[1]); atomicAdd(q + 2, v[2]);
+          } else {
+            double* q = P.acc + (size_t)cb * 4;
+            atomicAdd(q + 0, (double)v[0]); atomicAdd(q + 1, (double)v[1]); atomicAdd(q + 2, (double)v[2]);
+          }
+        }
+        if (MODE == ACC_WARP) __syncwarp();
       }
-      if (MODE == ACC_WARP) __syncwarp();
     }
   }
   if (SMEM) {

@@ -106,7 +106,8 @@ def test_many_bins_global_accumulator_path(jps, field128):
 
 def test_huge_bin_count_global_reds_path(jps, field128):
     """> 8192 reachable bins: neither shared-memory accumulator layout fits, float64 global reds are used."""
-    n, box, p, rho, delta = field128
+    n, box = 192, 1000.0
+    delta = np.random.default_rng(8).standard_normal((n, n, n)).astype(F32)
     kF = 2 * np.pi / box
     ke = np.arange(1e-4, 1.01 * np.sqrt(3) * np.pi * n / box, 0.004 * kF).astype(F32)
     k3d, pk, nm = jps.powspec_vec(delta, box, ke)
