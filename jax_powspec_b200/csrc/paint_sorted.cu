@@ -539,17 +539,17 @@ size_t paint_sorted_workspace(int n, int64_t n_part, int order) {
   return sorted_layout(n, n, n_part).total + 4096;   // a full mesh bounds every slab of it
 }
 
+// bucket one piece of the catalogue (count -> scan -> scatter) on stream `s`
 template <int ORDER, bool REFCIC>
-static int run_sorted(const PaintParams& p, const TileGeom& g, const SortedLayout& L, char* ws,
-                      cudaStream_t s) {
+static int run_bucket(const PaintParams& p, const TileGeom& g, const SortedLayout& L, char* ws, cudaStream_t s) {
   unsigned* counts = (unsigned*)(ws + L.counts);
   unsigned* offsets = (unsigned*)(ws + L.offsets);
   unsigned* cursor = (unsigned*)(ws + L.cursor);
   float4* sorted = (float4*)(ws + L.sorted);
+  unsigned* wmax_bits = (unsigned*)(ws + L.wmax);
   const int threads = 256;
   const int64_t want = (p.n_part + (int64_t)threads * BUCKET_UNROLL - 1) / ((int64_t)threads * BUCKET_UNROLL);
   const int blocks = (int)std::min<int64_t>(want, (int64_t)kNumSMs * 8 * 2);
-  unsigned* wmax_bits = (unsigned*)(ws + L.wmax);
   {
     ScopedLaunch T(K_MEMSET, s);
     JPS_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)(L.nbuckets + 1) * 4, s));
@@ -573,6 +573,15 @@ static int run_sorted(const PaintParams& p, const TileGeom& g, const SortedLayou
     bucket_scatter_kernel<ORDER, REFCIC><<<blocks, threads, 0, s>>>(p, g, cursor, sorted);
   }
   JPS_CHECK_LAUNCH();
+  return JPS_OK;
+}
+
+// deposit a bucketed piece into the mesh on stream `s`
+template <int ORDER, bool REFCIC>
+static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayout& L, char* ws, cudaStream_t s) {
+  const unsigned* offsets = (const unsigned*)(ws + L.offsets);
+  const float4* sorted = (const float4*)(ws + L.sorted);
+  const unsigned* wmax_bits = (const unsigned*)(ws + L.wmax);
   {
     ScopedLaunch T(K_PAINT_TILE, s);
     const int mesh_vec_ok = (((uintptr_t)p.mesh) & 15) == 0 ? 1 : 0;
@@ -602,6 +611,83 @@ static int run_sorted(const PaintParams& p, const TileGeom& g, const SortedLayou
   return JPS_OK;
 }
 
+// Auxiliary stream + events for the pipelined painter (one set per host thread, created lazily,
+// never destroyed: a plan-less C call has nowhere to hang them).
+struct PipeResources {
+  cudaStream_t aux = nullptr;
+  cudaEvent_t fork = nullptr, bucketed[2] = {nullptr, nullptr}, painted[2] = {nullptr, nullptr};
+  int device = -1;
+  bool ok = false;
+};
+
+static int pipe_resources(PipeResources** out) {
+  static thread_local PipeResources R;
+  int dev = 0;
+  JPS_CHECK_CUDA(cudaGetDevice(&dev));
+  if (!R.ok || R.device != dev) {
+    JPS_CHECK_CUDA(cudaStreamCreateWithFlags(&R.aux, cudaStreamNonBlocking));
+    JPS_CHECK_CUDA(cudaEventCreateWithFlags(&R.fork, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+      JPS_CHECK_CUDA(cudaEventCreateWithFlags(&R.bucketed[i], cudaEventDisableTiming));
+      JPS_CHECK_CUDA(cudaEventCreateWithFlags(&R.painted[i], cudaEventDisableTiming));
+    }
+    R.device = dev;
+    R.ok = true;
+  }
+  *out = &R;
+  return JPS_OK;
+}
+
+constexpr int64_t kPipelineMinParticles = (int64_t)1 << 24;   // below this one piece is cheaper
+constexpr int kPipelinePieces = 4;
+
+// The bucketing passes sit on the L2 atomic unit / memory latency and leave the SMs mostly idle;
+// the tile deposit saturates the SMs' shared-memory pipe and barely touches L2.  Large catalogues
+// are therefore cut into kPipelinePieces pieces: piece c+1 is bucketed on an auxiliary stream
+// (forked from / joined to the caller's stream with events) while piece c is deposited on the
+// caller's stream.  Two workspace slots are ping-ponged.
+template <int ORDER, bool REFCIC>
+static int run_sorted(const PaintParams& p, const TileGeom& g, char* ws, size_t ws_bytes, cudaStream_t s) {
+  static const bool no_pipe = [] { const char* e = getenv("JPS_PAINT_PIPELINE"); return e && !strcmp(e, "0"); }();
+  const int pieces = (p.n_part >= kPipelineMinParticles && !no_pipe) ? kPipelinePieces : 1;
+  if (pieces == 1) {
+    const SortedLayout L = sorted_layout(p.n, p.nx, p.n_part);
+    int rc = run_bucket<ORDER, REFCIC>(p, g, L, ws, s);
+    if (rc) return rc;
+    return run_deposit<ORDER, REFCIC>(p, g, L, ws, s);
+  }
+  const int64_t cap = (p.n_part + pieces - 1) / pieces;
+  const SortedLayout L = sorted_layout(p.n, p.nx, cap);
+  if (2 * L.total > ws_bytes) {
+    set_error("jps_paint: workspace too small for the pipelined painter");
+    return JPS_ERR_WORKSPACE;
+  }
+  PipeResources* R = nullptr;
+  int rc = pipe_resources(&R);
+  if (rc) return rc;
+  JPS_CHECK_CUDA(cudaEventRecord(R->fork, s));
+  JPS_CHECK_CUDA(cudaStreamWaitEvent(R->aux, R->fork, 0));
+  for (int c = 0; c < pieces; ++c) {
+    const int slot = c & 1;
+    char* wslot = ws + (size_t)slot * L.total;
+    const int64_t lo = (int64_t)c * cap;
+    PaintParams q = p;
+    q.n_part = std::min<int64_t>(cap, p.n_part - lo);
+    if (q.n_part <= 0) break;
+    q.x = p.x + lo * p.stride; q.y = p.y + lo * p.stride; q.z = p.z + lo * p.stride;
+    q.w = p.w ? p.w + lo : nullptr;
+    if (c >= 2) JPS_CHECK_CUDA(cudaStreamWaitEvent(R->aux, R->painted[slot], 0));   // slot free again
+    rc = run_bucket<ORDER, REFCIC>(q, g, L, wslot, R->aux);
+    if (rc) return rc;
+    JPS_CHECK_CUDA(cudaEventRecord(R->bucketed[slot], R->aux));
+    JPS_CHECK_CUDA(cudaStreamWaitEvent(s, R->bucketed[slot], 0));
+    rc = run_deposit<ORDER, REFCIC>(q, g, L, wslot, s);
+    if (rc) return rc;
+    JPS_CHECK_CUDA(cudaEventRecord(R->painted[slot], s));
+  }
+  return JPS_OK;
+}
+
 int paint_sorted(const PaintParams& p, int order, int compat, void* ws, size_t ws_bytes,
                  cudaStream_t s) {
   if (p.n_part == 0) return JPS_OK;
@@ -621,10 +707,10 @@ int paint_sorted(const PaintParams& p, int order, int compat, void* ws, size_t w
   g.ntiles = g.ntx * g.nt * g.nt;
   g.rep = replicas_for(g.ntiles);
   char* w = (char*)ws;
-  if (order == 2 && compat == JPS_COMPAT_REFERENCE) return run_sorted<2, true>(p, g, L, w, s);
-  if (order == 2) return run_sorted<2, false>(p, g, L, w, s);
-  if (order == 3) return run_sorted<3, false>(p, g, L, w, s);
-  return run_sorted<4, false>(p, g, L, w, s);
+  if (order == 2 && compat == JPS_COMPAT_REFERENCE) return run_sorted<2, true>(p, g, w, ws_bytes, s);
+  if (order == 2) return run_sorted<2, false>(p, g, w, ws_bytes, s);
+  if (order == 3) return run_sorted<3, false>(p, g, w, ws_bytes, s);
+  return run_sorted<4, false>(p, g, w, ws_bytes, s);
 }
 
 }  // namespace jps

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) pk_fold_bin_kernel(PkParams P) {
 #pragma unroll
     for (int r = 0; r < 8; ++r)
       rp[r] = P.dk + ((size_t)rows.ix[r] * n + rows.iy[r]) * pitch;
-    constexpr int UNR = 2;                         // kz chunks in flight: 8 rows x 2 chunks = 16 loads per lane
+    constexpr int UNR = 1;                         // kz chunks in flight per lane (8 rows each); 2 measured no faster
     for (int kzb = 0; kzb < nz; kzb += 32 * UNR) {
       float2 d[UNR][8];
 #pragma unroll
