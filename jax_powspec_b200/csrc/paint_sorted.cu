@@ -611,81 +611,17 @@ static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayo
   return JPS_OK;
 }
 
-// Auxiliary stream + events for the pipelined painter (one set per host thread, created lazily,
-// never destroyed: a plan-less C call has nowhere to hang them).
-struct PipeResources {
-  cudaStream_t aux = nullptr;
-  cudaEvent_t fork = nullptr, bucketed[2] = {nullptr, nullptr}, painted[2] = {nullptr, nullptr};
-  int device = -1;
-  bool ok = false;
-};
-
-static int pipe_resources(PipeResources** out) {
-  static thread_local PipeResources R;
-  int dev = 0;
-  JPS_CHECK_CUDA(cudaGetDevice(&dev));
-  if (!R.ok || R.device != dev) {
-    JPS_CHECK_CUDA(cudaStreamCreateWithFlags(&R.aux, cudaStreamNonBlocking));
-    JPS_CHECK_CUDA(cudaEventCreateWithFlags(&R.fork, cudaEventDisableTiming));
-    for (int i = 0; i < 2; ++i) {
-      JPS_CHECK_CUDA(cudaEventCreateWithFlags(&R.bucketed[i], cudaEventDisableTiming));
-      JPS_CHECK_CUDA(cudaEventCreateWithFlags(&R.painted[i], cudaEventDisableTiming));
-    }
-    R.device = dev;
-    R.ok = true;
-  }
-  *out = &R;
-  return JPS_OK;
-}
-
-constexpr int64_t kPipelineMinParticles = (int64_t)1 << 24;   // below this one piece is cheaper
-constexpr int kPipelinePieces = 4;
-
-// The bucketing passes sit on the L2 atomic unit / memory latency and leave the SMs mostly idle;
-// the tile deposit saturates the SMs' shared-memory pipe and barely touches L2.  Large catalogues
-// are therefore cut into kPipelinePieces pieces: piece c+1 is bucketed on an auxiliary stream
-// (forked from / joined to the caller's stream with events) while piece c is deposited on the
-// caller's stream.  Two workspace slots are ping-ponged.
+// (Measured and dropped in round 1: cutting the catalogue into 4 pieces and bucketing piece c+1 on
+// an auxiliary stream while piece c is deposited.  The step got SLOWER, 6.9 -> 8.5 ms on C2: each
+// piece re-zeroes and re-flushes every tile, so the deposit grows from 2.7 to 4 x 1.1 ms, and the
+// two kernels do not overlap well enough to pay that back.)
 template <int ORDER, bool REFCIC>
 static int run_sorted(const PaintParams& p, const TileGeom& g, char* ws, size_t ws_bytes, cudaStream_t s) {
-  static const bool no_pipe = [] { const char* e = getenv("JPS_PAINT_PIPELINE"); return e && !strcmp(e, "0"); }();
-  const int pieces = (p.n_part >= kPipelineMinParticles && !no_pipe) ? kPipelinePieces : 1;
-  if (pieces == 1) {
-    const SortedLayout L = sorted_layout(p.n, p.nx, p.n_part);
-    int rc = run_bucket<ORDER, REFCIC>(p, g, L, ws, s);
-    if (rc) return rc;
-    return run_deposit<ORDER, REFCIC>(p, g, L, ws, s);
-  }
-  const int64_t cap = (p.n_part + pieces - 1) / pieces;
-  const SortedLayout L = sorted_layout(p.n, p.nx, cap);
-  if (2 * L.total > ws_bytes) {
-    set_error("jps_paint: workspace too small for the pipelined painter");
-    return JPS_ERR_WORKSPACE;
-  }
-  PipeResources* R = nullptr;
-  int rc = pipe_resources(&R);
+  (void)ws_bytes;
+  const SortedLayout L = sorted_layout(p.n, p.nx, p.n_part);
+  int rc = run_bucket<ORDER, REFCIC>(p, g, L, ws, s);
   if (rc) return rc;
-  JPS_CHECK_CUDA(cudaEventRecord(R->fork, s));
-  JPS_CHECK_CUDA(cudaStreamWaitEvent(R->aux, R->fork, 0));
-  for (int c = 0; c < pieces; ++c) {
-    const int slot = c & 1;
-    char* wslot = ws + (size_t)slot * L.total;
-    const int64_t lo = (int64_t)c * cap;
-    PaintParams q = p;
-    q.n_part = std::min<int64_t>(cap, p.n_part - lo);
-    if (q.n_part <= 0) break;
-    q.x = p.x + lo * p.stride; q.y = p.y + lo * p.stride; q.z = p.z + lo * p.stride;
-    q.w = p.w ? p.w + lo : nullptr;
-    if (c >= 2) JPS_CHECK_CUDA(cudaStreamWaitEvent(R->aux, R->painted[slot], 0));   // slot free again
-    rc = run_bucket<ORDER, REFCIC>(q, g, L, wslot, R->aux);
-    if (rc) return rc;
-    JPS_CHECK_CUDA(cudaEventRecord(R->bucketed[slot], R->aux));
-    JPS_CHECK_CUDA(cudaStreamWaitEvent(s, R->bucketed[slot], 0));
-    rc = run_deposit<ORDER, REFCIC>(q, g, L, wslot, s);
-    if (rc) return rc;
-    JPS_CHECK_CUDA(cudaEventRecord(R->painted[slot], s));
-  }
-  return JPS_OK;
+  return run_deposit<ORDER, REFCIC>(p, g, L, ws, s);
 }
 
 int paint_sorted(const PaintParams& p, int order, int compat, void* ws, size_t ws_bytes,
