@@ -93,9 +93,19 @@ __global__ void __launch_bounds__(256) bucket_count_kernel(PaintParams p, TileGe
     for (int u = 0; u < BUCKET_UNROLL; ++u)
       if (tile[u] >= 0) atomicAdd(counts + tile[u], 1u);
   }
+  if (!p.w) {                                       // unit weights: nothing to reduce
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(wmax_bits, __float_as_uint(1.0f));
+    return;
+  }
+  __shared__ float wmax_warp[8];
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
-  if ((threadIdx.x & 31) == 0) atomicMax(wmax_bits, __float_as_uint(wmax));   // non-negative floats order as uints
+  if ((threadIdx.x & 31) == 0) wmax_warp[threadIdx.x >> 5] = wmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < (int)(blockDim.x >> 5); ++q) wmax = fmaxf(wmax, wmax_warp[q]);
+    atomicMax(wmax_bits, __float_as_uint(wmax));    // non-negative floats order as uints; one per CTA
+  }
 }
 
 // ---------------------------------------------------------------- K1b: exclusive scan
@@ -339,10 +349,10 @@ __global__ void __launch_bounds__(256) paint_tile_kernel(const float4* __restric
 // Shared-memory float atomicAdd is a compare-and-swap loop on sm_100a (ATOMS.CAST.SPIN); the only
 // native shared atomic add is the 32-bit integer one (ATOMS.ADD), measured 2x faster and immune to
 // same-address retries.  So the tile is accumulated in 64-bit fixed point held as two 32-bit words
-// per cell: lo += v_lo (native atomic, returns the old value -> carry), hi += v_hi + carry (native,
-// only when non-zero: ~4% of the updates).  Each contribution is the SAME float32 product the
-// reference forms, scaled by a power of two 2^(32-e) with 2^e >= max|w| (exact in float32) and
-// rounded to an integer, i.e. quantised at 2^-32 of the largest weight -- far below float32
+// per cell: lo += q (native atomic, returns the old value -> carry), hi += carry (native, only on
+// overflow of the low word: ~4% of the updates).  Each contribution is the SAME float32 product the
+// reference forms, scaled by a power of two 2^(31-e) with 2^e >= max|w| (exact in float32) and
+// rounded to an integer, i.e. quantised at 2^-31 of the largest weight -- far below float32
 // resolution -- and integer addition is associative, so the tile sum is independent of the order
 // in which particles arrive (the float32 path is only reproducible to ~1e-7).
 // A cleverer ordering of the particles (in-tile counting sort by cell, tried in round 1) was
@@ -355,13 +365,63 @@ struct TileDims {
   static constexpr int CELLS = L * L * LP;
 };
 
+// v >= 0 is the magnitude of one contribution in units of 2^-31 of the weight scale (< 2^32, one
+// F2I); NEG selects subtraction (negative particle weight).  64-bit two's-complement arithmetic on
+// the (hi, lo) word pair: the low-word atomic returns the old value, from which carry / borrow follow.
+template <bool NEG>
 __device__ __forceinline__ void fx_add(unsigned* __restrict__ lo, unsigned* __restrict__ hi, int idx, float v) {
-  const long long q = __float2ll_rn(v);
-  if (q == 0) return;
-  const unsigned ql = (unsigned)q, qh = (unsigned)((unsigned long long)q >> 32);
-  const unsigned old = atomicAdd(lo + idx, ql);
-  const unsigned h = qh + ((old + ql) < old ? 1u : 0u);      // carry out of the low word
-  if (h) atomicAdd(hi + idx, h);
+  const unsigned q = __float2uint_rn(v);           // q == 0 needs no special case: no carry, no borrow
+  if (!NEG) {
+    const unsigned old = atomicAdd(lo + idx, q);
+    if (old + q < old) atomicAdd(hi + idx, 1u);              // carry
+  } else {
+    const unsigned old = atomicAdd(lo + idx, 0u - q);
+    if (old < q) atomicAdd(hi + idx, 0xffffffffu);           // borrow
+  }
+}
+
+template <int ORDER, bool REFCIC, bool NEG>
+__device__ __forceinline__ void fx_deposit(const float4& r, float ws, unsigned* lo, unsigned* hi,
+                                           const TileGeom& g, int wrap, int variant, int ox, int oy, int oz) {
+  constexpr int L = TileDims<ORDER>::L, LP = TileDims<ORDER>::LP;
+  const int n = g.n;
+  // ws = |w| * 2^(31-e): the power-of-two scale is folded into the weight, which commutes exactly
+  // with the float32 products below, so each contribution is the reference's float32 product
+  // (src/mas.py:142-151, left to right) times 2^(31-e).
+  if (REFCIC) {
+    int x0, x1, y0, y1, z0, z1;
+    float mdx, ddx, mdy, ddy, mdz, ddz;
+    cic_reference_axis(r.x, n, wrap, variant, x0, x1, mdx, ddx);
+    cic_reference_axis(r.y, n, wrap, variant, y0, y1, mdy, ddy);
+    cic_reference_axis(r.z, n, wrap, variant, z0, z1, mdz, ddz);
+    const int c = ((local_plane(x0, g.x0, g.nx, n) - ox) * L + (y0 - oy)) * LP + (z0 - oz);
+    constexpr int SX = L * LP, SY = LP;
+    fx_add<NEG>(lo, hi, c, ((mdx * mdy) * mdz) * ws);
+    fx_add<NEG>(lo, hi, c + SX, ((ddx * mdy) * mdz) * ws);
+    fx_add<NEG>(lo, hi, c + SY, ((mdx * ddy) * mdz) * ws);
+    fx_add<NEG>(lo, hi, c + 1, ((mdx * mdy) * ddz) * ws);
+    fx_add<NEG>(lo, hi, c + SX + SY, ((ddx * ddy) * mdz) * ws);
+    fx_add<NEG>(lo, hi, c + SX + 1, ((ddx * mdy) * ddz) * ws);
+    fx_add<NEG>(lo, hi, c + SY + 1, ((mdx * mdy) * ddz) * ws);       // Q1 (reference weight)
+    fx_add<NEG>(lo, hi, c + SX + SY + 1, ((ddx * ddy) * ddz) * ws);
+  } else {
+    int ax, ay, az;
+    float wx[ORDER], wy[ORDER], wz[ORDER];
+    tile_axis<ORDER>(r.x, n, wrap, ax, wx);
+    tile_axis<ORDER>(r.y, n, wrap, ay, wy);
+    tile_axis<ORDER>(r.z, n, wrap, az, wz);
+    const int c = ((local_plane(ax, g.x0, g.nx, n) - ox) * L + (ay - oy)) * LP + (az - oz);
+#pragma unroll
+    for (int a = 0; a < ORDER; ++a) {
+#pragma unroll
+      for (int b = 0; b < ORDER; ++b) {
+        const float wxy = wx[a] * wy[b];
+#pragma unroll
+        for (int cc = 0; cc < ORDER; ++cc)
+          fx_add<NEG>(lo, hi, c + (a * L + b) * LP + cc, (wxy * wz[cc]) * ws);
+      }
+    }
+  }
 }
 
 template <int ORDER, bool REFCIC>
@@ -382,58 +442,25 @@ __global__ void __launch_bounds__(256) paint_tile_fx_kernel(const float4* __rest
   const int ox = tx * TILE, oy = ty * TILE, oz = tz * TILE;
   const int n = g.n;
   for (int i = threadIdx.x; i < 2 * NC; i += blockDim.x) fx_smem[i] = 0u;
-  // power-of-two scale: 2^e >= max|w|  ->  |contribution| * 2^(32-e) <= 2^32
+  // power-of-two scale: 2^e >= max|w|  ->  |contribution| * 2^(31-e) <= 2^31 fits one 32-bit word
   float wmax = __uint_as_float(*wmax_bits);
   if (!(wmax > 0.0f) || !(wmax < 3.0e38f)) wmax = 1.0f;
   int e;
   frexpf(wmax, &e);
   e = max(-90, min(90, e));
-  const float scale = ldexpf(1.0f, 32 - e);
+  const float scale = ldexpf(1.0f, 31 - e);
   __syncthreads();
 
   for (unsigned i = beg + threadIdx.x; i < end; i += blockDim.x) {
     const float4 r = sorted[i];
-    if (REFCIC) {
-      int x0, x1, y0, y1, z0, z1;
-      float mdx, ddx, mdy, ddy, mdz, ddz;
-      cic_reference_axis(r.x, n, wrap, variant, x0, x1, mdx, ddx);
-      cic_reference_axis(r.y, n, wrap, variant, y0, y1, mdy, ddy);
-      cic_reference_axis(r.z, n, wrap, variant, z0, z1, mdz, ddz);
-      const int c = ((local_plane(x0, g.x0, g.nx, n) - ox) * L + (y0 - oy)) * LP + (z0 - oz);
-      const float wgt = r.w;
-      constexpr int SX = L * LP, SY = LP;
-      // the float32 products of src/mas.py:142-151 (left to right), then the exact power-of-two scale
-      fx_add(lo, hi, c, (((mdx * mdy) * mdz) * wgt) * scale);
-      fx_add(lo, hi, c + SX, (((ddx * mdy) * mdz) * wgt) * scale);
-      fx_add(lo, hi, c + SY, (((mdx * ddy) * mdz) * wgt) * scale);
-      fx_add(lo, hi, c + 1, (((mdx * mdy) * ddz) * wgt) * scale);
-      fx_add(lo, hi, c + SX + SY, (((ddx * ddy) * mdz) * wgt) * scale);
-      fx_add(lo, hi, c + SX + 1, (((ddx * mdy) * ddz) * wgt) * scale);
-      fx_add(lo, hi, c + SY + 1, (((mdx * mdy) * ddz) * wgt) * scale);     // Q1 (reference weight)
-      fx_add(lo, hi, c + SX + SY + 1, (((ddx * ddy) * ddz) * wgt) * scale);
-    } else {
-      int ax, ay, az;
-      float wx[ORDER], wy[ORDER], wz[ORDER];
-      tile_axis<ORDER>(r.x, n, wrap, ax, wx);
-      tile_axis<ORDER>(r.y, n, wrap, ay, wy);
-      tile_axis<ORDER>(r.z, n, wrap, az, wz);
-      const int c = ((local_plane(ax, g.x0, g.nx, n) - ox) * L + (ay - oy)) * LP + (az - oz);
-#pragma unroll
-      for (int a = 0; a < ORDER; ++a) {
-#pragma unroll
-        for (int b = 0; b < ORDER; ++b) {
-          const float wxy = wx[a] * wy[b];
-#pragma unroll
-          for (int cc = 0; cc < ORDER; ++cc)
-            fx_add(lo, hi, c + (a * L + b) * LP + cc, ((wxy * wz[cc]) * r.w) * scale);
-        }
-      }
-    }
+    const float ws = fabsf(r.w) * scale;
+    if (r.w >= 0.0f) fx_deposit<ORDER, REFCIC, false>(r, ws, lo, hi, g, wrap, variant, ox, oy, oz);
+    else fx_deposit<ORDER, REFCIC, true>(r, ws, lo, hi, g, wrap, variant, ox, oy, oz);
   }
   __syncthreads();
 
   // flush: fixed point -> float32 (one rounding), 16-byte vector reds where aligned
-  const double inv_scale = (double)ldexpf(1.0f, e - 32);
+  const double inv_scale = (double)ldexpf(1.0f, e - 31);
   const size_t n2 = (size_t)n * n;
   const bool vec_ok = (n % 4 == 0) && mesh_vec_ok;
   constexpr int NV = TILE / 4;
