@@ -287,6 +287,11 @@ def run_gpu_arm(a, wl):
     prof = _lib.profile_snapshot()
     _lib.profile_enable(False)
 
+    if a.quick_kernels:                            # parameter sweeps: skip the e2e / cpu legs
+        if rank == 0:
+            print(json.dumps({"ms_per_step": ms, "kernels": {k: {"ms_per_launch": t / c} for k, (c, t) in prof.items()}}), flush=True)
+        return 0
+
     # ---- end to end through the public API with host buffers
     xh, yh, zh = (t.cpu().pin_memory() for t in (x, y, z))
     del x, y, z
@@ -486,6 +491,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="stop after the device-resident timed region (ncu runs)")
+    ap.add_argument("--quick-kernels", action="store_true", help="stop after the per-kernel pass (sweeps)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
                     help="c2: one realisation per GPU (default, weak scaling); c4: one slab-sharded mesh (strong scaling)")
     ap.add_argument("--order", type=int, default=None)

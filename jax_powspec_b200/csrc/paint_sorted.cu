@@ -108,6 +108,57 @@ __global__ void __launch_bounds__(256) bucket_count_kernel(PaintParams p, TileGe
   }
 }
 
+// K1a, small-mesh variant: when all tile counters fit in one SM's shared memory (<= 48 K tiles,
+// i.e. N <= 576) every CTA histograms its share of the catalogue with native shared-memory integer
+// atomics and adds its 128 KB table to the global counters once -- 4.8 M global reds instead of
+// 1e8, which turns the pass from L2-atomic-bound (0.69 ms on C2) into a plain read of x, y, z.
+constexpr int kSmemCountMaxTiles = 49152;
+
+template <int ORDER, bool REFCIC>
+__global__ void __launch_bounds__(1024) bucket_count_smem_kernel(PaintParams p, TileGeom g,
+                                                                 unsigned* __restrict__ counts,
+                                                                 unsigned* __restrict__ wmax_bits) {
+  extern __shared__ unsigned hist[];               // [ntiles + 1]; requires g.rep == 1
+  const int nb = g.ntiles + 1;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = 0u;
+  __syncthreads();
+  const int64_t T = (int64_t)gridDim.x * blockDim.x;
+  float wmax = p.w ? 0.0f : 1.0f;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < p.n_part; i0 += BUCKET_UNROLL * T) {
+    int tile[BUCKET_UNROLL];
+#pragma unroll
+    for (int u = 0; u < BUCKET_UNROLL; ++u) {
+      const int64_t i = i0 + u * T;
+      tile[u] = -1;
+      if (i < p.n_part) {
+        const float px = grid_pos(p.x[i * p.stride], p.xmin, p.inv);
+        const float py = grid_pos(p.y[i * p.stride], p.ymin, p.inv);
+        const float pz = grid_pos(p.z[i * p.stride], p.zmin, p.inv);
+        tile[u] = tile_of<ORDER, REFCIC>(px, py, pz, g, 0u);
+        if (p.w) {
+          const float a = fabsf(p.w[i]);
+          if (a < 3.0e38f) wmax = fmaxf(wmax, a);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < BUCKET_UNROLL; ++u)
+      if (tile[u] >= 0) atomicAdd(hist + tile[u], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    const unsigned c = hist[i];
+    if (c) atomicAdd(counts + i, c);
+  }
+  if (!p.w) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(wmax_bits, __float_as_uint(1.0f));
+    return;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
+  if ((threadIdx.x & 31) == 0) atomicMax(wmax_bits, __float_as_uint(wmax));    // 32 per CTA, 148 CTAs
+}
+
 // ---------------------------------------------------------------- K1b: exclusive scan
 // Three small launches: per-block totals (SCAN_BLOCK counters per CTA, coalesced), a one-CTA scan of
 // the block totals, and the per-block rescan that writes offsets[] and the scatter cursors.
@@ -196,17 +247,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const unsigned
 // bucket is filled at a moving frontier and the 16-byte records merge into full lines in L2
 // before they reach DRAM (ncu: dram bytes written == 16 B/particle).  (Taking the slot from the
 // count pass instead -- no second atomic -- was measured 1.8x SLOWER: it breaks that locality.)
-template <int ORDER, bool REFCIC>
+template <int ORDER, bool REFCIC, int UNR>
 __global__ void __launch_bounds__(256) bucket_scatter_kernel(PaintParams p, TileGeom g,
                                                              unsigned* __restrict__ cursor,
                                                              float4* __restrict__ sorted) {
   const int64_t T = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < p.n_part;
-       i0 += BUCKET_UNROLL * T) {
-    float4 rec[BUCKET_UNROLL];
-    int tile[BUCKET_UNROLL];
+       i0 += UNR * T) {
+    float4 rec[UNR];
+    int tile[UNR];
 #pragma unroll
-    for (int u = 0; u < BUCKET_UNROLL; ++u) {
+    for (int u = 0; u < UNR; ++u) {
       const int64_t i = i0 + u * T;
       tile[u] = -1;
       if (i < p.n_part) {
@@ -217,12 +268,12 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(PaintParams p, Tile
         tile[u] = tile_of<ORDER, REFCIC>(rec[u].x, rec[u].y, rec[u].z, g, blockIdx.x);
       }
     }
-    unsigned slot[BUCKET_UNROLL];
+    unsigned slot[UNR];
 #pragma unroll
-    for (int u = 0; u < BUCKET_UNROLL; ++u)
+    for (int u = 0; u < UNR; ++u)
       slot[u] = (tile[u] >= 0) ? atomicAdd(cursor + tile[u], 1u) : 0u;
 #pragma unroll
-    for (int u = 0; u < BUCKET_UNROLL; ++u)
+    for (int u = 0; u < UNR; ++u)
       if (tile[u] >= 0) sorted[slot[u]] = rec[u];
   }
 }
@@ -540,7 +591,9 @@ struct SortedLayout {
 };
 
 static int replicas_for(int ntiles) {
-  int rep = 8;
+  if (ntiles <= kSmemCountMaxTiles) return 1;      // shared-memory histogram: no same-address pressure
+  static const int rep_max = [] { const char* e = getenv("JPS_BUCKET_REP"); return e ? atoi(e) : 8; }();
+  int rep = rep_max;
   while (rep > 1 && (long long)ntiles * rep > (1 << 19)) rep >>= 1;   // keep the scan + hot lines small
   return rep;
 }
@@ -582,7 +635,19 @@ static int run_bucket(const PaintParams& p, const TileGeom& g, const SortedLayou
     JPS_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)(L.nbuckets + 1) * 4, s));
     JPS_CHECK_CUDA(cudaMemsetAsync(wmax_bits, 0, 4, s));
   }
-  {
+  if (g.rep == 1 && g.ntiles <= kSmemCountMaxTiles) {
+    const int smem = (g.ntiles + 1) * (int)sizeof(unsigned);
+    static bool attr_set = false;
+    if (!attr_set) {
+      JPS_CHECK_CUDA(cudaFuncSetAttribute(bucket_count_smem_kernel<ORDER, REFCIC>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (kSmemCountMaxTiles + 1) * (int)sizeof(unsigned)));
+      attr_set = true;
+    }
+    const int64_t w1 = (p.n_part + 1024 * BUCKET_UNROLL - 1) / (1024 * BUCKET_UNROLL);
+    ScopedLaunch T(K_BUCKET_COUNT, s);
+    bucket_count_smem_kernel<ORDER, REFCIC><<<(int)std::min<int64_t>(w1, kNumSMs), 1024, smem, s>>>(p, g, counts, wmax_bits);
+  } else {
     ScopedLaunch T(K_BUCKET_COUNT, s);
     bucket_count_kernel<ORDER, REFCIC><<<blocks, threads, 0, s>>>(p, g, counts, wmax_bits);
   }
@@ -596,8 +661,14 @@ static int run_bucket(const PaintParams& p, const TileGeom& g, const SortedLayou
   }
   JPS_CHECK_LAUNCH();
   {
+    static const int unr = [] { const char* e = getenv("JPS_SCATTER_UNROLL"); return e ? atoi(e) : 4; }();
+    static const int bpsm = [] { const char* e = getenv("JPS_SCATTER_BLOCKS_PER_SM"); return e ? atoi(e) : 16; }();
+    const int64_t w2 = (p.n_part + (int64_t)threads * unr - 1) / ((int64_t)threads * unr);
+    const int b2 = (int)std::min<int64_t>(w2, (int64_t)kNumSMs * bpsm);
     ScopedLaunch T(K_BUCKET_SCATTER, s);
-    bucket_scatter_kernel<ORDER, REFCIC><<<blocks, threads, 0, s>>>(p, g, cursor, sorted);
+    if (unr == 1) bucket_scatter_kernel<ORDER, REFCIC, 1><<<b2, threads, 0, s>>>(p, g, cursor, sorted);
+    else if (unr == 2) bucket_scatter_kernel<ORDER, REFCIC, 2><<<b2, threads, 0, s>>>(p, g, cursor, sorted);
+    else bucket_scatter_kernel<ORDER, REFCIC, 4><<<b2, threads, 0, s>>>(p, g, cursor, sorted);
   }
   JPS_CHECK_LAUNCH();
   return JPS_OK;
