@@ -146,7 +146,12 @@ __global__ void __launch_bounds__(1024) bucket_count_smem_kernel(PaintParams p, 
       if (tile[u] >= 0) atomicAdd(hist + tile[u], 1u);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+  // every CTA adds its table to the same global counters: rotate the start so that at any moment
+  // the CTAs touch different addresses (same-address reds serialise in L2)
+  const int rot = (int)(((long long)blockIdx.x * nb) / gridDim.x);
+  for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+    int i = k + rot;
+    if (i >= nb) i -= nb;
     const unsigned c = hist[i];
     if (c) atomicAdd(counts + i, c);
   }
@@ -424,8 +429,8 @@ __device__ __forceinline__ void fx_add(unsigned* __restrict__ lo, unsigned* __re
   const unsigned q = __float2uint_rn(v);           // q == 0 needs no special case: no carry, no borrow
   if (!NEG) {
     const unsigned old = atomicAdd(lo + idx, q);
-    if (old + q < old) atomicAdd(hi + idx, 1u);              // carry
-  } else {
+    if (old + q < old) atomicAdd(hi + idx, 1u);              // carry (rare; a predicated PTX red
+  } else {                                                   // compiles to the same branch)
     const unsigned old = atomicAdd(lo + idx, 0u - q);
     if (old < q) atomicAdd(hi + idx, 0xffffffffu);           // borrow
   }
