@@ -283,6 +283,236 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(PaintParams p, Tile
   }
 }
 
+// ---------------------------------------------------------------- K1 v2: two-level partition
+// The single-level scatter above pays one global atomic (with return) and one scattered 16-byte
+// store per particle and sits at ~41 G particles/s whatever the unroll / occupancy / replica count
+// (tools/sweep_bucket.sh).  Two-level partition, no per-particle global atomics:
+//   A0 coarse_count    : per-CTA shared histogram over GROUPS of 2^gshift consecutive tiles
+//   A1 coarse_scatter  : a CTA takes 8192 particles, ranks them per group with shared-memory integer
+//                        atomics, reserves its run in every group with ONE global atomic per
+//                        (CTA, group), stages the records in shared memory in group order and
+//                        writes them out as coalesced runs
+//   B  fine_scatter    : one CTA per group (its records are contiguous and L2-sized): shared
+//                        histogram over the group's tiles -> tile offsets -> second pass places every
+//                        record with a warp-aggregated SHARED cursor; writes go to <= 2^gshift
+//                        frontiers per resident group, which L2 merges into full lines.
+constexpr int COARSE_CHUNK = 8192;
+constexpr int COARSE_THREADS = 1024;
+constexpr int COARSE_PT = COARSE_CHUNK / COARSE_THREADS;
+constexpr int kMaxGroups = 2048;
+
+// exclusive scan of a[0..n) in shared memory, in place, by all threads of the CTA (n <= 4 * blockDim);
+// returns the total.  `scratch` holds >= 33 words.
+__device__ __forceinline__ unsigned block_scan_inplace(unsigned* a, int n, unsigned* scratch) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x + 31) >> 5;
+  const int ipt = (n + blockDim.x - 1) / blockDim.x;
+  unsigned v[4];
+  unsigned tsum = 0;
+  for (int j = 0; j < ipt; ++j) {
+    const int i = tid * ipt + j;
+    v[j] = i < n ? a[i] : 0u;
+    tsum += v[j];
+  }
+  unsigned incl = tsum;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += t;
+  }
+  if (lane == 31) scratch[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned w = lane < nwarps ? scratch[lane] : 0u;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, w, off);
+      if (lane >= off) w += t;
+    }
+    scratch[lane] = w;                             // inclusive scan of the warp totals
+  }
+  __syncthreads();
+  unsigned run = (warp ? scratch[warp - 1] : 0u) + (incl - tsum);
+  const unsigned total = scratch[nwarps - 1];
+  for (int j = 0; j < ipt; ++j) {
+    const int i = tid * ipt + j;
+    if (i < n) a[i] = run;
+    run += v[j];
+  }
+  __syncthreads();
+  return total;
+}
+
+template <int ORDER, bool REFCIC>
+__global__ void __launch_bounds__(256) coarse_count_kernel(PaintParams p, TileGeom g, int gshift, int ngroups,
+                                                           unsigned* __restrict__ gcounts,
+                                                           unsigned* __restrict__ wmax_bits) {
+  extern __shared__ unsigned csm[];                // [ngroups]
+  for (int i = threadIdx.x; i < ngroups; i += blockDim.x) csm[i] = 0u;
+  __syncthreads();
+  const int64_t T = (int64_t)gridDim.x * blockDim.x;
+  float wmax = p.w ? 0.0f : 1.0f;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < p.n_part; i0 += BUCKET_UNROLL * T) {
+    int grp[BUCKET_UNROLL];
+#pragma unroll
+    for (int u = 0; u < BUCKET_UNROLL; ++u) {
+      const int64_t i = i0 + u * T;
+      grp[u] = -1;
+      if (i < p.n_part) {
+        const float px = grid_pos(p.x[i * p.stride], p.xmin, p.inv);
+        const float py = grid_pos(p.y[i * p.stride], p.ymin, p.inv);
+        const float pz = grid_pos(p.z[i * p.stride], p.zmin, p.inv);
+        grp[u] = tile_of<ORDER, REFCIC>(px, py, pz, g, 0u) >> gshift;
+        if (p.w) {
+          const float a = fabsf(p.w[i]);
+          if (a < 3.0e38f) wmax = fmaxf(wmax, a);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < BUCKET_UNROLL; ++u)
+      if (grp[u] >= 0) atomicAdd(csm + grp[u], 1u);
+  }
+  __syncthreads();
+  const int rot = (int)(((long long)blockIdx.x * ngroups) / gridDim.x);
+  for (int k = threadIdx.x; k < ngroups; k += blockDim.x) {
+    int i = k + rot;
+    if (i >= ngroups) i -= ngroups;
+    const unsigned c = csm[i];
+    if (c) atomicAdd(gcounts + i, c);
+  }
+  if (!p.w) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(wmax_bits, __float_as_uint(1.0f));
+    return;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
+  if ((threadIdx.x & 31) == 0) atomicMax(wmax_bits, __float_as_uint(wmax));
+}
+
+// gbase[0..ngroups] = exclusive scan of gcounts; gcursor = gbase (one CTA; ngroups <= kMaxGroups)
+__global__ void __launch_bounds__(1024) group_scan_kernel(const unsigned* __restrict__ gcounts,
+                                                          unsigned* __restrict__ gbase,
+                                                          unsigned* __restrict__ gcursor, int ngroups) {
+  __shared__ unsigned a[kMaxGroups];
+  __shared__ unsigned scratch[33];
+  for (int i = threadIdx.x; i < ngroups; i += blockDim.x) a[i] = gcounts[i];
+  __syncthreads();
+  const unsigned total = block_scan_inplace(a, ngroups, scratch);
+  for (int i = threadIdx.x; i < ngroups; i += blockDim.x) { gbase[i] = a[i]; gcursor[i] = a[i]; }
+  if (threadIdx.x == 0) gbase[ngroups] = total;
+}
+
+template <int ORDER, bool REFCIC>
+__global__ void __launch_bounds__(COARSE_THREADS) coarse_scatter_kernel(PaintParams p, TileGeom g, int gshift,
+                                                                        int ngroups,
+                                                                        unsigned* __restrict__ gcursor,
+                                                                        float4* __restrict__ tmp) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  float4* stage = reinterpret_cast<float4*>(smraw);                                   // [COARSE_CHUNK]
+  unsigned short* skey = reinterpret_cast<unsigned short*>(stage + COARSE_CHUNK);     // [COARSE_CHUNK]
+  unsigned* h = reinterpret_cast<unsigned*>(skey + COARSE_CHUNK);                     // [ngroups] counts -> local offsets
+  unsigned* gb = h + ngroups;                                                         // [ngroups] reserved global base
+  unsigned* scratch = gb + ngroups;                                                   // [33]
+  const int tid = threadIdx.x;
+  const int64_t nchunks = (p.n_part + COARSE_CHUNK - 1) / COARSE_CHUNK;
+  for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const int64_t c0 = ch * COARSE_CHUNK;
+    const int m = (int)min((int64_t)COARSE_CHUNK, p.n_part - c0);
+    for (int i = tid; i < ngroups; i += COARSE_THREADS) h[i] = 0u;
+    __syncthreads();
+    unsigned key[COARSE_PT];                       // group | rank << 12
+#pragma unroll
+    for (int u = 0; u < COARSE_PT; ++u) {
+      const int j = u * COARSE_THREADS + tid;
+      key[u] = 0xffffffffu;
+      if (j < m) {
+        const int64_t i = c0 + j;
+        const float px = grid_pos(p.x[i * p.stride], p.xmin, p.inv);
+        const float py = grid_pos(p.y[i * p.stride], p.ymin, p.inv);
+        const float pz = grid_pos(p.z[i * p.stride], p.zmin, p.inv);
+        const unsigned grp = (unsigned)(tile_of<ORDER, REFCIC>(px, py, pz, g, 0u) >> gshift);
+        key[u] = grp | (atomicAdd(h + grp, 1u) << 12);
+      }
+    }
+    __syncthreads();
+    for (int k = tid; k < ngroups; k += COARSE_THREADS) {
+      const unsigned c = h[k];
+      gb[k] = c ? atomicAdd(gcursor + k, c) : 0u;  // this CTA's run inside group k
+    }
+    block_scan_inplace(h, ngroups, scratch);       // h -> local exclusive offsets (syncs inside)
+#pragma unroll
+    for (int u = 0; u < COARSE_PT; ++u) {
+      if (key[u] != 0xffffffffu) {
+        const int64_t i = c0 + u * COARSE_THREADS + tid;       // re-read (L2): keeps 8 records out of registers
+        const unsigned grp = key[u] & 0xfffu, pos = h[grp] + (key[u] >> 12);
+        stage[pos] = make_float4(grid_pos(p.x[i * p.stride], p.xmin, p.inv), grid_pos(p.y[i * p.stride], p.ymin, p.inv),
+                                 grid_pos(p.z[i * p.stride], p.zmin, p.inv), p.w ? p.w[i] : 1.0f);
+        skey[pos] = (unsigned short)grp;
+      }
+    }
+    __syncthreads();
+    for (int j = tid; j < m; j += COARSE_THREADS) {
+      const unsigned grp = skey[j];
+      tmp[gb[grp] + ((unsigned)j - h[grp])] = stage[j];        // consecutive j of a group -> consecutive slots
+    }
+    __syncthreads();
+  }
+}
+
+template <int ORDER, bool REFCIC>
+__global__ void __launch_bounds__(512) fine_scatter_kernel(const float4* __restrict__ tmp,
+                                                           const unsigned* __restrict__ gbase, TileGeom g,
+                                                           int gshift, int ngroups, int nbuckets,
+                                                           unsigned* __restrict__ offsets,
+                                                           float4* __restrict__ sorted) {
+  extern __shared__ unsigned fsm[];                // [G] counts -> offsets, [G] cursors, [33] scratch
+  const int G = 1 << gshift;
+  unsigned* fh = fsm;
+  unsigned* cur = fsm + G;
+  unsigned* scratch = cur + G;
+  const int grp = blockIdx.x;
+  const unsigned beg = gbase[grp], end = gbase[grp + 1];
+  const int t0 = grp << gshift;
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < G; i += blockDim.x) fh[i] = 0u;
+  __syncthreads();
+  // pass 1: histogram over the group's tiles (warp-aggregated: lanes with the same tile add once)
+  for (unsigned i0 = beg; i0 < end; i0 += blockDim.x) {
+    const unsigned i = i0 + threadIdx.x;
+    int f = -1;
+    if (i < end) {
+      const float4 r = tmp[i];
+      f = tile_of<ORDER, REFCIC>(r.x, r.y, r.z, g, 0u) - t0;
+    }
+    const unsigned same = __match_any_sync(0xffffffffu, f);
+    if (f >= 0 && lane == __ffs(same) - 1) atomicAdd(fh + f, (unsigned)__popc(same));
+  }
+  __syncthreads();
+  block_scan_inplace(fh, G, scratch);              // fh -> exclusive offsets inside the group
+  for (int i = threadIdx.x; i < G; i += blockDim.x) {
+    cur[i] = fh[i];
+    if (t0 + i < nbuckets) offsets[t0 + i] = beg + fh[i];
+  }
+  if (grp == ngroups - 1 && threadIdx.x == 0) offsets[nbuckets] = end;
+  __syncthreads();
+  // pass 2: place (the group's records are L2 resident by now)
+  for (unsigned i0 = beg; i0 < end; i0 += blockDim.x) {
+    const unsigned i = i0 + threadIdx.x;
+    int f = -1;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < end) {
+      r = tmp[i];
+      f = tile_of<ORDER, REFCIC>(r.x, r.y, r.z, g, 0u) - t0;
+    }
+    const unsigned same = __match_any_sync(0xffffffffu, f);
+    const int leader = __ffs(same) - 1;
+    unsigned base = 0;
+    if (f >= 0 && lane == leader) base = atomicAdd(cur + f, (unsigned)__popc(same));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (f >= 0) sorted[beg + base + __popc(same & ((1u << lane) - 1u))] = r;
+  }
+}
+
 // ---------------------------------------------------------------- K2: per-tile deposit
 __device__ __forceinline__ void red_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
@@ -591,7 +821,7 @@ __global__ void __launch_bounds__(256) paint_outliers_kernel(const float4* __res
 
 // ---------------------------------------------------------------- host side
 struct SortedLayout {
-  size_t sorted, counts, offsets, cursor, block_tot, wmax, total;
+  size_t sorted, tmp, counts, offsets, cursor, block_tot, wmax, gcounts, gbase, gcursor, total;
   int nbuckets;
 };
 
@@ -615,6 +845,10 @@ static SortedLayout sorted_layout(int n, int nx, int64_t n_part) {
   L.cursor = take((size_t)(L.nbuckets + 1) * 4);
   L.block_tot = take((size_t)(L.nbuckets / 2048 + 4) * 4);
   L.wmax = take(256);
+  L.tmp = take((size_t)(n_part > 0 ? n_part : 1) * sizeof(float4));       // coarse-partitioned records (K1 v2)
+  L.gcounts = take((size_t)(kMaxGroups + 1) * 4);
+  L.gbase = take((size_t)(kMaxGroups + 1) * 4);
+  L.gcursor = take((size_t)(kMaxGroups + 1) * 4);
   L.total = off;
   return L;
 }
@@ -679,6 +913,61 @@ static int run_bucket(const PaintParams& p, const TileGeom& g, const SortedLayou
   return JPS_OK;
 }
 
+// K1 v2 host side.  `g.rep` must be 1 (offsets are per tile).
+template <int ORDER, bool REFCIC>
+static int run_bucket_two_level(const PaintParams& p, const TileGeom& g, const SortedLayout& L, char* ws,
+                                cudaStream_t s) {
+  unsigned* offsets = (unsigned*)(ws + L.offsets);
+  float4* sorted = (float4*)(ws + L.sorted);
+  float4* tmp = (float4*)(ws + L.tmp);
+  unsigned* wmax_bits = (unsigned*)(ws + L.wmax);
+  unsigned* gcounts = (unsigned*)(ws + L.gcounts);
+  unsigned* gbase = (unsigned*)(ws + L.gbase);
+  unsigned* gcursor = (unsigned*)(ws + L.gcursor);
+  const int nbuckets = g.ntiles + 1;               // + the outlier bucket
+  int gshift = 0;
+  while (((nbuckets + (1 << gshift) - 1) >> gshift) > kMaxGroups) ++gshift;
+  const int ngroups = (nbuckets + (1 << gshift) - 1) >> gshift;
+  {
+    ScopedLaunch T(K_MEMSET, s);
+    JPS_CHECK_CUDA(cudaMemsetAsync(gcounts, 0, (size_t)(ngroups + 1) * 4, s));
+    JPS_CHECK_CUDA(cudaMemsetAsync(wmax_bits, 0, 4, s));
+  }
+  {
+    const int64_t want = (p.n_part + 256 * BUCKET_UNROLL - 1) / (256 * BUCKET_UNROLL);
+    ScopedLaunch T(K_BUCKET_COUNT, s);
+    coarse_count_kernel<ORDER, REFCIC><<<(int)std::min<int64_t>(want, (int64_t)kNumSMs * 8), 256, ngroups * 4, s>>>(
+        p, g, gshift, ngroups, gcounts, wmax_bits);
+  }
+  JPS_CHECK_LAUNCH();
+  {
+    ScopedLaunch T(K_BUCKET_SCAN, s);
+    group_scan_kernel<<<1, 1024, 0, s>>>(gcounts, gbase, gcursor, ngroups);
+  }
+  JPS_CHECK_LAUNCH();
+  {
+    const size_t smem = (size_t)COARSE_CHUNK * (sizeof(float4) + 2) + (size_t)ngroups * 8 + 33 * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+      JPS_CHECK_CUDA(cudaFuncSetAttribute(coarse_scatter_kernel<ORDER, REFCIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)((size_t)COARSE_CHUNK * (sizeof(float4) + 2) + (size_t)kMaxGroups * 8 + 33 * 4)));
+      attr_set = true;
+    }
+    const int64_t nchunks = (p.n_part + COARSE_CHUNK - 1) / COARSE_CHUNK;
+    ScopedLaunch T(K_BUCKET_SCATTER, s);
+    coarse_scatter_kernel<ORDER, REFCIC><<<(int)std::min<int64_t>(nchunks, kNumSMs), COARSE_THREADS, smem, s>>>(
+        p, g, gshift, ngroups, gcursor, tmp);
+  }
+  JPS_CHECK_LAUNCH();
+  {
+    const size_t smem = (size_t)(2 << gshift) * 4 + 33 * 4;
+    ScopedLaunch T(K_BUCKET_SCATTER, s);
+    fine_scatter_kernel<ORDER, REFCIC><<<ngroups, 512, smem, s>>>(tmp, gbase, g, gshift, ngroups, nbuckets, offsets, sorted);
+  }
+  JPS_CHECK_LAUNCH();
+  return JPS_OK;
+}
+
 // deposit a bucketed piece into the mesh on stream `s`
 template <int ORDER, bool REFCIC>
 static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayout& L, char* ws, cudaStream_t s) {
@@ -722,7 +1011,7 @@ template <int ORDER, bool REFCIC>
 static int run_sorted(const PaintParams& p, const TileGeom& g, char* ws, size_t ws_bytes, cudaStream_t s) {
   (void)ws_bytes;
   const SortedLayout L = sorted_layout(p.n, p.nx, p.n_part);
-  int rc = run_bucket<ORDER, REFCIC>(p, g, L, ws, s);
+  int rc = (g.rep == 1) ? run_bucket_two_level<ORDER, REFCIC>(p, g, L, ws, s) : run_bucket<ORDER, REFCIC>(p, g, L, ws, s);
   if (rc) return rc;
   return run_deposit<ORDER, REFCIC>(p, g, L, ws, s);
 }
@@ -744,7 +1033,9 @@ int paint_sorted(const PaintParams& p, int order, int compat, void* ws, size_t w
   g.nt = (p.n + TILE - 1) / TILE;
   g.ntx = (p.nx + TILE - 1) / TILE;
   g.ntiles = g.ntx * g.nt * g.nt;
-  g.rep = replicas_for(g.ntiles);
+  static const bool single_level = [] { const char* e = getenv("JPS_BUCKET"); return e && !strcmp(e, "atomic"); }();
+  // two-level partition: (ntiles+1) <= kMaxGroups groups x 2048 tiles; beyond that (n > 2500) fall back
+  g.rep = (!single_level && g.ntiles + 1 <= kMaxGroups * 2048) ? 1 : replicas_for(g.ntiles);
   char* w = (char*)ws;
   if (order == 2 && compat == JPS_COMPAT_REFERENCE) return run_sorted<2, true>(p, g, w, ws_bytes, s);
   if (order == 2) return run_sorted<2, false>(p, g, w, ws_bytes, s);
