@@ -194,6 +194,7 @@ ALGO_BYTES = {
     "paint_tile": lambda np_, n, w: np_ * 16 + 4 * n ** 3,
     "bucket_count": lambda np_, n, w: np_ * 12,
     "bucket_scatter": lambda np_, n, w: np_ * (12 + 4 * w) + np_ * 16,
+    "bucket_fine": lambda np_, n, w: np_ * 16 + np_ * 16,
     "pk_fold_bin": lambda np_, n, w: 8 * n * n * (n // 2 + 1),
     "cufft_r2c": lambda np_, n, w: 24 * n ** 3,
     "memset": lambda np_, n, w: 4 * n ** 3,

@@ -60,6 +60,7 @@ enum KernelId {
   K_BUCKET_COUNT,
   K_BUCKET_SCAN,
   K_BUCKET_SCATTER,
+  K_BUCKET_FINE,
   K_PAINT_TILE,
   K_PK_FOLD_BIN,
   K_PK_COUNT,

@@ -26,6 +26,7 @@ struct TileGeom {
   int nt;       // tiles per y / z axis = ceil(n / TILE)
   int ntx;      // tiles along x = ceil(nx / TILE)
   int ntiles;   // ntx * nt * nt
+  int two_level;  // 1: K1 v2 (two-level partition, rep == 1); 0: single-level atomic-cursor scatter
   int rep;      // counter replicas per tile (power of two): bucket = tile*rep + (block & (rep-1)).
                 // Same-address global atomics serialise in L2; with ~3000 particles per tile and
                 // ~3e5 threads in flight the single-counter version ran at half the red rate of
@@ -961,7 +962,7 @@ static int run_bucket_two_level(const PaintParams& p, const TileGeom& g, const S
   JPS_CHECK_LAUNCH();
   {
     const size_t smem = (size_t)(2 << gshift) * 4 + 33 * 4;
-    ScopedLaunch T(K_BUCKET_SCATTER, s);
+    ScopedLaunch T(K_BUCKET_FINE, s);
     fine_scatter_kernel<ORDER, REFCIC><<<ngroups, 512, smem, s>>>(tmp, gbase, g, gshift, ngroups, nbuckets, offsets, sorted);
   }
   JPS_CHECK_LAUNCH();
@@ -1011,7 +1012,7 @@ template <int ORDER, bool REFCIC>
 static int run_sorted(const PaintParams& p, const TileGeom& g, char* ws, size_t ws_bytes, cudaStream_t s) {
   (void)ws_bytes;
   const SortedLayout L = sorted_layout(p.n, p.nx, p.n_part);
-  int rc = (g.rep == 1) ? run_bucket_two_level<ORDER, REFCIC>(p, g, L, ws, s) : run_bucket<ORDER, REFCIC>(p, g, L, ws, s);
+  int rc = g.two_level ? run_bucket_two_level<ORDER, REFCIC>(p, g, L, ws, s) : run_bucket<ORDER, REFCIC>(p, g, L, ws, s);
   if (rc) return rc;
   return run_deposit<ORDER, REFCIC>(p, g, L, ws, s);
 }
@@ -1033,9 +1034,18 @@ int paint_sorted(const PaintParams& p, int order, int compat, void* ws, size_t w
   g.nt = (p.n + TILE - 1) / TILE;
   g.ntx = (p.nx + TILE - 1) / TILE;
   g.ntiles = g.ntx * g.nt * g.nt;
-  static const bool single_level = [] { const char* e = getenv("JPS_BUCKET"); return e && !strcmp(e, "atomic"); }();
-  // two-level partition: (ntiles+1) <= kMaxGroups groups x 2048 tiles; beyond that (n > 2500) fall back
-  g.rep = (!single_level && g.ntiles + 1 <= kMaxGroups * 2048) ? 1 : replicas_for(g.ntiles);
+  // Bucketing flavour.  Measured on C2 (N=512, 1e8 particles): single-level 0.60 + 2.36 ms, two-level
+  // 0.38 + 1.36 + 1.32 ms -- a tie, because the two-level version reads the records twice in its fine
+  // pass.  The single-level scatter relies on L2 keeping one write frontier (128 B) per tile, so it is
+  // the default while those fit comfortably (<= 600 K tiles ~ 77 MB); beyond, the two-level partition
+  // (<= 2^gshift frontiers per resident group) takes over.  JPS_BUCKET=atomic|two forces one.
+  static const int forced = [] {
+    const char* e = getenv("JPS_BUCKET");
+    return !e ? 0 : !strcmp(e, "atomic") ? 1 : !strcmp(e, "two") ? 2 : 0;
+  }();
+  const bool fits_two = g.ntiles + 1 <= kMaxGroups * 2048;
+  g.two_level = (forced == 2 && fits_two) || (forced == 0 && g.ntiles > 600000 && fits_two) ? 1 : 0;
+  g.rep = g.two_level ? 1 : replicas_for(g.ntiles);
   char* w = (char*)ws;
   if (order == 2 && compat == JPS_COMPAT_REFERENCE) return run_sorted<2, true>(p, g, w, ws_bytes, s);
   if (order == 2) return run_sorted<2, false>(p, g, w, ws_bytes, s);

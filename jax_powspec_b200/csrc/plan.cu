@@ -16,7 +16,7 @@ void set_error(const char* fmt, ...) {
 
 // ---------------------------------------------------------------- launch accounting
 static const char* kKernelNames[K_NUM] = {
-    "paint_atomic", "bucket_count", "bucket_scan", "bucket_scatter", "paint_tile", "pk_fold_bin",
+    "paint_atomic", "bucket_count", "bucket_scan", "bucket_scatter", "bucket_fine", "paint_tile", "pk_fold_bin",
     "pk_count_modes", "pk_finalize", "cufft_r2c", "cufft_c2r", "memset", "shell_filter",
     "triple_reduce", "xi_bin", "misc"};
 
