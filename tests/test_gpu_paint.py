@@ -164,3 +164,13 @@ def test_float32_grid_position_is_not_fused(jps, order, compat, method):
                     order=order, compat=compat, method=method)
     err = np.abs(got - want) / np.maximum(np.abs(want), 1.0)
     assert err.max() < 2e-6, f"max error relative to max(|cell|,1): {err.max():.3e}"
+
+
+def test_two_level_partition_in_subprocess():
+    """The bucketing flavour is chosen once per process (JPS_BUCKET); run the two-level partition in its own."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, JPS_BUCKET="two")
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "helpers", "two_level_check.py")],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "two-level ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
