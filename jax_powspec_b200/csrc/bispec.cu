@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) shell_filter_kernel(const float2* __restr
     const float wxy = wl[ix] * wl[iy];
     const float2* src = dk + (size_t)row * pitch;
     float2* dd = out_delta + (size_t)row * pitch;
-    float2* di = out_ind + (size_t)row * pitch;
+    float2* di = out_ind ? out_ind + (size_t)row * pitch : nullptr;   // indicator only when its sums are not cached
     for (int kz = threadIdx.x; kz < pitch; kz += blockDim.x) {
       float2 od = make_float2(0.0f, 0.0f), oi = make_float2(0.0f, 0.0f);
       if (kz < nz) {
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) shell_filter_kernel(const float2* __restr
         }
       }
       dd[kz] = od;
-      di[kz] = oi;
+      if (di) di[kz] = oi;
     }
   }
 }
@@ -66,8 +66,10 @@ __global__ void __launch_bounds__(256) triple_reduce_kernel(const float* __restr
                                                             const float* __restrict__ i0,
                                                             const float* __restrict__ i1,
                                                             const float* __restrict__ i3, int n,
-                                                            int rowpitch, int triple,
-                                                            double* __restrict__ out) {
+                                                            int rowpitch, int triple, int with_ind,
+                                                            double* __restrict__ out,
+                                                            double* __restrict__ out_i2,
+                                                            double* __restrict__ out_i3) {
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   const long long rows = (long long)n * n;
   const int half = n / 2;                         // float2 loads (rows are 8-byte aligned, n even)
@@ -78,26 +80,32 @@ __global__ void __launch_bounds__(256) triple_reduce_kernel(const float* __restr
     if (vec) {
       for (int j = threadIdx.x; j < half; j += blockDim.x) {
         const float2 x3 = *reinterpret_cast<const float2*>(d3 + base + 2 * j);
-        const float2 y3 = *reinterpret_cast<const float2*>(i3 + base + 2 * j);
         s0 += x3.x * x3.x + x3.y * x3.y;
-        s1 += y3.x * y3.x + y3.y * y3.y;
+        float2 y3 = make_float2(0.0f, 0.0f);
+        if (with_ind) {
+          y3 = *reinterpret_cast<const float2*>(i3 + base + 2 * j);
+          s1 += y3.x * y3.x + y3.y * y3.y;
+        }
         if (triple) {
           const float2 x0 = *reinterpret_cast<const float2*>(d0 + base + 2 * j);
           const float2 x1 = *reinterpret_cast<const float2*>(d1 + base + 2 * j);
-          const float2 y0 = *reinterpret_cast<const float2*>(i0 + base + 2 * j);
-          const float2 y1 = *reinterpret_cast<const float2*>(i1 + base + 2 * j);
           s2 += x0.x * x1.x * x3.x + x0.y * x1.y * x3.y;
-          s3 += y0.x * y1.x * y3.x + y0.y * y1.y * y3.y;
+          if (with_ind) {
+            const float2 y0 = *reinterpret_cast<const float2*>(i0 + base + 2 * j);
+            const float2 y1 = *reinterpret_cast<const float2*>(i1 + base + 2 * j);
+            s3 += y0.x * y1.x * y3.x + y0.y * y1.y * y3.y;
+          }
         }
       }
     } else {
       for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        const float x3 = d3[base + j], y3 = i3[base + j];
+        const float x3 = d3[base + j];
+        const float y3 = with_ind ? i3[base + j] : 0.0f;
         s0 += x3 * x3;
         s1 += y3 * y3;
         if (triple) {
           s2 += d0[base + j] * d1[base + j] * x3;
-          s3 += i0[base + j] * i1[base + j] * y3;
+          if (with_ind) s3 += i0[base + j] * i1[base + j] * y3;
         }
       }
     }
@@ -118,27 +126,34 @@ __global__ void __launch_bounds__(256) triple_reduce_kernel(const float* __restr
   if (threadIdx.x < 4) {
     double t = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
-    if (threadIdx.x < 2 || triple) atomicAdd(out + threadIdx.x, t);
+    // data sums go to the per-call scratch, indicator sums to their cached device slots
+    if (threadIdx.x == 0) atomicAdd(out + 0, t);
+    if (threadIdx.x == 2 && triple) atomicAdd(out + 1, t);
+    if (threadIdx.x == 1 && with_ind) atomicAdd(out_i2, t);
+    if (threadIdx.x == 3 && triple && with_ind) atomicAdd(out_i3, t);
   }
 }
 
-// scal layout: [4*j + 0..3] for shell j: sum d^2, sum I^2, sum d0 d1 d_j, sum I0 I1 I_j
-__global__ void bispec_finalize_kernel(const double* __restrict__ scal, int nshell, double vol_p,
+// scal layout: [2*j + 0..1] for shell j: sum d_j^2, sum d_0 d_1 d_j.  The indicator sums
+// sum I_j^2 / sum I_0 I_1 I_j live in isum[slot2[j]] / isum[slot3[j]] (slots passed in `slots`:
+// [nshell] pair slots then [nshell] triple slots).
+__global__ void bispec_finalize_kernel(const double* __restrict__ scal, const double* __restrict__ isum,
+                                       const int* __restrict__ slots, int nshell, double vol_p,
                                        double vol_b, float* __restrict__ pk, float* __restrict__ B,
                                        float* __restrict__ Q) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nshell) return;
-  const double pj = scal[4 * j] / scal[4 * j + 1] * vol_p;
+  const double pj = scal[2 * j] / isum[slots[j]] * vol_p;
   pk[j] = (float)pj;
   if (j >= 2) {
-    const double p0 = scal[0] / scal[1] * vol_p, p1 = scal[4] / scal[5] * vol_p;
-    const double b = scal[4 * j + 2] / scal[4 * j + 3] * vol_b;
+    const double p0 = scal[0] / isum[slots[0]] * vol_p, p1 = scal[2] / isum[slots[1]] * vol_p;
+    const double b = scal[2 * j + 1] / isum[slots[nshell + j]] * vol_b;
     B[j - 2] = (float)b;
     Q[j - 2] = (float)(b / (p0 * p1 + p0 * pj + p1 * pj));
   }
 }
 
-constexpr int kMaxShells = 250;      // 4 doubles per shell in the 1024-double scratch
+constexpr int kMaxShells = 250;      // 2 doubles per shell + 2 ints per shell (slots) in the 1024-double scratch
 
 // Bispectrum stage given plan->dk.  Needs 6 shell fields: d0, d1, i0, i1 and a (d3, i3) pair.
 int bispec_from_dk(jps_plan* plan, int normalise, float box_size, float k1, float k2,
@@ -167,9 +182,35 @@ int bispec_from_dk(jps_plan* plan, int normalise, float box_size, float k1, floa
     thi[(size_t)j] = (int)edge_threshold(hi, false, plan->k2max);     // |k| <  hi
   }
   JPS_CHECK_CUDA(cudaMemcpyAsync(k_all_out, k_all.data(), (size_t)nshell * 4, cudaMemcpyHostToDevice, s));
+  // cached indicator sums: find / assign device slots
+  if ((int)plan->isum_slot.size() + 2 * nshell > kIsumSlots) plan->isum_slot.clear();   // simple eviction
+  std::vector<int> slots((size_t)2 * nshell, 0);
+  std::vector<char> fresh2((size_t)nshell, 0), fresh3((size_t)nshell, 0);
+  auto slot_of = [&](const std::vector<int>& key, char& fresh) {
+    auto it = plan->isum_slot.find(key);
+    if (it != plan->isum_slot.end()) { fresh = 0; return it->second; }
+    const int sidx = (int)plan->isum_slot.size();
+    plan->isum_slot[key] = sidx;
+    fresh = 1;
+    return sidx;
+  };
+  for (int j = 0; j < nshell; ++j) {
+    slots[(size_t)j] = slot_of({tlo[(size_t)j], thi[(size_t)j]}, fresh2[(size_t)j]);
+    if (j >= 2)
+      slots[(size_t)nshell + j] = slot_of({tlo[0], thi[0], tlo[1], thi[1], tlo[(size_t)j], thi[(size_t)j]}, fresh3[(size_t)j]);
+  }
+  // a fresh triple needs I_0 and I_1 as fields: recompute them even if their own sums are cached
+  bool any_fresh3 = false;
+  for (int j = 2; j < nshell; ++j) any_fresh3 = any_fresh3 || fresh3[(size_t)j];
+  for (int j = 0; j < nshell; ++j) {
+    if (fresh2[(size_t)j]) JPS_CHECK_CUDA(cudaMemsetAsync(plan->isum + slots[(size_t)j], 0, 8, s));
+    if (j >= 2 && fresh3[(size_t)j]) JPS_CHECK_CUDA(cudaMemsetAsync(plan->isum + slots[(size_t)nshell + j], 0, 8, s));
+  }
+  int* slots_dev = reinterpret_cast<int*>(plan->scal + 768);        // tail of the 1024-double scratch
+  JPS_CHECK_CUDA(cudaMemcpyAsync(slots_dev, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, s));
   {
     ScopedLaunch L(K_MEMSET, s);
-    JPS_CHECK_CUDA(cudaMemsetAsync(plan->scal, 0, 1024 * sizeof(double), s));
+    JPS_CHECK_CUDA(cudaMemsetAsync(plan->scal, 0, 762 * sizeof(double), s));   // sums + dump; [768..) holds the slot table
   }
   const size_t field_floats = (size_t)n * n * 2 * plan->pitch;
   float* F[6];
@@ -182,24 +223,34 @@ int bispec_from_dk(jps_plan* plan, int normalise, float box_size, float k1, floa
   for (int j = 0; j < nshell; ++j) {
     float* dj = (j == 0) ? F[0] : (j == 1) ? F[1] : F[4];
     float* ij = (j == 0) ? F[2] : (j == 1) ? F[3] : F[5];
+    // the indicator field of this shell is needed if one of its sums is not cached yet
+    // (shells 0 and 1: also when any triple with them is new)
+    const bool need_ind = fresh2[(size_t)j] || (j >= 2 && fresh3[(size_t)j]) || (j < 2 && any_fresh3);
     {
       ScopedLaunch L(K_SHELL_FILTER, s);
       shell_filter_kernel<<<fblocks, 256, 0, s>>>(plan->dk, n, plan->nz, plan->pitch, wl, normalise,
-                                                  tlo[(size_t)j], thi[(size_t)j], (float2*)dj, (float2*)ij);
+                                                  tlo[(size_t)j], thi[(size_t)j], (float2*)dj,
+                                                  need_ind ? (float2*)ij : nullptr);
     }
     JPS_CHECK_LAUNCH();
     {
       ScopedLaunch L(K_FFT_C2R, s);
       JPS_CHECK_CUFFT(cufftExecC2R(plan->c2r, (cufftComplex*)dj, (cufftReal*)dj));
     }
-    {
+    if (need_ind) {
       ScopedLaunch L(K_FFT_C2R, s);
       JPS_CHECK_CUFFT(cufftExecC2R(plan->c2r, (cufftComplex*)ij, (cufftReal*)ij));
     }
     {
+      // with_ind: accumulate the indicator sums of this shell.  A cached pair sum must not be added
+      // to again: route it to a dummy slot when only the triple is fresh.
+      const int with_ind = need_ind && (fresh2[(size_t)j] || (j >= 2 && fresh3[(size_t)j])) ? 1 : 0;
+      double* dump = plan->scal + 760;
+      double* o2 = fresh2[(size_t)j] ? plan->isum + slots[(size_t)j] : dump;
+      double* o3 = (j >= 2 && fresh3[(size_t)j]) ? plan->isum + slots[(size_t)nshell + j] : dump + 1;
       ScopedLaunch L(K_TRIPLE_REDUCE, s);
       triple_reduce_kernel<<<rblocks, 256, 0, s>>>(F[0], F[1], dj, F[2], F[3], ij, n, 2 * plan->pitch,
-                                                   j >= 2 ? 1 : 0, plan->scal + 4 * j);
+                                                   j >= 2 ? 1 : 0, with_ind, plan->scal + 2 * j, o2, o3);
     }
     JPS_CHECK_LAUNCH();
   }
@@ -207,8 +258,9 @@ int bispec_from_dk(jps_plan* plan, int normalise, float box_size, float k1, floa
   const float tb = (box_size * box_size) / (float)((long long)n * n * n);   // (box_size**2 / dims**3)**3, :451
   {
     ScopedLaunch L(K_PK_FINALIZE, s);
-    bispec_finalize_kernel<<<(nshell + 127) / 128, 128, 0, s>>>(plan->scal, nshell, (double)(tp * tp * tp),
-                                                               (double)(tb * tb * tb), pk_out, B_out, Q_out);
+    bispec_finalize_kernel<<<(nshell + 127) / 128, 128, 0, s>>>(plan->scal, plan->isum, slots_dev, nshell,
+                                                               (double)(tp * tp * tp), (double)(tb * tb * tb),
+                                                               pk_out, B_out, Q_out);
   }
   JPS_CHECK_LAUNCH();
   return JPS_OK;

@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -91,6 +92,7 @@ constexpr int kMaxSmemBins = 576;
 // Up to this many bins one shared accumulator set per CTA is used (shared atomics by segment
 // heads); above it the kernels fall back to global float64 reds.
 constexpr int kMaxBlockBins = 8192;
+constexpr int kIsumSlots = 4096;
 enum AccMode { ACC_WARP = 0, ACC_BLOCK = 1, ACC_GLOBAL = 2 };
 constexpr int kMaxUserBins = 1 << 18;
 
@@ -145,6 +147,11 @@ struct jps_plan {
   float* wlut = nullptr;        // [3][n] per-axis window factors for p = 2,3,4
   double* acc = nullptr;        // [acc_cap][4] per-call sums of the l=0,2,4 weights (4th slot spare)
   double* scal = nullptr;       // [1024] small float64 scratch (bispectrum sums)
+  // Sums over the shell INDICATOR fields (sum I_j^2, sum I_0 I_1 I_j) depend only on (N, shell
+  // bounds), not on the data: they are computed once, kept ON THE DEVICE in `isum` (so no host
+  // read-back / synchronisation is ever needed) and found again through this host-side key -> slot map.
+  double* isum = nullptr;       // [kIsumSlots]
+  std::map<std::vector<int>, int> isum_slot;
   float* shell = nullptr;       // n_shell_fields real fields [n][n][2*pitch] (in-place C2R layout)
   int acc_cap = 0;
 

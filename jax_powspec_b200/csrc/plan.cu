@@ -82,7 +82,7 @@ struct TableLayout {
 };
 
 struct Layout {
-  size_t dk, fft_work, wlut, acc, scal, shell, total;
+  size_t dk, fft_work, wlut, acc, scal, isum, shell, total;
   TableLayout t[kNumTables];
   int cap;
 };
@@ -108,6 +108,7 @@ static Layout make_layout(int n, int pitch, size_t fft_work_bytes, int n_shell_f
   L.wlut = take((size_t)3 * n * 4);
   L.acc = take((size_t)L.cap * 4 * 8);
   L.scal = take((size_t)1024 * 8);
+  L.isum = take((size_t)kIsumSlots * 8);
   L.shell = take((size_t)n_shell_fields * n * n * pitch * sizeof(float2));
   L.total = off;
   return L;
@@ -239,6 +240,7 @@ extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* 
   p->wlut = (float*)(ws + L.wlut);
   p->acc = (double*)(ws + L.acc);
   p->scal = (double*)(ws + L.scal);
+  p->isum = (double*)(ws + L.isum);
   p->shell = (float*)(ws + L.shell);
   p->acc_cap = L.cap;
   cufftResult r = CUFFT_SUCCESS;

@@ -122,3 +122,26 @@ def test_xi_n128_oracle(jps):
     _, xi64, counts = oc.xi(delta, box, se, precision="f64", guard_mu=True)
     np.testing.assert_array_equal(nm.astype(np.int64), counts)
     _close_scaled(xi, xi64, 1e-5)
+
+
+def test_bispec_indicator_cache_is_transparent(jps, golden_dir):
+    """The sums over the shell indicator fields are data independent and cached on the device after the
+    first call: repeated calls, calls with other (k1,k2) in between and calls on other data must agree
+    with a cold computation."""
+    from jax_powspec_b200.plan import clear_plans
+    g = np.load(os.path.join(golden_dir, "ref_corr_a.npz"))
+    delta, box = g["delta"], float(g["box"])
+    k1, k2, th = float(g["bk_k1"]), float(g["bk_k2"]), g["bk_theta"]
+    clear_plans()
+    cold = jps.bispec(delta, box, k1, k2, th)
+    warm = jps.bispec(delta, box, k1, k2, th)                  # everything cached
+    for a, b in zip(cold, warm):
+        np.testing.assert_allclose(a, b, rtol=2e-6, equal_nan=True)
+    other = jps.bispec(delta, box, 0.8 * k1, k2, th)           # new triples, partly cached pairs
+    back = jps.bispec(2.0 * delta, box, k1, k2, th)            # other data, cached geometry
+    np.testing.assert_allclose(back[3], 8.0 * cold[3], rtol=1e-5)      # B scales as delta^3
+    np.testing.assert_allclose(back[1], 4.0 * cold[1], rtol=1e-5)      # P scales as delta^2
+    clear_plans()
+    cold_other = jps.bispec(delta, box, 0.8 * k1, k2, th)
+    for a, b in zip(other, cold_other):
+        np.testing.assert_allclose(a, b, rtol=2e-6, equal_nan=True)
