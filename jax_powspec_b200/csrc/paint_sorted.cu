@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(PaintParams p, Tile
 //                        histogram over the group's tiles -> tile offsets -> second pass places every
 //                        record with a warp-aggregated SHARED cursor; writes go to <= 2^gshift
 //                        frontiers per resident group, which L2 merges into full lines.
-constexpr int COARSE_CHUNK = 8192;
+constexpr int COARSE_CHUNK = 4096;                 // 64 KB of staged records: two CTAs per SM overlap their phases
 constexpr int COARSE_THREADS = 1024;
 constexpr int COARSE_PT = COARSE_CHUNK / COARSE_THREADS;
 constexpr int kMaxGroups = 2048;
@@ -403,6 +403,17 @@ __global__ void __launch_bounds__(1024) group_scan_kernel(const unsigned* __rest
   if (threadIdx.x == 0) gbase[ngroups] = total;
 }
 
+// group bases from per-tile offsets: gbase[g] = offsets[g << gshift], gbase[ngroups] = total
+__global__ void group_bases_from_offsets_kernel(const unsigned* __restrict__ offsets, int nbuckets, int gshift,
+                                                int ngroups, unsigned* __restrict__ gbase,
+                                                unsigned* __restrict__ gcursor) {
+  const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gidx > ngroups) return;
+  const unsigned v = offsets[min(gidx << gshift, nbuckets)];
+  gbase[gidx] = v;
+  if (gidx < ngroups) gcursor[gidx] = v;
+}
+
 template <int ORDER, bool REFCIC>
 __global__ void __launch_bounds__(COARSE_THREADS) coarse_scatter_kernel(PaintParams p, TileGeom g, int gshift,
                                                                         int ngroups,
@@ -422,16 +433,16 @@ __global__ void __launch_bounds__(COARSE_THREADS) coarse_scatter_kernel(PaintPar
     for (int i = tid; i < ngroups; i += COARSE_THREADS) h[i] = 0u;
     __syncthreads();
     unsigned key[COARSE_PT];                       // group | rank << 12
+    float4 rec[COARSE_PT];                         // the records stay in registers (4 per thread)
 #pragma unroll
     for (int u = 0; u < COARSE_PT; ++u) {
       const int j = u * COARSE_THREADS + tid;
       key[u] = 0xffffffffu;
       if (j < m) {
         const int64_t i = c0 + j;
-        const float px = grid_pos(p.x[i * p.stride], p.xmin, p.inv);
-        const float py = grid_pos(p.y[i * p.stride], p.ymin, p.inv);
-        const float pz = grid_pos(p.z[i * p.stride], p.zmin, p.inv);
-        const unsigned grp = (unsigned)(tile_of<ORDER, REFCIC>(px, py, pz, g, 0u) >> gshift);
+        rec[u] = make_float4(grid_pos(p.x[i * p.stride], p.xmin, p.inv), grid_pos(p.y[i * p.stride], p.ymin, p.inv),
+                             grid_pos(p.z[i * p.stride], p.zmin, p.inv), p.w ? p.w[i] : 1.0f);
+        const unsigned grp = (unsigned)(tile_of<ORDER, REFCIC>(rec[u].x, rec[u].y, rec[u].z, g, 0u) >> gshift);
         key[u] = grp | (atomicAdd(h + grp, 1u) << 12);
       }
     }
@@ -444,10 +455,8 @@ __global__ void __launch_bounds__(COARSE_THREADS) coarse_scatter_kernel(PaintPar
 #pragma unroll
     for (int u = 0; u < COARSE_PT; ++u) {
       if (key[u] != 0xffffffffu) {
-        const int64_t i = c0 + u * COARSE_THREADS + tid;       // re-read (L2): keeps 8 records out of registers
         const unsigned grp = key[u] & 0xfffu, pos = h[grp] + (key[u] >> 12);
-        stage[pos] = make_float4(grid_pos(p.x[i * p.stride], p.xmin, p.inv), grid_pos(p.y[i * p.stride], p.ymin, p.inv),
-                                 grid_pos(p.z[i * p.stride], p.zmin, p.inv), p.w ? p.w[i] : 1.0f);
+        stage[pos] = rec[u];
         skey[pos] = (unsigned short)grp;
       }
     }
@@ -460,11 +469,13 @@ __global__ void __launch_bounds__(COARSE_THREADS) coarse_scatter_kernel(PaintPar
   }
 }
 
-template <int ORDER, bool REFCIC>
+// HAVE_OFFSETS: the per-tile offsets already exist (small meshes: the shared-memory tile histogram
+// of bucket_count_smem_kernel), so the group's records are read ONCE; otherwise pass 1 builds them.
+template <int ORDER, bool REFCIC, bool HAVE_OFFSETS>
 __global__ void __launch_bounds__(512) fine_scatter_kernel(const float4* __restrict__ tmp,
                                                            const unsigned* __restrict__ gbase, TileGeom g,
                                                            int gshift, int ngroups, int nbuckets,
-                                                           unsigned* __restrict__ offsets,
+                                                           unsigned* offsets,
                                                            float4* __restrict__ sorted) {
   extern __shared__ unsigned fsm[];                // [G] counts -> offsets, [G] cursors, [33] scratch
   const int G = 1 << gshift;
@@ -475,18 +486,31 @@ __global__ void __launch_bounds__(512) fine_scatter_kernel(const float4* __restr
   const unsigned beg = gbase[grp], end = gbase[grp + 1];
   const int t0 = grp << gshift;
   const int lane = threadIdx.x & 31;
+  constexpr int FINE_UNR = 4;                      // records in flight per thread
+  if (HAVE_OFFSETS) {
+    for (int i = threadIdx.x; i < G; i += blockDim.x)
+      cur[i] = (t0 + i < nbuckets) ? offsets[t0 + i] - beg : 0u;
+    __syncthreads();
+  } else {
   for (int i = threadIdx.x; i < G; i += blockDim.x) fh[i] = 0u;
   __syncthreads();
   // pass 1: histogram over the group's tiles (warp-aggregated: lanes with the same tile add once)
-  for (unsigned i0 = beg; i0 < end; i0 += blockDim.x) {
-    const unsigned i = i0 + threadIdx.x;
-    int f = -1;
-    if (i < end) {
-      const float4 r = tmp[i];
-      f = tile_of<ORDER, REFCIC>(r.x, r.y, r.z, g, 0u) - t0;
+  for (unsigned i0 = beg; i0 < end; i0 += FINE_UNR * blockDim.x) {
+    float4 r[FINE_UNR];
+    bool ok[FINE_UNR];
+#pragma unroll
+    for (int u = 0; u < FINE_UNR; ++u) {
+      const unsigned i = i0 + u * blockDim.x + threadIdx.x;
+      ok[u] = i < end;
+      if (ok[u]) r[u] = tmp[i];
     }
-    const unsigned same = __match_any_sync(0xffffffffu, f);
-    if (f >= 0 && lane == __ffs(same) - 1) atomicAdd(fh + f, (unsigned)__popc(same));
+#pragma unroll
+    for (int u = 0; u < FINE_UNR; ++u) {
+      if (i0 + u * blockDim.x >= end) break;       // CTA-uniform
+      const int f = ok[u] ? tile_of<ORDER, REFCIC>(r[u].x, r[u].y, r[u].z, g, 0u) - t0 : -1;
+      const unsigned same = __match_any_sync(0xffffffffu, f);
+      if (f >= 0 && lane == __ffs(same) - 1) atomicAdd(fh + f, (unsigned)__popc(same));
+    }
   }
   __syncthreads();
   block_scan_inplace(fh, G, scratch);              // fh -> exclusive offsets inside the group
@@ -496,21 +520,28 @@ __global__ void __launch_bounds__(512) fine_scatter_kernel(const float4* __restr
   }
   if (grp == ngroups - 1 && threadIdx.x == 0) offsets[nbuckets] = end;
   __syncthreads();
-  // pass 2: place (the group's records are L2 resident by now)
-  for (unsigned i0 = beg; i0 < end; i0 += blockDim.x) {
-    const unsigned i = i0 + threadIdx.x;
-    int f = -1;
-    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < end) {
-      r = tmp[i];
-      f = tile_of<ORDER, REFCIC>(r.x, r.y, r.z, g, 0u) - t0;
+  }
+  // pass 2: place
+  for (unsigned i0 = beg; i0 < end; i0 += FINE_UNR * blockDim.x) {
+    float4 r[FINE_UNR];
+    bool ok[FINE_UNR];
+#pragma unroll
+    for (int u = 0; u < FINE_UNR; ++u) {
+      const unsigned i = i0 + u * blockDim.x + threadIdx.x;
+      ok[u] = i < end;
+      if (ok[u]) r[u] = tmp[i];
     }
-    const unsigned same = __match_any_sync(0xffffffffu, f);
-    const int leader = __ffs(same) - 1;
-    unsigned base = 0;
-    if (f >= 0 && lane == leader) base = atomicAdd(cur + f, (unsigned)__popc(same));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (f >= 0) sorted[beg + base + __popc(same & ((1u << lane) - 1u))] = r;
+#pragma unroll
+    for (int u = 0; u < FINE_UNR; ++u) {
+      if (i0 + u * blockDim.x >= end) break;       // CTA-uniform
+      const int f = ok[u] ? tile_of<ORDER, REFCIC>(r[u].x, r[u].y, r[u].z, g, 0u) - t0 : -1;
+      const unsigned same = __match_any_sync(0xffffffffu, f);
+      const int leader = __ffs(same) - 1;
+      unsigned base = 0;
+      if (f >= 0 && lane == leader) base = atomicAdd(cur + f, (unsigned)__popc(same));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (f >= 0) sorted[beg + base + __popc(same & ((1u << lane) - 1u))] = r[u];
+    }
   }
 }
 
@@ -827,9 +858,9 @@ struct SortedLayout {
 };
 
 static int replicas_for(int ntiles) {
-  if (ntiles <= kSmemCountMaxTiles) return 1;      // shared-memory histogram: no same-address pressure
-  static const int rep_max = [] { const char* e = getenv("JPS_BUCKET_REP"); return e ? atoi(e) : 8; }();
-  int rep = rep_max;
+  static const int rep_env = [] { const char* e = getenv("JPS_BUCKET_REP"); return e ? atoi(e) : 0; }();
+  if (!rep_env && ntiles <= kSmemCountMaxTiles) return 1;   // shared-memory histogram: no same-address pressure
+  int rep = rep_env ? rep_env : 8;
   while (rep > 1 && (long long)ntiles * rep > (1 << 19)) rep >>= 1;   // keep the scan + hot lines small
   return rep;
 }
@@ -929,6 +960,40 @@ static int run_bucket_two_level(const PaintParams& p, const TileGeom& g, const S
   int gshift = 0;
   while (((nbuckets + (1 << gshift) - 1) >> gshift) > kMaxGroups) ++gshift;
   const int ngroups = (nbuckets + (1 << gshift) - 1) >> gshift;
+  const bool have_offsets = g.ntiles <= kSmemCountMaxTiles;     // tile histogram fits one SM's shared memory
+  if (have_offsets) {
+    // tile-level histogram (shared-memory privatised) + scan -> offsets[]; group bases are a sample of it
+    unsigned* counts = (unsigned*)(ws + L.counts);
+    unsigned* cursor = (unsigned*)(ws + L.cursor);
+    {
+      ScopedLaunch T(K_MEMSET, s);
+      JPS_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)(nbuckets + 1) * 4, s));
+      JPS_CHECK_CUDA(cudaMemsetAsync(wmax_bits, 0, 4, s));
+    }
+    {
+      const int smem = (g.ntiles + 1) * (int)sizeof(unsigned);
+      static bool attr_set = false;
+      if (!attr_set) {
+        JPS_CHECK_CUDA(cudaFuncSetAttribute(bucket_count_smem_kernel<ORDER, REFCIC>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (kSmemCountMaxTiles + 1) * (int)sizeof(unsigned)));
+        attr_set = true;
+      }
+      const int64_t w1 = (p.n_part + 1024 * BUCKET_UNROLL - 1) / (1024 * BUCKET_UNROLL);
+      ScopedLaunch T(K_BUCKET_COUNT, s);
+      bucket_count_smem_kernel<ORDER, REFCIC><<<(int)std::min<int64_t>(w1, kNumSMs), 1024, smem, s>>>(p, g, counts, wmax_bits);
+    }
+    JPS_CHECK_LAUNCH();
+    {
+      const int nsb = (nbuckets + SCAN_BLOCK - 1) / SCAN_BLOCK;
+      unsigned* block_tot = (unsigned*)(ws + L.block_tot);
+      { ScopedLaunch T(K_BUCKET_SCAN, s); scan_block_totals_kernel<<<nsb, SCAN_THREADS, 0, s>>>(counts, block_tot, nbuckets); }
+      { ScopedLaunch T(K_BUCKET_SCAN, s); scan_of_totals_kernel<<<1, SCAN_THREADS, 0, s>>>(block_tot, nsb); }
+      { ScopedLaunch T(K_BUCKET_SCAN, s); scan_write_kernel<<<nsb, SCAN_THREADS, 0, s>>>(counts, block_tot, offsets, cursor, nbuckets, nsb); }
+      { ScopedLaunch T(K_BUCKET_SCAN, s); group_bases_from_offsets_kernel<<<(ngroups + 256) / 256, 256, 0, s>>>(offsets, nbuckets, gshift, ngroups, gbase, gcursor); }
+    }
+    JPS_CHECK_LAUNCH();
+  } else {
   {
     ScopedLaunch T(K_MEMSET, s);
     JPS_CHECK_CUDA(cudaMemsetAsync(gcounts, 0, (size_t)(ngroups + 1) * 4, s));
@@ -946,6 +1011,7 @@ static int run_bucket_two_level(const PaintParams& p, const TileGeom& g, const S
     group_scan_kernel<<<1, 1024, 0, s>>>(gcounts, gbase, gcursor, ngroups);
   }
   JPS_CHECK_LAUNCH();
+  }
   {
     const size_t smem = (size_t)COARSE_CHUNK * (sizeof(float4) + 2) + (size_t)ngroups * 8 + 33 * 4;
     static bool attr_set = false;
@@ -956,14 +1022,17 @@ static int run_bucket_two_level(const PaintParams& p, const TileGeom& g, const S
     }
     const int64_t nchunks = (p.n_part + COARSE_CHUNK - 1) / COARSE_CHUNK;
     ScopedLaunch T(K_BUCKET_SCATTER, s);
-    coarse_scatter_kernel<ORDER, REFCIC><<<(int)std::min<int64_t>(nchunks, kNumSMs), COARSE_THREADS, smem, s>>>(
+    coarse_scatter_kernel<ORDER, REFCIC><<<(int)std::min<int64_t>(nchunks, 2 * kNumSMs), COARSE_THREADS, smem, s>>>(
         p, g, gshift, ngroups, gcursor, tmp);
   }
   JPS_CHECK_LAUNCH();
   {
     const size_t smem = (size_t)(2 << gshift) * 4 + 33 * 4;
     ScopedLaunch T(K_BUCKET_FINE, s);
-    fine_scatter_kernel<ORDER, REFCIC><<<ngroups, 512, smem, s>>>(tmp, gbase, g, gshift, ngroups, nbuckets, offsets, sorted);
+    if (have_offsets)
+      fine_scatter_kernel<ORDER, REFCIC, true><<<ngroups, 512, smem, s>>>(tmp, gbase, g, gshift, ngroups, nbuckets, offsets, sorted);
+    else
+      fine_scatter_kernel<ORDER, REFCIC, false><<<ngroups, 512, smem, s>>>(tmp, gbase, g, gshift, ngroups, nbuckets, offsets, sorted);
   }
   JPS_CHECK_LAUNCH();
   return JPS_OK;
@@ -1034,17 +1103,17 @@ int paint_sorted(const PaintParams& p, int order, int compat, void* ws, size_t w
   g.nt = (p.n + TILE - 1) / TILE;
   g.ntx = (p.nx + TILE - 1) / TILE;
   g.ntiles = g.ntx * g.nt * g.nt;
-  // Bucketing flavour.  Measured on C2 (N=512, 1e8 particles): single-level 0.60 + 2.36 ms, two-level
-  // 0.38 + 1.36 + 1.32 ms -- a tie, because the two-level version reads the records twice in its fine
-  // pass.  The single-level scatter relies on L2 keeping one write frontier (128 B) per tile, so it is
-  // the default while those fit comfortably (<= 600 K tiles ~ 77 MB); beyond, the two-level partition
-  // (<= 2^gshift frontiers per resident group) takes over.  JPS_BUCKET=atomic|two forces one.
+  // Bucketing flavour.  Measured on C2 (N=512, 1e8 particles): single-level 0.60 + 2.36 = 2.96 ms;
+  // two-level 0.60 (tile histogram) + 1.10 (coarse) + 0.78 (fine, one read) = 2.51 ms, or
+  // 0.38 + 1.10 + 1.32 = 2.80 ms when the tile histogram does not fit shared memory and the fine pass
+  // reads its records twice.  The two-level partition is the default whenever the tile count fits
+  // its group table; JPS_BUCKET=atomic|two forces one (A/B runs, tests).
   static const int forced = [] {
     const char* e = getenv("JPS_BUCKET");
     return !e ? 0 : !strcmp(e, "atomic") ? 1 : !strcmp(e, "two") ? 2 : 0;
   }();
   const bool fits_two = g.ntiles + 1 <= kMaxGroups * 2048;
-  g.two_level = (forced == 2 && fits_two) || (forced == 0 && g.ntiles > 600000 && fits_two) ? 1 : 0;
+  g.two_level = (forced != 1 && fits_two) ? 1 : 0;
   g.rep = g.two_level ? 1 : replicas_for(g.ntiles);
   char* w = (char*)ws;
   if (order == 2 && compat == JPS_COMPAT_REFERENCE) return run_sorted<2, true>(p, g, w, ws_bytes, s);
