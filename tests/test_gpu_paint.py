@@ -174,3 +174,26 @@ def test_two_level_partition_in_subprocess():
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "helpers", "two_level_check.py")],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "two-level ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("order", [2, 3, 4])
+def test_garbage_positions_do_not_crash_or_corrupt(jps, order):
+    """NaN / inf / absurd coordinates must not fault or write out of bounds (nothing is validated, as
+    in the reference); in the bucketed painter a non-finite contribution rounds to zero, so the mesh
+    equals the mesh of the well-formed particles."""
+    n, box, npart = 128, 1000.0, 300_000
+    p = clustered_particles(77, npart, box)
+    bad = np.array([[np.nan, 1.0, 2.0], [np.inf, 5.0, 5.0], [-np.inf, 5.0, 5.0], [1e30, -1e30, 3.0],
+                    [3.0, np.nan, np.nan], [-1e9, 2e9, 7.0]], dtype=F32)
+    q = np.concatenate([p, bad])
+    zero = np.zeros((n, n, n), F32)
+    good = jps.paint(zero, p[:, 0], p[:, 1], p[:, 2], None, 0., 0., 0., box, n, True, order=order, compat="fixed", method="sorted")
+    got = jps.paint(zero, q[:, 0], q[:, 1], q[:, 2], None, 0., 0., 0., box, n, True, order=order, compat="fixed", method="sorted")
+    assert np.isfinite(got).all()
+    # the finite-but-absurd ones wrap periodically and land somewhere; NaN/inf ones vanish
+    assert abs(float(got.sum(dtype=np.float64)) - float(good.sum(dtype=np.float64))) <= len(bad) + 1e-3
+    jps.paint(zero, q[:, 0], q[:, 1], q[:, 2], None, 0., 0., 0., box, n, True, order=order, compat="fixed", method="atomic")
+    import torch
+    torch.cuda.synchronize()          # no sticky CUDA error
+    jps.cic_mas_vec(zero, q[:, 0], q[:, 1], q[:, 2], np.ones(len(q), F32), len(q), 0., 0., 0., box, n, True, method="sorted")
+    torch.cuda.synchronize()
