@@ -394,7 +394,7 @@ def run_slab_arm(a, wl):
     z = torch.rand(nloc, generator=g, device=dev) * box
     for t in (y, z):
         t[t >= box] = 0.0
-    pipe = SlabPipeline(n, box, k_edges_for(box, n), order=order, compat="fixed", method=a.method)
+    pipe = SlabPipeline(n, box, k_edges_for(box, n), order=order, compat="fixed", method=a.method, transport=a.transport)
 
     def sync():
         if world > 1:
@@ -437,7 +437,7 @@ def run_slab_arm(a, wl):
     if world > 1:
         timed("halo_exchange", lambda: halo_exchange_add(pipe.mesh, pipe.nxl))
     timed("fft_yz_pack", pipe.stage_fft_yz_pack)
-    if world > 1:
+    if world > 1 and pipe.transport == "nccl":
         timed("all_to_all", lambda: transpose_all_to_all(pipe.buf_b, pipe.buf_a))
     timed("fft_x", pipe.stage_fft_x)
     timed("bin_partial", lambda: pipe.stage_partial(True))
@@ -461,7 +461,11 @@ def run_slab_arm(a, wl):
                        "parallelism": f"{world} x-slabs, halo ring exchange + all-to-all + allreduce per step"},
             "clocks": clocks, "gpu_launches": int(launches), "stages_ms_max_over_ranks": stages,
             "kernels_ms_rank0": {k: round(ms_ / max(c, 1), 4) for k, (c, ms_) in prof.items()},
-            "all_to_all": {"bytes_per_rank": a2a, "achieved_gbs_per_rank": (a2a / stages["all_to_all"] / 1e6) if world > 1 else None,
+            "transport": pipe.transport,
+            "all_to_all": {"bytes_per_rank": a2a,
+                           "achieved_gbs_per_rank": (a2a / stages["all_to_all"] / 1e6) if "all_to_all" in stages else None,
+                           "note": "p2p transport: the transfer is inside fft_yz_pack (one fused pack + peer-store kernel)"
+                                   if pipe.transport == "p2p" else "NCCL all_to_all_single",
                            "nvlink_peer_copy_ref_gbs": 770.0},
             "roofline": {"kernel": "paint (bucket + tile deposit)", "bound": "hbm", "achieved": paint_bytes / stages["paint"] / 1e6,
                          "peak": peak, "unit": "GB/s", "frac": paint_bytes / stages["paint"] / 1e6 / peak, "traffic": None,
@@ -496,6 +500,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
                     help="c2: one realisation per GPU (default, weak scaling); c4: one slab-sharded mesh (strong scaling)")
     ap.add_argument("--order", type=int, default=None)
+    ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="c4: how the slab transpose crosses GPUs (fused peer-store kernel or NCCL all-to-all)")
     a = ap.parse_args()
     wl = dict(C4 if a.workload == "c4" else C2)
     if a.order:

@@ -226,6 +226,12 @@ JPS_API int jps_slab_plan_create(int n_mesh, int nranks, int rank, void* workspa
 JPS_API int jps_slab_plan_destroy(jps_slab_plan_t* plan);
 JPS_API int jps_slab_fft_yz(jps_slab_plan_t* plan, const float* slab, void* yz, void* stream);
 JPS_API int jps_slab_pack(jps_slab_plan_t* plan, const void* yz, void* packed, void* stream);
+/* Fused pack + all-to-all through NVLink peer memory: writes block q of `yz` straight into
+ * peer_recv[q] (HOST array of nranks DEVICE pointers to every rank's `dk` buffer, peer-mapped with
+ * CUDA IPC by the caller; peer_recv[rank] is the local buffer), at this rank's slot.  Replaces
+ * jps_slab_pack + the NCCL all-to-all.  The caller orders it against the peers' use of `dk`
+ * (stream-ordered collectives before and after; see jax_powspec_b200/slab.py). */
+JPS_API int jps_slab_pack_p2p(jps_slab_plan_t* plan, const void* yz, void* const* peer_recv, void* stream);
 JPS_API int jps_slab_fft_x(jps_slab_plan_t* plan, void* dk, void* stream);
 /* This rank's partial sums of |delta_k|^2 L_l per user bin (sums[nb*3], float64, overwritten) and the
  * GLOBAL exact mode counts (counts[nb], identical on every rank; may be NULL).  dc: device pointer to

@@ -67,6 +67,7 @@ SIGNATURES = {
     "jps_slab_plan_destroy": (_i, [_vp]),
     "jps_slab_fft_yz": (_i, [_vp, _vp, _vp, _vp]),
     "jps_slab_pack": (_i, [_vp, _vp, _vp, _vp]),
+    "jps_slab_pack_p2p": (_i, [_vp, _vp, C.POINTER(_vp), _vp]),
     "jps_slab_fft_x": (_i, [_vp, _vp, _vp]),
     "jps_slab_powspec_partial": (_i, [_vp, _vp, _vp, _i, _f, _fp, _i, _i, _vp, _vp, _vp]),
     "jps_slab_powspec_finalize": (_i, [_vp, _f, _fp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp]),

@@ -16,8 +16,12 @@
 #include <algorithm>
 #include <cmath>
 
+constexpr int kMaxRanks = 64;
+
 struct jps_slab_plan {
   int n = 0, nz = 0, nranks = 1, rank = 0, nxl = 0, nyl = 0;
+  void** peer_dev = nullptr;        // device copy of the peers' receive-buffer pointers (pack_p2p)
+  void* peer_host[kMaxRanks] = {};  // last pointers uploaded
   cufftHandle fft_yz = 0, fft_x = 0;
   bool yz_ok = false, x_ok = false;
   void* work = nullptr;
@@ -156,6 +160,33 @@ __global__ void __launch_bounds__(256) pk_bin_ysharded_kernel(SlabPkParams P) {
   }
 }
 
+// Fused pack + all-to-all over NVLink peer memory: block q of this rank's yz-transformed planes is
+// written DIRECTLY into rank q's receive buffer (peer pointers obtained through CUDA IPC on the host
+// side), at the slot of this rank -- no packed send buffer, no NCCL copy kernels.  One launch moves
+// (P-1)/P of the shard over NVLink and 1/P locally; CTAs interleave destinations so all links are
+// busy at once.
+//   dst_q[(rank*nxl + xl)*nyl*nz + e] = yz[xl*n*nz + q*nyl*nz + e],  e in [0, nyl*nz)
+__global__ void __launch_bounds__(256) slab_pack_p2p_kernel(const float2* __restrict__ yz,
+                                                            void* const* __restrict__ peers, int n,
+                                                            int nz, int nxl, int nyl, int nranks, int rank) {
+  const long long run = (long long)nyl * nz;                 // contiguous complex elements per (xl, q)
+  const long long nrun = (long long)nxl * nranks;
+  const bool vec = (run % 2 == 0);                           // 16-byte moves when every run is 16-byte aligned
+  for (long long r = blockIdx.x; r < nrun; r += gridDim.x) {
+    const int q = (int)(r % nranks);                         // consecutive CTAs -> different peers
+    const int xl = (int)(r / nranks);
+    const float2* src = yz + (size_t)xl * n * nz + (size_t)q * run;
+    float2* dst = reinterpret_cast<float2*>(peers[q]) + ((size_t)rank * nxl + xl) * run;
+    if (vec) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* d4 = reinterpret_cast<float4*>(dst);
+      for (long long e = threadIdx.x; e < run / 2; e += blockDim.x) d4[e] = s4[e];
+    } else {
+      for (long long e = threadIdx.x; e < run; e += blockDim.x) dst[e] = src[e];
+    }
+  }
+}
+
 // compact accumulators -> user-bin arrays
 __global__ void slab_expand_kernel(int nb, const int32_t* __restrict__ bin_to_compact,
                                    const double* __restrict__ acc,
@@ -206,7 +237,7 @@ extern "C" int jps_slab_plan_workspace_bytes(int n_mesh, int nranks, size_t* byt
   if (rc) return rc;
   const size_t tb = tables_bytes(n_mesh);
   JPS_REQUIRE(tb > 0, "jps_slab_plan_workspace_bytes: table sizing failed");
-  *bytes = align_up(std::max(w1, w2), 256) + align_up(tb, 256) + 512;
+  *bytes = align_up(std::max(w1, w2), 256) + align_up(tb, 256) + 1024 + 512;
   return JPS_OK;
 }
 
@@ -237,14 +268,15 @@ extern "C" int jps_slab_plan_create(int n_mesh, int nranks, int rank, void* work
   rc = make_fft_x(n_mesh, p->nyl, &p->fft_x, &w2);
   if (rc) { jps_slab_plan_destroy(p); return rc; }
   p->x_ok = true;
-  const size_t wb = align_up(std::max(w1, w2), 256);
+  const size_t wb = align_up(std::max(w1, w2), 256) + 1024;       // + the peer pointer table
   const size_t tb = tables_bytes(n_mesh);
   if (workspace_bytes < wb + align_up(tb, 256)) {
     set_error("jps_slab_plan_create: workspace has %zu bytes, %zu needed", workspace_bytes, wb + align_up(tb, 256));
     jps_slab_plan_destroy(p);
     return JPS_ERR_WORKSPACE;
   }
-  p->work = workspace; p->work_bytes = wb;
+  p->work = workspace; p->work_bytes = wb - 1024;
+  p->peer_dev = (void**)((char*)workspace + wb - 1024);
   if (cufftSetWorkArea(p->fft_yz, p->work) != CUFFT_SUCCESS || cufftSetWorkArea(p->fft_x, p->work) != CUFFT_SUCCESS) {
     set_error("jps_slab_plan_create: cufftSetWorkArea failed");
     jps_slab_plan_destroy(p);
@@ -277,6 +309,28 @@ extern "C" int jps_slab_pack(jps_slab_plan_t* p, const void* in, void* out, void
                                      (const char*)in + (size_t)q * row, spitch, row, (size_t)p->nxl,
                                      cudaMemcpyDeviceToDevice, s));
   }
+  return JPS_OK;
+}
+
+extern "C" int jps_slab_pack_p2p(jps_slab_plan_t* p, const void* yz, void* const* peer_recv, void* stream) {
+  JPS_REQUIRE(p && yz && peer_recv, "jps_slab_pack_p2p: NULL argument");
+  JPS_REQUIRE(p->nranks <= kMaxRanks, "jps_slab_pack_p2p: too many ranks");
+  cudaStream_t s = (cudaStream_t)stream;
+  bool changed = false;
+  for (int q = 0; q < p->nranks; ++q) {
+    JPS_REQUIRE(peer_recv[q] != nullptr && ((uintptr_t)peer_recv[q] & 15) == 0, "jps_slab_pack_p2p: peer pointer %d is NULL or misaligned", q);
+    if (p->peer_host[q] != peer_recv[q]) { p->peer_host[q] = peer_recv[q]; changed = true; }
+  }
+  if (changed)
+    JPS_CHECK_CUDA(cudaMemcpyAsync(p->peer_dev, p->peer_host, (size_t)p->nranks * sizeof(void*), cudaMemcpyHostToDevice, s));
+  JPS_REQUIRE(((uintptr_t)yz & 15) == 0, "jps_slab_pack_p2p: yz must be 16-byte aligned");
+  {
+    ScopedLaunch L(K_MISC, s);
+    const long long nrun = (long long)p->nxl * p->nranks;
+    slab_pack_p2p_kernel<<<(int)std::min<long long>(nrun, (long long)kNumSMs * 8), 256, 0, s>>>(
+        (const float2*)yz, p->peer_dev, p->n, p->nz, p->nxl, p->nyl, p->nranks, p->rank);
+  }
+  JPS_CHECK_LAUNCH();
   return JPS_OK;
 }
 

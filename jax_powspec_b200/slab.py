@@ -113,7 +113,10 @@ class SlabPipeline:
     """Per-rank object: owns the slab mesh, the two complex transpose buffers and the slab plan."""
 
     def __init__(self, n_mesh, box_size, k_edges, *, order=2, compat="fixed", method="auto", wrap=True,
-                 shot_noise=0.0, rank=None, world=None, device=None):
+                 shot_noise=0.0, rank=None, world=None, device=None, transport="auto"):
+        """transport: how the transpose crosses GPUs -- "p2p": one fused pack + peer-store kernel
+        over NVLink peer memory (receive buffers mapped into every rank with CUDA IPC); "nccl":
+        pack kernel + ``all_to_all_single``; "auto": p2p when the mapping succeeds, else nccl."""
         r, w = _world()
         self.rank = r if rank is None else rank
         self.world = w if world is None else world
@@ -155,6 +158,45 @@ class SlabPipeline:
         self.pk = torch.empty((self.nb, 3), dtype=torch.float32, device=d)
         self.nm = torch.empty(self.nb, dtype=torch.float32, device=d)
         self.pws, self.pws_bytes = None, 0
+        self.transport = "nccl"
+        self.peer_views, self.peer_ptrs = None, None
+        if not self.single and transport in ("auto", "p2p") and rank is None and dist.is_initialized():
+            ok = self._map_peer_buffers()
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=d)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)              # every rank must succeed
+            if int(flag.item()) == 1:
+                self.transport = "p2p"
+            elif transport == "p2p":
+                raise _lib.JpsError("SlabPipeline: transport='p2p' requested but peer mapping failed")
+        self._sync_flag = torch.zeros(1, dtype=torch.int32, device=d)
+
+    def _map_peer_buffers(self) -> bool:
+        """Map every rank's receive buffer (buf_a) into this process through CUDA IPC and enable peer
+        access; fills self.peer_ptrs (ctypes array of device pointers, indexed by rank)."""
+        try:
+            handle = self.buf_a.untyped_storage()._share_cuda_()
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (handle, self.buf_a.storage_offset(), tuple(self.buf_a.shape)))
+            views = []
+            for q, (h, off, shape) in enumerate(handles):
+                if q == self.rank:
+                    views.append(self.buf_a)
+                    continue
+                st = torch.UntypedStorage._new_shared_cuda(*h)
+                t = torch.empty(0, dtype=torch.complex64, device=st.device).set_(st, off, shape)
+                probe = torch.empty(1, dtype=torch.complex64, device=self.device)
+                probe.copy_(t.view(-1)[:1])                         # makes torch enable peer access both ways
+                views.append(t)
+            torch.cuda.synchronize(self.device)
+            if not all(torch.cuda.can_device_access_peer(self.device.index, v.device.index)
+                       for q, v in enumerate(views) if q != self.rank):
+                return False
+            self.peer_views = views
+            self.peer_ptrs = (C.c_void_p * self.world)(*[v.data_ptr() for v in views])
+            return True
+        except Exception as e:                                       # private torch API: fall back to NCCL
+            self._p2p_error = repr(e)
+            return False
 
     def close(self):
         if getattr(self, "handle", None):
@@ -187,9 +229,20 @@ class SlabPipeline:
         return self.mesh[self.gl: self.gl + self.nxl]
 
     def stage_fft_yz_pack(self):
+        if self.transport == "p2p":
+            return self.stage_fft_yz_p2p()
         check(lib.jps_slab_fft_yz(self.handle, ptr(self.owned()), ptr(self.buf_a), stream_ptr()), "jps_slab_fft_yz")
         if not self.single:
             check(lib.jps_slab_pack(self.handle, ptr(self.buf_a), ptr(self.buf_b), stream_ptr()), "jps_slab_pack")
+
+    def stage_fft_yz_p2p(self):
+        """2-D FFT into the local buffer, then ONE kernel that writes every destination's block straight
+        into that rank's receive buffer over NVLink.  Ordering: the peers finished reading their
+        receive buffers before the previous step's allreduce completed (stream order), and the tiny
+        allreduce below makes every rank's stores visible before anyone starts the 1-D FFT."""
+        check(lib.jps_slab_fft_yz(self.handle, ptr(self.owned()), ptr(self.buf_b), stream_ptr()), "jps_slab_fft_yz")
+        check(lib.jps_slab_pack_p2p(self.handle, ptr(self.buf_b), self.peer_ptrs, stream_ptr()), "jps_slab_pack_p2p")
+        dist.all_reduce(self._sync_flag)
 
     def stage_fft_x(self):
         check(lib.jps_slab_fft_x(self.handle, ptr(self.buf_a), stream_ptr()), "jps_slab_fft_x")
@@ -216,7 +269,7 @@ class SlabPipeline:
         if not self.single:
             halo_exchange_add(self.mesh, self.nxl)
         self.stage_fft_yz_pack()
-        if not self.single:
+        if not self.single and self.transport == "nccl":
             transpose_all_to_all(self.buf_b, self.buf_a)
         self.stage_fft_x()
         if self.rank == 0:
