@@ -231,6 +231,12 @@ JPS_API int jps_slab_pack(jps_slab_plan_t* plan, const void* yz, void* packed, v
  * CUDA IPC by the caller; peer_recv[rank] is the local buffer), at this rank's slot.  Replaces
  * jps_slab_pack + the NCCL all-to-all.  The caller orders it against the peers' use of `dk`
  * (stream-ordered collectives before and after; see jax_powspec_b200/slab.py). */
+/* CUDA IPC: map a peer process's allocation into this process on the CURRENT device (handle = the
+ * 64-byte cudaIpcMemHandle_t of the allocation's base); returns the base pointer. */
+JPS_API int jps_ipc_open(const void* handle, void** out_ptr);
+JPS_API int jps_ipc_close(void* ptr);
+/* Let kernels on the current device dereference memory of `peer_device` (NVLink peer access). */
+JPS_API int jps_enable_peer_access(int peer_device);
 JPS_API int jps_slab_pack_p2p(jps_slab_plan_t* plan, const void* yz, void* const* peer_recv, void* stream);
 JPS_API int jps_slab_fft_x(jps_slab_plan_t* plan, void* dk, void* stream);
 /* This rank's partial sums of |delta_k|^2 L_l per user bin (sums[nb*3], float64, overwritten) and the

@@ -67,6 +67,9 @@ SIGNATURES = {
     "jps_slab_plan_destroy": (_i, [_vp]),
     "jps_slab_fft_yz": (_i, [_vp, _vp, _vp, _vp]),
     "jps_slab_pack": (_i, [_vp, _vp, _vp, _vp]),
+    "jps_ipc_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
+    "jps_ipc_close": (_i, [_vp]),
+    "jps_enable_peer_access": (_i, [_i]),
     "jps_slab_pack_p2p": (_i, [_vp, _vp, C.POINTER(_vp), _vp]),
     "jps_slab_fft_x": (_i, [_vp, _vp, _vp]),
     "jps_slab_powspec_partial": (_i, [_vp, _vp, _vp, _i, _f, _fp, _i, _i, _vp, _vp, _vp]),

@@ -312,6 +312,39 @@ extern "C" int jps_slab_pack(jps_slab_plan_t* p, const void* in, void* out, void
   return JPS_OK;
 }
 
+// Open a CUDA IPC memory handle exported by another process ON THE CURRENT DEVICE, so that kernels
+// of this device can dereference the peer's memory over NVLink (peer access is enabled lazily by
+// the driver).  `handle` is the 64-byte cudaIpcMemHandle_t.
+extern "C" int jps_ipc_open(const void* handle, void** out_ptr) {
+  JPS_REQUIRE(handle && out_ptr, "jps_ipc_open: NULL argument");
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(&h, handle, sizeof(h));
+  JPS_CHECK_CUDA(cudaIpcOpenMemHandle(out_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return JPS_OK;
+}
+
+extern "C" int jps_ipc_close(void* ptr) {
+  if (ptr) JPS_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
+  return JPS_OK;
+}
+
+extern "C" int jps_enable_peer_access(int peer_device) {
+  int dev = 0;
+  JPS_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev == peer_device) return JPS_OK;
+  int can = 0;
+  JPS_CHECK_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+  if (!can) {
+    set_error("jps_enable_peer_access: device %d cannot access device %d", dev, peer_device);
+    return JPS_ERR_UNSUPPORTED;
+  }
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return JPS_OK; }
+  JPS_CHECK_CUDA(e);
+  return JPS_OK;
+}
+
 extern "C" int jps_slab_pack_p2p(jps_slab_plan_t* p, const void* yz, void* const* peer_recv, void* stream) {
   JPS_REQUIRE(p && yz && peer_recv, "jps_slab_pack_p2p: NULL argument");
   JPS_REQUIRE(p->nranks <= kMaxRanks, "jps_slab_pack_p2p: too many ranks");

@@ -159,7 +159,7 @@ class SlabPipeline:
         self.nm = torch.empty(self.nb, dtype=torch.float32, device=d)
         self.pws, self.pws_bytes = None, 0
         self.transport = "nccl"
-        self.peer_views, self.peer_ptrs = None, None
+        self.peer_ptrs, self._ipc_bases = None, []
         if not self.single and transport in ("auto", "p2p") and rank is None and dist.is_initialized():
             ok = self._map_peer_buffers()
             flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=d)
@@ -171,34 +171,43 @@ class SlabPipeline:
         self._sync_flag = torch.zeros(1, dtype=torch.int32, device=d)
 
     def _map_peer_buffers(self) -> bool:
-        """Map every rank's receive buffer (buf_a) into this process through CUDA IPC and enable peer
-        access; fills self.peer_ptrs (ctypes array of device pointers, indexed by rank)."""
+        """Map every rank's receive buffer (buf_a) into this process through CUDA IPC, opened on THIS
+        rank's device so that its kernels can store into the peers over NVLink; fills self.peer_ptrs
+        (ctypes array of device pointers, indexed by rank)."""
         try:
-            handle = self.buf_a.untyped_storage()._share_cuda_()
+            # (device, 64-byte cudaIpcMemHandle_t of the allocator block, size, offset of the storage, ...)
+            shared = self.buf_a.untyped_storage()._share_cuda_()
+            byte_off = int(shared[3]) + self.buf_a.storage_offset() * self.buf_a.element_size()
+            raw = bytes(shared[1])
+            if len(raw) > 64:                        # newer torch: [version byte][type byte]handle; b'c' = cudaMalloc block
+                kind = raw[len(raw) - 65: len(raw) - 64]
+                if kind != b"c":
+                    raise RuntimeError(f"receive buffer is not a plain cudaMalloc block (type {kind!r}): no cudaIpcMemHandle")
+                raw = raw[-64:]
+            if len(raw) != 64:
+                raise RuntimeError(f"unexpected IPC handle size {len(raw)}")
             handles = [None] * self.world
-            dist.all_gather_object(handles, (handle, self.buf_a.storage_offset(), tuple(self.buf_a.shape)))
-            views = []
-            for q, (h, off, shape) in enumerate(handles):
-                if q == self.rank:
-                    views.append(self.buf_a)
-                    continue
-                st = torch.UntypedStorage._new_shared_cuda(*h)
-                t = torch.empty(0, dtype=torch.complex64, device=st.device).set_(st, off, shape)
-                probe = torch.empty(1, dtype=torch.complex64, device=self.device)
-                probe.copy_(t.view(-1)[:1])                         # makes torch enable peer access both ways
-                views.append(t)
-            torch.cuda.synchronize(self.device)
-            if not all(torch.cuda.can_device_access_peer(self.device.index, v.device.index)
-                       for q, v in enumerate(views) if q != self.rank):
-                return False
-            self.peer_views = views
-            self.peer_ptrs = (C.c_void_p * self.world)(*[v.data_ptr() for v in views])
+            dist.all_gather_object(handles, (raw, byte_off))
+            ptrs, self._ipc_bases = [], []
+            with torch.cuda.device(self.device):
+                for q, (h, off) in enumerate(handles):
+                    if q == self.rank:
+                        ptrs.append(self.buf_a.data_ptr())
+                        continue
+                    base = C.c_void_p(0)
+                    check(lib.jps_ipc_open(h, C.byref(base)), "jps_ipc_open")
+                    self._ipc_bases.append(base)
+                    ptrs.append(base.value + off)
+            self.peer_ptrs = (C.c_void_p * self.world)(*ptrs)
             return True
-        except Exception as e:                                       # private torch API: fall back to NCCL
+        except Exception as e:                                       # private torch API / no peer access: use NCCL
             self._p2p_error = repr(e)
             return False
 
     def close(self):
+        for base in getattr(self, "_ipc_bases", []):
+            lib.jps_ipc_close(base)
+        self._ipc_bases = []
         if getattr(self, "handle", None):
             lib.jps_slab_plan_destroy(self.handle)
             self.handle = None
