@@ -197,3 +197,33 @@ def test_garbage_positions_do_not_crash_or_corrupt(jps, order):
     torch.cuda.synchronize()          # no sticky CUDA error
     jps.cic_mas_vec(zero, q[:, 0], q[:, 1], q[:, 2], np.ones(len(q), F32), len(q), 0., 0., 0., box, n, True, method="sorted")
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("order,compat", [(2, "reference"), (3, "fixed"), (4, "fixed")])
+@pytest.mark.parametrize("wkind", ["mixed_sign", "wide_range", "tiny", "huge", "zeros"])
+def test_fixed_point_deposit_weight_ranges(jps, order, compat, wkind):
+    """The bucketed painter accumulates tiles in 64-bit fixed point scaled by 2^e >= max|w|: negative
+    weights (borrow path), 6 decades of dynamic range, very small / very large scales and all-zero
+    weights must all agree with the f64 oracle to float32 accuracy RELATIVE TO max|w|."""
+    n, box, npart = 64, 1000.0, 200_000
+    p = clustered_particles(9, npart, box)
+    rng = np.random.default_rng(17)
+    w = {"mixed_sign": rng.uniform(-1, 1, npart),
+         "wide_range": 10.0 ** rng.uniform(-3, 3, npart) * rng.choice([-1.0, 1.0], npart),
+         "tiny": rng.uniform(0.5, 1, npart) * 1e-20,
+         "huge": rng.uniform(0.5, 1, npart) * 1e20,
+         "zeros": np.zeros(npart)}[wkind].astype(F32)
+    want = om.paint(np.zeros((n, n, n)), p[:, 0], p[:, 1], p[:, 2], w, 0., 0., 0., box, n, True,
+                    order=order, compat=compat, precision="f64")
+    got = jps.paint(np.zeros((n, n, n), F32), p[:, 0], p[:, 1], p[:, 2], w, 0., 0., 0., box, n, True,
+                    order=order, compat=compat, method="sorted").astype(np.float64)
+    wmax = float(np.abs(w).max())
+    if wmax == 0.0:
+        assert np.all(got == 0.0)
+        return
+    # absolute accuracy: float32 rounding of every product (6e-8 * |contribution|) plus 2^-31 wmax per update
+    per_cell = om.paint(np.zeros((n, n, n)), p[:, 0], p[:, 1], p[:, 2], np.abs(w), 0., 0., 0., box, n, True,
+                        order=order, compat=compat, precision="f64")          # sum of |contributions|
+    tol = 3e-7 * per_cell + 1e-7 * wmax
+    bad = np.abs(got - want) > tol
+    assert not bad.any(), f"{bad.sum()} cells off, worst {np.max(np.abs(got - want) / (tol + 1e-300)):.2f}x tol"
