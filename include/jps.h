@@ -250,6 +250,21 @@ JPS_API int jps_slab_powspec_finalize(jps_slab_plan_t* plan, float box_size, con
                               const double* sums, const int64_t* counts, float shot_noise,
                               float* k3d, float* pk3d, float* nmodes, void* stream);
 
+/* ------------------------------------------------------------------ gradients -------- */
+/* Reverse-mode derivatives (the reference is differentiated with jax.value_and_grad, e.g.
+ * tests/lognormal.py:99-107).  grad_pk: device float32 [nb*3] cotangent of Pk3D (NaN-free; empty bins
+ * are ignored).  grad_mesh: device float32 [n,n,n] cotangent of the mesh passed to jps_powspec with
+ * the same arguments. */
+JPS_API int jps_powspec_grad(jps_plan_t* plan, const float* mesh, int normalise, float box_size,
+                     const float* k_edges, int nb, int mas_order, const float* grad_pk,
+                     float* grad_mesh, void* stream);
+/* Cotangents of the particles of jps_paint: gx, gy, gz, gw device float32 [n_part] (any may be NULL).
+ * Cell choice (int / floor of the grid coordinate) has zero derivative, as under JAX autodiff. */
+JPS_API int jps_paint_grad(int n_mesh, const float* x, const float* y, const float* z, const float* w,
+                   int64_t stride, int64_t n_part, float xmin, float ymin, float zmin, float box_size,
+                   int order, int wrap, int compat, int variant, const float* grad_mesh,
+                   float* gx, float* gy, float* gz, float* gw, void* stream);
+
 /* ------------------------------------------------------------------ fused ------------ */
 /* paint (into the plan-owned mesh, zeroed first) -> R2C FFT -> multipoles; the call the
  * benchmark times.  Arguments as jps_paint + jps_powspec(normalise=1, mas_order=order). */

@@ -74,6 +74,9 @@ SIGNATURES = {
     "jps_slab_fft_x": (_i, [_vp, _vp, _vp]),
     "jps_slab_powspec_partial": (_i, [_vp, _vp, _vp, _i, _f, _fp, _i, _i, _vp, _vp, _vp]),
     "jps_slab_powspec_finalize": (_i, [_vp, _f, _fp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
+    "jps_powspec_grad": (_i, [_vp, _vp, _i, _f, _fp, _i, _i, _vp, _vp, _vp]),
+    "jps_paint_grad": (_i, [_i, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _f, _f, _i, _i, _i, _i, _vp,
+                            _vp, _vp, _vp, _vp, _vp]),
     "jps_paint_powspec": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _f, _f, _i, _i, _i, _i,
                                _fp, _i, _f, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

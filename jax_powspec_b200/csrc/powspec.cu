@@ -399,6 +399,10 @@ static int bin_from_dk(jps_plan* plan, const BinTable& T, int normalise, int mas
   return JPS_OK;
 }
 
+int bin_from_dk_public(jps_plan* plan, const BinTable& T, int normalise, int mas_order, cudaStream_t s) {
+  return bin_from_dk(plan, T, normalise, mas_order, s);
+}
+
 double ref_volume(float box_size, int n) {
   const float t = box_size / (float)(n * n);    // (box_size/dims**2)**3 in float32, :50
   return (double)(t * t * t);
