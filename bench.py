@@ -201,6 +201,23 @@ ALGO_BYTES = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
+# this same command (profiles/r1_ncu_full_summary.md); only meaningful for the default C2 configuration.
+NCU_KERNEL = {"paint_tile": "paint_tile_fx_kernel", "bucket_scatter": "coarse_scatter_kernel",
+              "bucket_fine": "fine_scatter_kernel", "bucket_count": "bucket_count_smem_kernel",
+              "pk_fold_bin": "pk_fold_bin_kernel"}
+
+
+def ncu_traffic(kernel, wl):
+    if (wl["n_part"], wl["n_mesh"], wl["order"]) != (C2["n_part"], C2["n_mesh"], C2["order"]):
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_dram_traffic_c2.json")) as f:
+            return json.load(f).get(NCU_KERNEL.get(kernel, ""))
+    except Exception:
+        return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -323,6 +340,7 @@ def run_gpu_arm(a, wl):
         if name in ALGO_BYTES:
             b = ALGO_BYTES[name](npart, n, 0)
             entry["algorithmic_bytes"] = b
+            entry["ncu_dram_bytes"] = ncu_traffic(name, wl)
             entry["achieved_gbs"] = b / per / 1e6
             entry["frac_of_peak"] = b / per / 1e6 / peak
         kernels[name] = entry
@@ -332,7 +350,9 @@ def run_gpu_arm(a, wl):
     if dom:
         d = ours[dom]
         roofline = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": d["frac_of_peak"], "traffic": None, "peak_source": peak_src,
+                    "frac": d["frac_of_peak"], "traffic": ncu_traffic(dom, wl),
+                    "traffic_source": "profiles/r1_ncu_full_summary.md (ncu --set full, same command)",
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": d["algorithmic_bytes"], "ms_per_launch": d["ms_per_launch"]}
 
     cpu = None
