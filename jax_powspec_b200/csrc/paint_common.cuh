@@ -36,19 +36,24 @@ __device__ __forceinline__ float grid_pos(float x, float xmin, float inv) {
 }
 
 // Python-style a mod n (result in [0, n)).  Integer division by a run-time n costs ~30
-// instructions and was the dominant instruction cost of the bucketing passes; particles inside
-// the box only ever need one conditional add / subtract.
-__device__ __forceinline__ int pymod(int a, int n) {
-  if ((unsigned)a < (unsigned)n) return a;
-  if (a < 0) {
-    a += n;
-    if (a >= 0) return a;
-  } else {
-    a -= n;
-    if (a < n) return a;
-  }
+// instructions and was the dominant instruction cost of the bucketing passes; particles within one
+// box length of the box only need a conditional add and a conditional subtract (branch-free
+// selects), and the division lives out of line so that the hot loops stay small.
+static __device__ __noinline__ int pymod_slow(int a, int n) {
   const int r = a % n;
   return r < 0 ? r + n : r;
+}
+
+__device__ __forceinline__ int wrap_once(int a, int n) {
+  a += (a < 0) ? n : 0;
+  a -= (a >= n) ? n : 0;
+  return a;                                        // in [0, n) iff the input was in [-n, 2n)
+}
+
+__device__ __forceinline__ int pymod(int a, int n) {
+  a = wrap_once(a, n);
+  if ((unsigned)a >= (unsigned)n) a = pymod_slow(a, n);
+  return a;
 }
 
 // Global (already wrapped / validated, or -1) x-plane -> local plane of a [nx][n][n] slab mesh

@@ -37,28 +37,100 @@ struct TileGeom {
 
 // Lowest stencil node of a particle along one axis, wrapped into [0, n); -1 if the particle
 // cannot be handled by the tile kernel (reference-compat CIC outside the box).
+template <int ORDER>
+__device__ __forceinline__ int anchor_base(float pos) {      // unwrapped lowest node of the B-spline stencil
+  if (ORDER == 2) return (int)floorf(pos);
+  if (ORDER == 3) return (int)floorf(pos + 0.5f) - 1;
+  return (int)floorf(pos) - 1;
+}
+
 template <int ORDER, bool REFCIC>
 __device__ __forceinline__ int anchor_axis(float pos, int n) {
   if (REFCIC) {
     const int i = (int)pos;              // truncation (Q3); in-box particles have 0 <= i < n
     return (pos >= 0.0f && i < n) ? i : -1;
   }
-  int base;
-  if (ORDER == 2) base = (int)floorf(pos);
-  else if (ORDER == 3) base = (int)floorf(pos + 0.5f) - 1;
-  else base = (int)floorf(pos) - 1;
-  return pymod(base, n);
+  return pymod(anchor_base<ORDER>(pos), n);
 }
 
 // bucket id of a particle; `block` selects the counter replica (count and scatter passes use
-// the same particle -> block mapping, so a particle sees the same replica in both)
+// the same particle -> block mapping, so a particle sees the same replica in both).
+// The three anchors are wrapped with branch-free selects and share ONE rarely taken branch to the
+// out-of-line division (particles more than a box length outside the box).
 template <int ORDER, bool REFCIC>
 __device__ __forceinline__ int tile_of(float px, float py, float pz, const TileGeom& g, unsigned block) {
-  const int ax = local_plane(anchor_axis<ORDER, REFCIC>(px, g.n), g.x0, g.nx, g.n);   // not held here -> dropped
-  const int ay = anchor_axis<ORDER, REFCIC>(py, g.n);
-  const int az = anchor_axis<ORDER, REFCIC>(pz, g.n);
+  int ax, ay, az;
+  if (REFCIC) {
+    ax = anchor_axis<ORDER, REFCIC>(px, g.n);
+    ay = anchor_axis<ORDER, REFCIC>(py, g.n);
+    az = anchor_axis<ORDER, REFCIC>(pz, g.n);
+  } else {
+    const int n = g.n;
+    ax = wrap_once(anchor_base<ORDER>(px), n);
+    ay = wrap_once(anchor_base<ORDER>(py), n);
+    az = wrap_once(anchor_base<ORDER>(pz), n);
+    if (((unsigned)ax >= (unsigned)n) | ((unsigned)ay >= (unsigned)n) | ((unsigned)az >= (unsigned)n)) {
+      ax = pymod_slow(ax, n);
+      ay = pymod_slow(ay, n);
+      az = pymod_slow(az, n);
+    }
+  }
+  if (g.nx != g.n || g.x0 != 0) ax = local_plane(ax, g.x0, g.nx, g.n);   // slab: not held here -> dropped
   if ((ax | ay | az) < 0) return g.ntiles * g.rep;
-  return (((ax / TILE) * g.nt + (ay / TILE)) * g.nt + (az / TILE)) * g.rep + (int)(block & (unsigned)(g.rep - 1));
+  const unsigned t = (((unsigned)ax / TILE) * g.nt + ((unsigned)ay / TILE)) * g.nt + ((unsigned)az / TILE);
+  return (int)(t * g.rep + (block & (unsigned)(g.rep - 1)));
+}
+
+// ---------------------------------------------------------------- catalogue access
+// The passes that read the caller's catalogue give every thread FOUR consecutive particles.  For the
+// usual (N, 3) float32 array (x, y, z interleaved, 16-byte aligned) those are 48 contiguous bytes =
+// three 16-byte loads instead of twelve 4-byte loads with 64-bit index arithmetic each; any other
+// layout (separate arrays, other strides) takes the scalar path.
+struct Quad {
+  float x[4], y[4], z[4];
+};
+
+__device__ __forceinline__ bool catalogue_is_aos(const PaintParams& p) {
+  return p.stride == 3 && p.y == p.x + 1 && p.z == p.x + 2 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0;
+}
+
+// i is a multiple of 4; cnt = number of valid particles in the quad (1..4)
+__device__ __forceinline__ void load_quad(const PaintParams& p, bool aos, int64_t i, int cnt, Quad& q) {
+  if (aos && cnt == 4) {
+    const float4* b = reinterpret_cast<const float4*>(p.x + 3 * i);
+    const float4 a = __ldg(b), m = __ldg(b + 1), c = __ldg(b + 2);
+    q.x[0] = a.x; q.y[0] = a.y; q.z[0] = a.z;
+    q.x[1] = a.w; q.y[1] = m.x; q.z[1] = m.y;
+    q.x[2] = m.z; q.y[2] = m.w; q.z[2] = c.x;
+    q.x[3] = c.y; q.y[3] = c.z; q.z[3] = c.w;
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t j = (i + (u < cnt ? u : 0)) * p.stride;
+      q.x[u] = p.x[j]; q.y[u] = p.y[j]; q.z[u] = p.z[j];
+    }
+  }
+}
+
+__device__ __forceinline__ void load_quad_weights(const PaintParams& p, int64_t i, int cnt, float (&w)[4]) {
+  if (!p.w) {
+    w[0] = w[1] = w[2] = w[3] = 1.0f;
+  } else if (cnt == 4 && (reinterpret_cast<uintptr_t>(p.w) & 15) == 0) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + i));
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) w[u] = p.w[i + (u < cnt ? u : 0)];
+  }
+}
+
+__device__ __forceinline__ float quad_wmax(const float (&w)[4], int cnt, float wmax) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float a = fabsf(w[u]);
+    if (u < cnt && a < 3.0e38f) wmax = fmaxf(wmax, a);     // ignores inf / NaN
+  }
+  return wmax;
 }
 
 // ---------------------------------------------------------------- K1a: histogram of tile ids
@@ -124,27 +196,25 @@ __global__ void __launch_bounds__(1024) bucket_count_smem_kernel(PaintParams p, 
   for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = 0u;
   __syncthreads();
   const int64_t T = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nquads = (p.n_part + 3) >> 2;
+  const bool aos = catalogue_is_aos(p);
   float wmax = p.w ? 0.0f : 1.0f;
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < p.n_part; i0 += BUCKET_UNROLL * T) {
-    int tile[BUCKET_UNROLL];
-#pragma unroll
-    for (int u = 0; u < BUCKET_UNROLL; ++u) {
-      const int64_t i = i0 + u * T;
-      tile[u] = -1;
-      if (i < p.n_part) {
-        const float px = grid_pos(p.x[i * p.stride], p.xmin, p.inv);
-        const float py = grid_pos(p.y[i * p.stride], p.ymin, p.inv);
-        const float pz = grid_pos(p.z[i * p.stride], p.zmin, p.inv);
-        tile[u] = tile_of<ORDER, REFCIC>(px, py, pz, g, 0u);
-        if (p.w) {
-          const float a = fabsf(p.w[i]);
-          if (a < 3.0e38f) wmax = fmaxf(wmax, a);
-        }
-      }
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += T) {
+    const int64_t i = q << 2;
+    const int cnt = (int)min((int64_t)4, p.n_part - i);
+    Quad c;
+    load_quad(p, aos, i, cnt, c);
+    if (p.w) {
+      float w[4];
+      load_quad_weights(p, i, cnt, w);
+      wmax = quad_wmax(w, cnt, wmax);
     }
 #pragma unroll
-    for (int u = 0; u < BUCKET_UNROLL; ++u)
-      if (tile[u] >= 0) atomicAdd(hist + tile[u], 1u);
+    for (int u = 0; u < 4; ++u) {
+      const int tile = tile_of<ORDER, REFCIC>(grid_pos(c.x[u], p.xmin, p.inv), grid_pos(c.y[u], p.ymin, p.inv),
+                                              grid_pos(c.z[u], p.zmin, p.inv), g, 0u);
+      if (u < cnt) atomicAdd(hist + tile, 1u);
+    }
   }
   __syncthreads();
   // every CTA adds its table to the same global counters: rotate the start so that at any moment
@@ -297,9 +367,9 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(PaintParams p, Tile
 //                        histogram over the group's tiles -> tile offsets -> second pass places every
 //                        record with a warp-aggregated SHARED cursor; writes go to <= 2^gshift
 //                        frontiers per resident group, which L2 merges into full lines.
-constexpr int COARSE_CHUNK = 4096;                 // 64 KB of staged records: two CTAs per SM overlap their phases
-constexpr int COARSE_THREADS = 1024;
-constexpr int COARSE_PT = COARSE_CHUNK / COARSE_THREADS;
+constexpr int COARSE_CHUNK = 4096;                 // 64 KB of staged records per CTA
+constexpr int COARSE_THREADS = 512;
+constexpr int COARSE_QPT = COARSE_CHUNK / (4 * COARSE_THREADS);   // quads (4 particles) per thread
 constexpr int kMaxGroups = 2048;
 
 // exclusive scan of a[0..n) in shared memory, in place, by all threads of the CTA (n <= 4 * blockDim);
@@ -351,27 +421,25 @@ __global__ void __launch_bounds__(256) coarse_count_kernel(PaintParams p, TileGe
   for (int i = threadIdx.x; i < ngroups; i += blockDim.x) csm[i] = 0u;
   __syncthreads();
   const int64_t T = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nquads = (p.n_part + 3) >> 2;
+  const bool aos = catalogue_is_aos(p);
   float wmax = p.w ? 0.0f : 1.0f;
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < p.n_part; i0 += BUCKET_UNROLL * T) {
-    int grp[BUCKET_UNROLL];
-#pragma unroll
-    for (int u = 0; u < BUCKET_UNROLL; ++u) {
-      const int64_t i = i0 + u * T;
-      grp[u] = -1;
-      if (i < p.n_part) {
-        const float px = grid_pos(p.x[i * p.stride], p.xmin, p.inv);
-        const float py = grid_pos(p.y[i * p.stride], p.ymin, p.inv);
-        const float pz = grid_pos(p.z[i * p.stride], p.zmin, p.inv);
-        grp[u] = tile_of<ORDER, REFCIC>(px, py, pz, g, 0u) >> gshift;
-        if (p.w) {
-          const float a = fabsf(p.w[i]);
-          if (a < 3.0e38f) wmax = fmaxf(wmax, a);
-        }
-      }
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += T) {
+    const int64_t i = q << 2;
+    const int cnt = (int)min((int64_t)4, p.n_part - i);
+    Quad c;
+    load_quad(p, aos, i, cnt, c);
+    if (p.w) {
+      float w[4];
+      load_quad_weights(p, i, cnt, w);
+      wmax = quad_wmax(w, cnt, wmax);
     }
 #pragma unroll
-    for (int u = 0; u < BUCKET_UNROLL; ++u)
-      if (grp[u] >= 0) atomicAdd(csm + grp[u], 1u);
+    for (int u = 0; u < 4; ++u) {
+      const int tile = tile_of<ORDER, REFCIC>(grid_pos(c.x[u], p.xmin, p.inv), grid_pos(c.y[u], p.ymin, p.inv),
+                                              grid_pos(c.z[u], p.zmin, p.inv), g, 0u);
+      if (u < cnt) atomicAdd(csm + (tile >> gshift), 1u);
+    }
   }
   __syncthreads();
   const int rot = (int)(((long long)blockIdx.x * ngroups) / gridDim.x);
@@ -415,7 +483,7 @@ __global__ void group_bases_from_offsets_kernel(const unsigned* __restrict__ off
 }
 
 template <int ORDER, bool REFCIC>
-__global__ void __launch_bounds__(COARSE_THREADS) coarse_scatter_kernel(PaintParams p, TileGeom g, int gshift,
+__global__ void __launch_bounds__(COARSE_THREADS, 2) coarse_scatter_kernel(PaintParams p, TileGeom g, int gshift,
                                                                         int ngroups,
                                                                         unsigned* __restrict__ gcursor,
                                                                         float4* __restrict__ tmp) {
@@ -426,24 +494,45 @@ __global__ void __launch_bounds__(COARSE_THREADS) coarse_scatter_kernel(PaintPar
   unsigned* gb = h + ngroups;                                                         // [ngroups] reserved global base
   unsigned* scratch = gb + ngroups;                                                   // [33]
   const int tid = threadIdx.x;
+  const bool aos = catalogue_is_aos(p);
   const int64_t nchunks = (p.n_part + COARSE_CHUNK - 1) / COARSE_CHUNK;
-  for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+  // Thread `tid` owns quads tid + k * COARSE_THREADS of the chunk (k < COARSE_QPT), held in registers
+  // from the prefetch (issued before the PREVIOUS chunk's write-out, so the HBM latency hides behind
+  // it) until they are staged.
+  Quad cq[COARSE_QPT];
+  float cw[COARSE_QPT][4];
+  auto fetch = [&](int64_t ch) {
+    const int64_t c0 = ch * COARSE_CHUNK;
+    const int m = (int)min((int64_t)COARSE_CHUNK, p.n_part - c0);
+#pragma unroll
+    for (int k = 0; k < COARSE_QPT; ++k) {
+      const int q4 = 4 * (tid + k * COARSE_THREADS);
+      const int cnt = min(4, m - q4);
+      if (cnt > 0) {
+        load_quad(p, aos, c0 + q4, cnt, cq[k]);
+        load_quad_weights(p, c0 + q4, cnt, cw[k]);
+      }
+    }
+  };
+  int64_t ch = blockIdx.x;
+  if (ch < nchunks) fetch(ch);
+  for (; ch < nchunks; ch += gridDim.x) {
     const int64_t c0 = ch * COARSE_CHUNK;
     const int m = (int)min((int64_t)COARSE_CHUNK, p.n_part - c0);
     for (int i = tid; i < ngroups; i += COARSE_THREADS) h[i] = 0u;
     __syncthreads();
-    unsigned key[COARSE_PT];                       // group | rank << 12
+    unsigned key[COARSE_QPT][4];                   // group | rank << 12
 #pragma unroll
-    for (int u = 0; u < COARSE_PT; ++u) {
-      const int j = u * COARSE_THREADS + tid;
-      key[u] = 0xffffffffu;
-      if (j < m) {
-        const int64_t i = c0 + j;
-        const float px = grid_pos(p.x[i * p.stride], p.xmin, p.inv);
-        const float py = grid_pos(p.y[i * p.stride], p.ymin, p.inv);
-        const float pz = grid_pos(p.z[i * p.stride], p.zmin, p.inv);
-        const unsigned grp = (unsigned)(tile_of<ORDER, REFCIC>(px, py, pz, g, 0u) >> gshift);
-        key[u] = grp | (atomicAdd(h + grp, 1u) << 12);
+    for (int k = 0; k < COARSE_QPT; ++k) {
+      const int cnt = m - 4 * (tid + k * COARSE_THREADS);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        cq[k].x[u] = grid_pos(cq[k].x[u], p.xmin, p.inv);
+        cq[k].y[u] = grid_pos(cq[k].y[u], p.ymin, p.inv);
+        cq[k].z[u] = grid_pos(cq[k].z[u], p.zmin, p.inv);
+        const unsigned grp = (unsigned)(tile_of<ORDER, REFCIC>(cq[k].x[u], cq[k].y[u], cq[k].z[u], g, 0u) >> gshift);
+        key[k][u] = 0xffffffffu;
+        if (u < cnt) key[k][u] = grp | (atomicAdd(h + grp, 1u) << 12);
       }
     }
     __syncthreads();
@@ -453,18 +542,18 @@ __global__ void __launch_bounds__(COARSE_THREADS) coarse_scatter_kernel(PaintPar
     }
     block_scan_inplace(h, ngroups, scratch);       // h -> local exclusive offsets (syncs inside)
 #pragma unroll
-    for (int u = 0; u < COARSE_PT; ++u) {
-      if (key[u] != 0xffffffffu) {
-        // re-read from L2 instead of keeping 4 float4 in registers: 62 registers would halve the
-        // number of resident CTAs (measured 1.10 -> 1.48 ms)
-        const int64_t i = c0 + u * COARSE_THREADS + tid;
-        const unsigned grp = key[u] & 0xfffu, pos = h[grp] + (key[u] >> 12);
-        stage[pos] = make_float4(grid_pos(p.x[i * p.stride], p.xmin, p.inv), grid_pos(p.y[i * p.stride], p.ymin, p.inv),
-                                 grid_pos(p.z[i * p.stride], p.zmin, p.inv), p.w ? p.w[i] : 1.0f);
-        skey[pos] = (unsigned short)grp;
+    for (int k = 0; k < COARSE_QPT; ++k) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (key[k][u] != 0xffffffffu) {
+          const unsigned grp = key[k][u] & 0xfffu, pos = h[grp] + (key[k][u] >> 12);
+          stage[pos] = make_float4(cq[k].x[u], cq[k].y[u], cq[k].z[u], cw[k][u]);
+          skey[pos] = (unsigned short)grp;
+        }
       }
     }
     __syncthreads();
+    if (ch + gridDim.x < nchunks) fetch(ch + gridDim.x);
     for (int j = tid; j < m; j += COARSE_THREADS) {
       const unsigned grp = skey[j];
       tmp[gb[grp] + ((unsigned)j - h[grp])] = stage[j];        // consecutive j of a group -> consecutive slots
@@ -508,9 +597,10 @@ __global__ void __launch_bounds__(512) fine_scatter_kernel(const float4* __restr
       ok[u] = i < end;
       if (ok[u]) r[u] = tmp[i];
     }
+    // no early exit inside the unrolled body: the FINE_UNR match -> atomic chains stay independent
+    // and overlap (a CTA-uniform `break` serialised them)
 #pragma unroll
     for (int u = 0; u < FINE_UNR; ++u) {
-      if (i0 + u * blockDim.x >= end) break;       // CTA-uniform
       const int f = ok[u] ? tile_of<ORDER, REFCIC>(r[u].x, r[u].y, r[u].z, g, 0u) - t0 : -1;
       const unsigned same = __match_any_sync(0xffffffffu, f);
       if (f >= 0 && lane == __ffs(same) - 1) atomicAdd(fh + f, (unsigned)__popc(same));
@@ -535,16 +625,22 @@ __global__ void __launch_bounds__(512) fine_scatter_kernel(const float4* __restr
       ok[u] = i < end;
       if (ok[u]) r[u] = tmp[i];
     }
+    int f[FINE_UNR];
+    unsigned same[FINE_UNR], base[FINE_UNR];
 #pragma unroll
     for (int u = 0; u < FINE_UNR; ++u) {
-      if (i0 + u * blockDim.x >= end) break;       // CTA-uniform
-      const int f = ok[u] ? tile_of<ORDER, REFCIC>(r[u].x, r[u].y, r[u].z, g, 0u) - t0 : -1;
-      const unsigned same = __match_any_sync(0xffffffffu, f);
-      const int leader = __ffs(same) - 1;
-      unsigned base = 0;
-      if (f >= 0 && lane == leader) base = atomicAdd(cur + f, (unsigned)__popc(same));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (f >= 0) sorted[beg + base + __popc(same & ((1u << lane) - 1u))] = r[u];
+      f[u] = ok[u] ? tile_of<ORDER, REFCIC>(r[u].x, r[u].y, r[u].z, g, 0u) - t0 : -1;
+      same[u] = __match_any_sync(0xffffffffu, f[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < FINE_UNR; ++u) {
+      base[u] = 0;
+      if (f[u] >= 0 && lane == __ffs(same[u]) - 1) base[u] = atomicAdd(cur + f[u], (unsigned)__popc(same[u]));
+    }
+#pragma unroll
+    for (int u = 0; u < FINE_UNR; ++u) {
+      base[u] = __shfl_sync(0xffffffffu, base[u], __ffs(same[u]) - 1);
+      if (f[u] >= 0) sorted[beg + base[u] + __popc(same[u] & ((1u << lane) - 1u))] = r[u];
     }
   }
 }
@@ -734,20 +830,22 @@ __device__ __forceinline__ void fx_deposit(const float4& r, float ws, unsigned* 
     tile_axis<ORDER>(r.z, n, wrap, az, wz);
     const int c = ((local_plane(ax, g.x0, g.nx, n) - ox) * L + (ay - oy)) * LP + (az - oz);
 #pragma unroll
+    for (int cc = 0; cc < ORDER; ++cc) wz[cc] *= ws;   // one multiply per update instead of two
+#pragma unroll
     for (int a = 0; a < ORDER; ++a) {
 #pragma unroll
       for (int b = 0; b < ORDER; ++b) {
         const float wxy = wx[a] * wy[b];
 #pragma unroll
         for (int cc = 0; cc < ORDER; ++cc)
-          fx_add<NEG>(lo, hi, c + (a * L + b) * LP + cc, (wxy * wz[cc]) * ws);
+          fx_add<NEG>(lo, hi, c + (a * L + b) * LP + cc, wxy * wz[cc]);
       }
     }
   }
 }
 
 template <int ORDER, bool REFCIC>
-__global__ void __launch_bounds__(256) paint_tile_fx_kernel(const float4* __restrict__ sorted,
+__global__ void __launch_bounds__(1024) paint_tile_fx_kernel(const float4* __restrict__ sorted,
                                                             const unsigned* __restrict__ offsets,
                                                             TileGeom g, int wrap, int variant,
                                                             int mesh_vec_ok,
@@ -1063,7 +1161,8 @@ static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayo
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
       }
-      paint_tile_fx_kernel<ORDER, REFCIC><<<g.ntiles, 256, smem, s>>>(sorted, offsets, g, p.wrap, p.variant,
+      static const int tpb = [] { const char* e = getenv("JPS_TILE_THREADS"); return e ? atoi(e) : 512; }();
+      paint_tile_fx_kernel<ORDER, REFCIC><<<g.ntiles, tpb, smem, s>>>(sorted, offsets, g, p.wrap, p.variant,
                                                                     mesh_vec_ok, wmax_bits, p.mesh);
     }
   }
