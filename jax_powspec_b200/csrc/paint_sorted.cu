@@ -367,8 +367,19 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(PaintParams p, Tile
 //                        histogram over the group's tiles -> tile offsets -> second pass places every
 //                        record with a warp-aggregated SHARED cursor; writes go to <= 2^gshift
 //                        frontiers per resident group, which L2 merges into full lines.
-constexpr int COARSE_CHUNK = 4096;                 // 64 KB of staged records per CTA
-constexpr int COARSE_THREADS = 512;
+#ifndef JPS_COARSE_CHUNK
+#define JPS_COARSE_CHUNK 4096
+#define JPS_COARSE_THREADS 512
+#define JPS_COARSE_MINB 2
+#endif
+#ifndef JPS_FINE_MINB
+#define JPS_FINE_MINB 1
+#endif
+#ifndef JPS_FINE_UNR
+#define JPS_FINE_UNR 4
+#endif
+constexpr int COARSE_CHUNK = JPS_COARSE_CHUNK;     // 64 KB of staged records per CTA
+constexpr int COARSE_THREADS = JPS_COARSE_THREADS;
 constexpr int COARSE_QPT = COARSE_CHUNK / (4 * COARSE_THREADS);   // quads (4 particles) per thread
 constexpr int kMaxGroups = 2048;
 
@@ -483,7 +494,7 @@ __global__ void group_bases_from_offsets_kernel(const unsigned* __restrict__ off
 }
 
 template <int ORDER, bool REFCIC>
-__global__ void __launch_bounds__(COARSE_THREADS, 2) coarse_scatter_kernel(PaintParams p, TileGeom g, int gshift,
+__global__ void __launch_bounds__(COARSE_THREADS, JPS_COARSE_MINB) coarse_scatter_kernel(PaintParams p, TileGeom g, int gshift,
                                                                         int ngroups,
                                                                         unsigned* __restrict__ gcursor,
                                                                         float4* __restrict__ tmp) {
@@ -565,7 +576,7 @@ __global__ void __launch_bounds__(COARSE_THREADS, 2) coarse_scatter_kernel(Paint
 // HAVE_OFFSETS: the per-tile offsets already exist (small meshes: the shared-memory tile histogram
 // of bucket_count_smem_kernel), so the group's records are read ONCE; otherwise pass 1 builds them.
 template <int ORDER, bool REFCIC, bool HAVE_OFFSETS>
-__global__ void __launch_bounds__(512) fine_scatter_kernel(const float4* __restrict__ tmp,
+__global__ void __launch_bounds__(512, JPS_FINE_MINB) fine_scatter_kernel(const float4* __restrict__ tmp,
                                                            const unsigned* __restrict__ gbase, TileGeom g,
                                                            int gshift, int ngroups, int nbuckets,
                                                            unsigned* offsets,
@@ -579,7 +590,7 @@ __global__ void __launch_bounds__(512) fine_scatter_kernel(const float4* __restr
   const unsigned beg = gbase[grp], end = gbase[grp + 1];
   const int t0 = grp << gshift;
   const int lane = threadIdx.x & 31;
-  constexpr int FINE_UNR = 4;                      // records in flight per thread
+  constexpr int FINE_UNR = JPS_FINE_UNR;           // records in flight per thread
   if (HAVE_OFFSETS) {
     for (int i = threadIdx.x; i < G; i += blockDim.x)
       cur[i] = (t0 + i < nbuckets) ? offsets[t0 + i] - beg : 0u;
@@ -786,15 +797,31 @@ struct TileDims {
 // v >= 0 is the magnitude of one contribution in units of 2^-31 of the weight scale (< 2^32, one
 // F2I); NEG selects subtraction (negative particle weight).  64-bit two's-complement arithmetic on
 // the (hi, lo) word pair: the low-word atomic returns the old value, from which carry / borrow follow.
-template <bool NEG>
-__device__ __forceinline__ void fx_add(unsigned* __restrict__ lo, unsigned* __restrict__ hi, int idx, float v) {
-  const unsigned q = __float2uint_rn(v);           // q == 0 needs no special case: no carry, no borrow
-  if (!NEG) {
-    const unsigned old = atomicAdd(lo + idx, q);
-    if (old + q < old) atomicAdd(hi + idx, 1u);              // carry (rare; a predicated PTX red
-  } else {                                                   // compiles to the same branch)
-    const unsigned old = atomicAdd(lo + idx, 0u - q);
-    if (old < q) atomicAdd(hi + idx, 0xffffffffu);           // borrow
+// K contributions at once: all K low-word atomics are issued back to back (independent, K in
+// flight), and the K carry tests share ONE rarely taken branch.  (One atomic + test + branch per
+// contribution serialised every update behind the previous atomic's return and cost 9 instructions
+// per update instead of 6.)
+template <bool NEG, int K>
+__device__ __forceinline__ void fx_add_batch(unsigned* __restrict__ lo, unsigned* __restrict__ hi,
+                                             const int (&idx)[K], const float (&v)[K]) {
+  unsigned q[K], old[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) q[j] = __float2uint_rn(v[j]);     // q == 0: no carry, no borrow
+#pragma unroll
+  for (int j = 0; j < K; ++j) old[j] = atomicAdd(lo + idx[j], NEG ? 0u - q[j] : q[j]);
+  // carry of word j <=> q > ~old; borrow <=> old < q.  The slow path re-derives the flags from the
+  // wrapped sum so that the compiler keeps the fast path to K compares (it otherwise materialises
+  // both senses of every predicate before the branch).
+  bool any = false;
+#pragma unroll
+  for (int j = 0; j < K; ++j) any |= NEG ? (old[j] < q[j]) : (q[j] > ~old[j]);
+  if (any) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const unsigned sum = NEG ? old[j] - q[j] : old[j] + q[j];
+      if (NEG ? (sum > old[j]) : (sum < old[j]))
+        atomicAdd(hi + idx[j], NEG ? 0xffffffffu : 1u);          // borrow / carry into the high word
+    }
   }
 }
 
@@ -814,14 +841,15 @@ __device__ __forceinline__ void fx_deposit(const float4& r, float ws, unsigned* 
     cic_reference_axis(r.z, n, wrap, variant, z0, z1, mdz, ddz);
     const int c = ((local_plane(x0, g.x0, g.nx, n) - ox) * L + (y0 - oy)) * LP + (z0 - oz);
     constexpr int SX = L * LP, SY = LP;
-    fx_add<NEG>(lo, hi, c, ((mdx * mdy) * mdz) * ws);
-    fx_add<NEG>(lo, hi, c + SX, ((ddx * mdy) * mdz) * ws);
-    fx_add<NEG>(lo, hi, c + SY, ((mdx * ddy) * mdz) * ws);
-    fx_add<NEG>(lo, hi, c + 1, ((mdx * mdy) * ddz) * ws);
-    fx_add<NEG>(lo, hi, c + SX + SY, ((ddx * ddy) * mdz) * ws);
-    fx_add<NEG>(lo, hi, c + SX + 1, ((ddx * mdy) * ddz) * ws);
-    fx_add<NEG>(lo, hi, c + SY + 1, ((mdx * mdy) * ddz) * ws);       // Q1 (reference weight)
-    fx_add<NEG>(lo, hi, c + SX + SY + 1, ((ddx * ddy) * ddz) * ws);
+    const int ia[4] = {c, c + SX, c + SY, c + 1};
+    const float va[4] = {((mdx * mdy) * mdz) * ws, ((ddx * mdy) * mdz) * ws, ((mdx * ddy) * mdz) * ws,
+                         ((mdx * mdy) * ddz) * ws};
+    fx_add_batch<NEG, 4>(lo, hi, ia, va);
+    const int ib[4] = {c + SX + SY, c + SX + 1, c + SY + 1, c + SX + SY + 1};
+    const float vb[4] = {((ddx * ddy) * mdz) * ws, ((ddx * mdy) * ddz) * ws,
+                         ((mdx * mdy) * ddz) * ws,                       // Q1 (reference weight)
+                         ((ddx * ddy) * ddz) * ws};
+    fx_add_batch<NEG, 4>(lo, hi, ib, vb);
   } else {
     int ax, ay, az;
     float wx[ORDER], wy[ORDER], wz[ORDER];
@@ -836,9 +864,14 @@ __device__ __forceinline__ void fx_deposit(const float4& r, float ws, unsigned* 
 #pragma unroll
       for (int b = 0; b < ORDER; ++b) {
         const float wxy = wx[a] * wy[b];
+        int idx[ORDER];
+        float v[ORDER];
 #pragma unroll
-        for (int cc = 0; cc < ORDER; ++cc)
-          fx_add<NEG>(lo, hi, c + (a * L + b) * LP + cc, wxy * wz[cc]);
+        for (int cc = 0; cc < ORDER; ++cc) {
+          idx[cc] = c + (a * L + b) * LP + cc;
+          v[cc] = wxy * wz[cc];
+        }
+        fx_add_batch<NEG, ORDER>(lo, hi, idx, v);     // one z-row of the stencil
       }
     }
   }
@@ -1124,7 +1157,7 @@ static int run_bucket_two_level(const PaintParams& p, const TileGeom& g, const S
     }
     const int64_t nchunks = (p.n_part + COARSE_CHUNK - 1) / COARSE_CHUNK;
     ScopedLaunch T(K_BUCKET_SCATTER, s);
-    coarse_scatter_kernel<ORDER, REFCIC><<<(int)std::min<int64_t>(nchunks, 2 * kNumSMs), COARSE_THREADS, smem, s>>>(
+    coarse_scatter_kernel<ORDER, REFCIC><<<(int)std::min<int64_t>(nchunks, JPS_COARSE_MINB * kNumSMs), COARSE_THREADS, smem, s>>>(
         p, g, gshift, ngroups, gcursor, tmp);
   }
   JPS_CHECK_LAUNCH();
