@@ -14,6 +14,7 @@
  *   jps_xi_fundamental        src/correlations.py:191-261  xi_vec_fundamental
  *   jps_bispec                src/correlations.py:334-462  bispec
  *   jps_paint_powspec         tests/correlations.py:41-78  paint -> delta=rho/mean-1 -> powspec_vec
+ *   jps_text_parse            tests/correlations.py:29-31  np.loadtxt(usecols, float32) + box mask
  *
  * The reference has no FFI of its own (it is pure Python on jax.numpy); these are the
  * symbols a jax.ffi handler, a ctypes stub or any other host binds.
@@ -277,6 +278,34 @@ JPS_API int jps_paint_powspec(jps_plan_t* plan,
                       float* mesh, void* paint_workspace, size_t paint_workspace_bytes,
                       float* k3d, float* pk3d, float* nmodes,
                       double* sums, int64_t* counts, void* stream);
+
+/* ------------------------------------------------------------------ catalogue text --- */
+/* Whitespace-separated ASCII catalogue -> float32 rows on the device.
+ * Replaces  np.loadtxt(path, usecols=(0,1,2), dtype=np.float32)  (tests/correlations.py:29,
+ * tests/all_corr.py:26, tests/bispec.py:28) and the pd.read_csv(..., delim_whitespace=True)
+ * variant (tests/positions.py:25), plus the box mask ((p < box) & (p > 0)).all(axis=1) the scripts
+ * apply next (tests/correlations.py:30).  `text` is the raw file content in device memory
+ * (16-byte aligned).  Fields are converted exactly as NumPy does: decimal -> nearest double ->
+ * nearest float.  Lines that are blank or hold only a comment are skipped; `skiprows` leading
+ * lines are ignored (pandas' header line: skiprows=1).
+ *
+ * Two calls, because the output size is data dependent:
+ *   jps_text_count_lines : *n_lines (device int64) = number of text lines
+ *   jps_text_parse       : out[n_rows][ncols] (capacity n_lines rows), rows in file order;
+ *       counters (device int64[4]) = { n_rows, n_slow, n_bad, first_bad_line or -1 }
+ *       filter != 0 keeps only rows with lo < value < hi in every requested column
+ *       slow_rows (device int64[slow_capacity][2]) = (output row, byte offset of the line) of
+ *       the rows holding a field outside the exact envelope of the device converter (more than
+ *       19 significant digits, |decimal exponent| > 27, nan / inf): the host re-parses those
+ *       fields (n_slow may exceed slow_capacity: then call again with a larger list)
+ *       n_bad counts rows with a non-numeric or missing requested column (np.loadtxt raises). */
+JPS_API size_t jps_text_workspace_bytes(int64_t nbytes, int64_t n_lines, int ncols);
+JPS_API int jps_text_count_lines(const char* text, int64_t nbytes, int64_t* n_lines,
+                         void* workspace, size_t workspace_bytes, void* stream);
+JPS_API int jps_text_parse(const char* text, int64_t nbytes, int64_t n_lines, int skiprows, int comment,
+                   const int* usecols /* host */, int ncols, int filter, float lo, float hi,
+                   float* out, int64_t* counters, int64_t* slow_rows, int64_t slow_capacity,
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

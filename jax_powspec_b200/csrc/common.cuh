@@ -73,6 +73,9 @@ enum KernelId {
   K_TRIPLE_REDUCE,
   K_XI_BIN,
   K_MISC,
+  K_TEXT_INDEX,
+  K_TEXT_PARSE,
+  K_TEXT_COMPACT,
   K_NUM
 };
 

@@ -83,6 +83,15 @@ JPS_HD uint64_t pow5(int k) {                       // k <= 27: 5^27 < 2^63
 
 // w != 0, |q| <= 27
 JPS_HD double decimal_to_double(uint64_t w, int q) {
+  // Clinger's fast path: w and 10^|q| are both exact doubles (w < 2^53, |q| <= 22), so ONE IEEE
+  // multiplication / division is the correctly rounded result.  Covers "%.6f"-style catalogues;
+  // the 128-bit integer path below takes the 16..19-digit mantissas of "%.18e".
+  if (w < (1ull << 53) && q >= -22 && q <= 22) {
+    double p10 = 1.0;
+    const int a = q < 0 ? -q : q;
+    for (int i = 0; i < a; ++i) p10 *= 10.0;         // exact: 10^22 < 2^53 * 2^22 and 5^22 < 2^53
+    return q < 0 ? (double)w / p10 : (double)w * p10;
+  }
   if (q >= 0) return round_to_double((u128)w * pow5(q), q, false);
   const int lz = clz64(w);
   const u128 num = ((u128)(w << lz)) << 64;
