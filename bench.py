@@ -243,7 +243,10 @@ def run_gpu_arm(a, wl):
 
     import jax_powspec_b200 as jps
     from jax_powspec_b200 import _lib
+    from jax_powspec_b200.dist import bind_near_gpu
     from jax_powspec_b200.mocks import lognormal_catalog
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_near_gpu(local) if not a.no_numa_bind else {"bound": False, "disabled": True}
 
     def barrier():
         if world > 1:
@@ -357,6 +360,7 @@ def run_gpu_arm(a, wl):
 
     cpu = None
     if world == 1 and not a.no_cpu:
+        os.sched_setaffinity(0, all_cpus)          # the CPU baseline may use every host core
         from oracle import build as obuild
         obuild.build()
         n_sample = a.cpu_sample or 10_000_000
@@ -375,7 +379,7 @@ def run_gpu_arm(a, wl):
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(a, wl, world),
-        "clocks": clocks,
+        "clocks": clocks, "host_affinity": numa,
         "e2e": {"value": world * npart / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
@@ -515,6 +519,7 @@ def main():
     ap.add_argument("--n-mesh", type=int, default=None)
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the CPUs nearest its GPU")
     ap.add_argument("--quick", action="store_true", help="stop after the device-resident timed region (ncu runs)")
     ap.add_argument("--quick-kernels", action="store_true", help="stop after the per-kernel pass (sweeps)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"],

@@ -279,6 +279,20 @@ JPS_API int jps_paint_powspec(jps_plan_t* plan,
                       float* k3d, float* pk3d, float* nmodes,
                       double* sums, int64_t* counts, void* stream);
 
+/* Gradients of xi(s) and of the bispectrum with respect to the mesh (normalise = 0 semantics: the
+ * caller differentiates delta = rho/mean - 1 itself, as the reference's scripts do under JAX,
+ * tests/lognormal_bispec.py:71-106).  NaN cotangents (empty bins, Q11/Q22) count as zero.
+ *   jps_xi_grad     : grad_xi [nb][3] (cotangent of xi3D of jps_xi / the composites) -> grad_mesh [N^3];
+ *                     plan needs n_shell_fields >= 1
+ *   jps_bispec_grad : grad_pk [nbins+2], grad_B [nbins] (cotangents of Pk and B of jps_bispec; fold
+ *                     the cotangent of Q = B/(P0 P1 + P0 P3 + P1 P3) into them first) -> grad_mesh;
+ *                     plan needs n_shell_fields >= 6.  7 FFTs whatever nbins. */
+JPS_API int jps_xi_grad(jps_plan_t* plan, const float* mesh, float box_size, const float* s_edges /* host */,
+                int nb, int mas_order, const float* grad_xi, float* grad_mesh, void* stream);
+JPS_API int jps_bispec_grad(jps_plan_t* plan, const float* mesh, float box_size, float k1, float k2,
+                    const float* theta /* host */, int nbins, int mas_order,
+                    const float* grad_pk, const float* grad_B, float* grad_mesh, void* stream);
+
 /* ------------------------------------------------------------------ catalogue text --- */
 /* Whitespace-separated ASCII catalogue -> float32 rows on the device.
  * Replaces  np.loadtxt(path, usecols=(0,1,2), dtype=np.float32)  (tests/correlations.py:29,

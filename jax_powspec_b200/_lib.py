@@ -79,6 +79,8 @@ SIGNATURES = {
                             _vp, _vp, _vp, _vp, _vp]),
     "jps_paint_powspec": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _f, _f, _i, _i, _i, _i,
                                _fp, _i, _f, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "jps_xi_grad": (_i, [_vp, _vp, _f, _fp, _i, _i, _vp, _vp, _vp]),
+    "jps_bispec_grad": (_i, [_vp, _vp, _f, _f, _f, _fp, _i, _i, _vp, _vp, _vp, _vp]),
     "jps_text_workspace_bytes": (_sz, [_i64, _i64, _i]),
     "jps_text_count_lines": (_i, [_vp, _i64, _vp, _vp, _sz, _vp]),
     "jps_text_parse": (_i, [_vp, _i64, _i64, _i, _i, C.POINTER(_i), _i, _i, _f, _f, _vp, _vp, _vp, _i64,

@@ -58,6 +58,17 @@ __global__ void __launch_bounds__(256) shell_filter_kernel(const float2* __restr
   }
 }
 
+// host launcher for other translation units (grad_est.cu): masked, deconvolved delta_k of one shell
+int launch_shell_filter(jps_plan* plan, int mas_order, int tlo, int thi, float* out, cudaStream_t s) {
+  const int n = plan->n;
+  ScopedLaunch L(K_SHELL_FILTER, s);
+  const int blocks = (int)std::min<long long>((long long)n * n, (long long)kNumSMs * 16);
+  shell_filter_kernel<<<blocks, 256, 0, s>>>(plan->dk, n, plan->nz, plan->pitch,
+                                             plan->wlut + (size_t)(mas_order - 2) * n, 0, tlo, thi, (float2*)out, nullptr);
+  JPS_CHECK_LAUNCH();
+  return JPS_OK;
+}
+
 // out[0] += sum d3^2, out[1] += sum i3^2, and when `triple`: out[2] += sum d0 d1 d3,
 // out[3] += sum i0 i1 i3.  Fields are [n][n][rowpitch] reals (in-place C2R layout).
 __global__ void __launch_bounds__(256) triple_reduce_kernel(const float* __restrict__ d0,

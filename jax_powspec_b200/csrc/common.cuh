@@ -140,6 +140,8 @@ struct jps_plan {
   bool r2c_ok = false;
   cufftHandle c2r = 0;          // single inverse transform (xi, bispectrum shells)
   bool c2r_ok = false;
+  cufftHandle r2c_ip = 0;       // forward transform IN PLACE on a shell field (estimator gradients);
+  bool r2c_ip_ok = false;       // only when the plan has shell fields
 
   // workspace partition (all device pointers inside the caller's workspace)
   char* ws = nullptr;

@@ -208,6 +208,15 @@ __global__ void __launch_bounds__(256) paint_grad_kernel(PaintParams p, const fl
   }
 }
 
+// host launcher for other translation units (kernels cannot be launched across TUs without -rdc)
+int launch_unpad_add(const float* field, int n, int rowpitch, const double* dcterm, float* out, cudaStream_t s) {
+  ScopedLaunch L(K_MISC, s);
+  const int blocks = (int)std::min<long long>((long long)n * n, (long long)kNumSMs * 16);
+  unpad_add_kernel<<<blocks, 256, 0, s>>>(field, n, rowpitch, dcterm, out);
+  JPS_CHECK_LAUNCH();
+  return JPS_OK;
+}
+
 // powspec.cu
 int npairs_for(int n);
 int bin_from_dk_public(jps_plan* plan, const BinTable& T, int normalise, int mas_order, cudaStream_t s);

@@ -136,6 +136,17 @@ static int make_c2r_inplace(int n, int pitch, cufftHandle* h, size_t* work) {
   return JPS_OK;
 }
 
+static int make_r2c_inplace(int n, int pitch, cufftHandle* h, size_t* work) {
+  JPS_CHECK_CUFFT(cufftCreate(h));
+  JPS_CHECK_CUFFT(cufftSetAutoAllocation(*h, 0));
+  long long dims[3] = {n, n, n};
+  long long inembed[3] = {n, n, 2LL * pitch};
+  long long onembed[3] = {n, n, pitch};
+  JPS_CHECK_CUFFT(cufftMakePlanMany64(*h, 3, dims, inembed, 1, 2LL * n * n * pitch, onembed, 1,
+                                      (long long)n * n * pitch, CUFFT_R2C, 1, work));
+  return JPS_OK;
+}
+
 static int pitch_for(int n) { return n / 2 + 1; }
 
 }  // namespace jps
@@ -185,7 +196,13 @@ extern "C" int jps_plan_workspace_bytes(int n_mesh, int n_shell_fields, int flag
   rc = make_c2r_inplace(n_mesh, pitch, &h, &w2);
   cufftDestroy(h);
   if (rc) return rc;
-  *bytes = make_layout(n_mesh, pitch, std::max(w1, w2), n_shell_fields).total;
+  size_t w3 = 0;
+  if (n_shell_fields > 0) {
+    rc = make_r2c_inplace(n_mesh, pitch, &h, &w3);
+    cufftDestroy(h);
+    if (rc) return rc;
+  }
+  *bytes = make_layout(n_mesh, pitch, std::max(std::max(w1, w2), w3), n_shell_fields).total;
   return JPS_OK;
 }
 
@@ -205,7 +222,7 @@ extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* 
   p->k2max = 3LL * (n_mesh / 2) * (n_mesh / 2);
   cudaError_t ce = cudaGetDevice(&p->device);
   if (ce != cudaSuccess) { delete p; set_error("jps_plan_create: cudaGetDevice failed: %s", cudaGetErrorString(ce)); return JPS_ERR_CUDA; }
-  size_t w1 = 0, w2 = 0;
+  size_t w1 = 0, w2 = 0, w3 = 0;
   int rc = JPS_OK;
   if (!tables_only) {
     rc = make_r2c(n_mesh, p->pitch, &p->r2c, &w1);
@@ -214,8 +231,13 @@ extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* 
     rc = make_c2r_inplace(n_mesh, p->pitch, &p->c2r, &w2);
     if (rc) { cufftDestroy(p->r2c); delete p; return rc; }
     p->c2r_ok = true;
+    if (n_shell_fields > 0) {
+      rc = make_r2c_inplace(n_mesh, p->pitch, &p->r2c_ip, &w3);
+      if (rc) { cufftDestroy(p->r2c); cufftDestroy(p->c2r); delete p; return rc; }
+      p->r2c_ip_ok = true;
+    }
   }
-  Layout L = make_layout(n_mesh, p->pitch, std::max(w1, w2), n_shell_fields, tables_only);
+  Layout L = make_layout(n_mesh, p->pitch, std::max(std::max(w1, w2), w3), n_shell_fields, tables_only);
   if (workspace_bytes < L.total) {
     set_error("jps_plan_create: workspace has %zu bytes, %zu needed", workspace_bytes, L.total);
     jps_plan_destroy(p);
@@ -226,7 +248,7 @@ extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* 
   p->ws_bytes = workspace_bytes;
   p->dk = (float2*)(ws + L.dk);
   p->fft_work = ws + L.fft_work;
-  p->fft_work_bytes = std::max(w1, w2);
+  p->fft_work_bytes = std::max(std::max(w1, w2), w3);
   for (int i = 0; i < kNumTables; ++i) {
     BinTable& T = p->tables[i];
     T.lut = (int32_t*)(ws + L.t[i].lut);
@@ -247,6 +269,7 @@ extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* 
   if (!tables_only) {
     r = cufftSetWorkArea(p->r2c, p->fft_work);
     if (r == CUFFT_SUCCESS) r = cufftSetWorkArea(p->c2r, p->fft_work);
+    if (r == CUFFT_SUCCESS && p->r2c_ip_ok) r = cufftSetWorkArea(p->r2c_ip, p->fft_work);
   }
   if (r != CUFFT_SUCCESS) {
     set_error("jps_plan_create: cufftSetWorkArea failed (%d)", (int)r);
@@ -270,6 +293,7 @@ extern "C" int jps_plan_destroy(jps_plan_t* p) {
   if (!p) return JPS_OK;
   if (p->r2c_ok) cufftDestroy(p->r2c);
   if (p->c2r_ok) cufftDestroy(p->c2r);
+  if (p->r2c_ip_ok) cufftDestroy(p->r2c_ip);
   delete p;
   return JPS_OK;
 }

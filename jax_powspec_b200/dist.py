@@ -38,6 +38,37 @@ def init_from_env(backend: str | None = None, device: torch.device | None = None
     return r, w, lr
 
 
+def bind_near_gpu(local_rank: int | None = None) -> dict:
+    """Pin the calling process to the CPU cores NVML reports as closest to its GPU (same NUMA
+    node / PCIe root), so that the pinned host buffers it allocates next are first-touched on that
+    node.  With one process per GPU and 8 GPUs on two sockets, unbound ranks stage half of the
+    host->device traffic across the socket interconnect.  Best effort: returns what was done and
+    never raises (containers with a restricted cpuset keep their affinity)."""
+    info = {"bound": False}
+    try:
+        import pynvml
+        if local_rank is None:
+            local_rank = torch.cuda.current_device()
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(local_rank)
+        bus = f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        before = sorted(os.sched_getaffinity(0))
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        ideal = {64 * i + b for i, wd in enumerate(mask) for b in range(64) if (int(wd) >> b) & 1}
+        target = sorted(ideal & set(before))
+        info.update(pci=bus, cpus_before=len(before), cpus_ideal=len(ideal))
+        if target and len(target) < len(before):
+            os.sched_setaffinity(0, target)
+            info.update(bound=True, cpus_after=len(target), first_cpu=target[0])
+        else:
+            info.update(cpus_after=len(before))
+    except Exception as e:  # noqa: BLE001 -- diagnostics only
+        info["error"] = f"{type(e).__name__}: {e}"[:200]
+    return info
+
+
 def shard_indices(n_items: int, rank: int | None = None, world_size: int | None = None) -> list[int]:
     """Round-robin shard of range(n_items): rank r owns r, r+W, r+2W, ... (balanced to +-1)."""
     if rank is None or world_size is None:
