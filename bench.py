@@ -418,7 +418,8 @@ def run_slab_arm(a, wl):
     z = torch.rand(nloc, generator=g, device=dev) * box
     for t in (y, z):
         t[t >= box] = 0.0
-    pipe = SlabPipeline(n, box, k_edges_for(box, n), order=order, compat="fixed", method=a.method, transport=a.transport)
+    pipe = SlabPipeline(n, box, k_edges_for(box, n), order=order, compat="fixed", method=a.method, transport=a.transport,
+                        overlap=not a.no_overlap)
 
     def sync():
         if world > 1:
@@ -519,6 +520,7 @@ def main():
     ap.add_argument("--n-mesh", type=int, default=None)
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-overlap", action="store_true", help="c4: do not overlap the 2-D FFT with the peer transfer")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the CPUs nearest its GPU")
     ap.add_argument("--quick", action="store_true", help="stop after the device-resident timed region (ncu runs)")
     ap.add_argument("--quick-kernels", action="store_true", help="stop after the per-kernel pass (sweeps)")

@@ -239,6 +239,14 @@ JPS_API int jps_ipc_close(void* ptr);
 /* Let kernels on the current device dereference memory of `peer_device` (NVLink peer access). */
 JPS_API int jps_enable_peer_access(int peer_device);
 JPS_API int jps_slab_pack_p2p(jps_slab_plan_t* plan, const void* yz, void* const* peer_recv, void* stream);
+/* Plane-range variants: transform / send the owned planes [x_begin, x_begin + x_count) only, so
+ * that the 2-D FFT of one chunk overlaps the NVLink transfer of the previous one (two streams on
+ * the host side).  x_count must be the whole slab or jps_slab_chunk_planes() (0 = no chunking). */
+JPS_API int jps_slab_chunk_planes(jps_slab_plan_t* plan);
+JPS_API int jps_slab_fft_yz_planes(jps_slab_plan_t* plan, const float* slab, void* yz, int x_begin, int x_count,
+                           void* stream);
+JPS_API int jps_slab_pack_p2p_planes(jps_slab_plan_t* plan, const void* yz, void* const* peer_recv, int x_begin,
+                             int x_count, void* stream);
 JPS_API int jps_slab_fft_x(jps_slab_plan_t* plan, void* dk, void* stream);
 /* This rank's partial sums of |delta_k|^2 L_l per user bin (sums[nb*3], float64, overwritten) and the
  * GLOBAL exact mode counts (counts[nb], identical on every rank; may be NULL).  dc: device pointer to

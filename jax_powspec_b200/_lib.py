@@ -71,6 +71,9 @@ SIGNATURES = {
     "jps_ipc_close": (_i, [_vp]),
     "jps_enable_peer_access": (_i, [_i]),
     "jps_slab_pack_p2p": (_i, [_vp, _vp, C.POINTER(_vp), _vp]),
+    "jps_slab_chunk_planes": (_i, [_vp]),
+    "jps_slab_fft_yz_planes": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "jps_slab_pack_p2p_planes": (_i, [_vp, _vp, C.POINTER(_vp), _i, _i, _vp]),
     "jps_slab_fft_x": (_i, [_vp, _vp, _vp]),
     "jps_slab_powspec_partial": (_i, [_vp, _vp, _vp, _i, _f, _fp, _i, _i, _vp, _vp, _vp]),
     "jps_slab_powspec_finalize": (_i, [_vp, _f, _fp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp]),

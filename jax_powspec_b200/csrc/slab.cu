@@ -17,6 +17,9 @@
 #include <cmath>
 
 constexpr int kMaxRanks = 64;
+constexpr int kSlabChunks = 4;
+
+static int chunk_planes_for(int nxl) { return (nxl % kSlabChunks == 0 && nxl / kSlabChunks >= 2) ? nxl / kSlabChunks : 0; }
 
 struct jps_slab_plan {
   int n = 0, nz = 0, nranks = 1, rank = 0, nxl = 0, nyl = 0;
@@ -24,6 +27,11 @@ struct jps_slab_plan {
   void* peer_host[kMaxRanks] = {};  // last pointers uploaded
   cufftHandle fft_yz = 0, fft_x = 0;
   bool yz_ok = false, x_ok = false;
+  // A second 2-D plan over a quarter of the owned planes: the transform of chunk c+1 overlaps the
+  // NVLink transfer of chunk c (jps_slab_fft_yz_planes / jps_slab_pack_p2p_planes on two streams).
+  cufftHandle fft_yz_chunk = 0;
+  bool yzc_ok = false;
+  int chunk_planes = 0;
   void* work = nullptr;
   size_t work_bytes = 0;
   jps_plan* tables = nullptr;     // bin tables + accumulators (no 3-D FFT inside)
@@ -168,13 +176,14 @@ __global__ void __launch_bounds__(256) pk_bin_ysharded_kernel(SlabPkParams P) {
 //   dst_q[(rank*nxl + xl)*nyl*nz + e] = yz[xl*n*nz + q*nyl*nz + e],  e in [0, nyl*nz)
 __global__ void __launch_bounds__(256) slab_pack_p2p_kernel(const float2* __restrict__ yz,
                                                             void* const* __restrict__ peers, int n,
-                                                            int nz, int nxl, int nyl, int nranks, int rank) {
+                                                            int nz, int nxl, int nyl, int nranks, int rank,
+                                                            int x_begin, int x_count) {
   const long long run = (long long)nyl * nz;                 // contiguous complex elements per (xl, q)
-  const long long nrun = (long long)nxl * nranks;
+  const long long nrun = (long long)x_count * nranks;
   const bool vec = (run % 2 == 0);                           // 16-byte moves when every run is 16-byte aligned
   for (long long r = blockIdx.x; r < nrun; r += gridDim.x) {
     const int q = (int)(r % nranks);                         // consecutive CTAs -> different peers
-    const int xl = (int)(r / nranks);
+    const int xl = x_begin + (int)(r / nranks);
     const float2* src = yz + (size_t)xl * n * nz + (size_t)q * run;
     float2* dst = reinterpret_cast<float2*>(peers[q]) + ((size_t)rank * nxl + xl) * run;
     if (vec) {
@@ -235,9 +244,15 @@ extern "C" int jps_slab_plan_workspace_bytes(int n_mesh, int nranks, size_t* byt
   rc = make_fft_x(n_mesh, n_mesh / nranks, &h, &w2);
   cufftDestroy(h);
   if (rc) return rc;
+  size_t w3 = 0;
+  if (chunk_planes_for(n_mesh / nranks)) {
+    rc = make_fft_yz(n_mesh, chunk_planes_for(n_mesh / nranks), &h, &w3);
+    cufftDestroy(h);
+    if (rc) return rc;
+  }
   const size_t tb = tables_bytes(n_mesh);
   JPS_REQUIRE(tb > 0, "jps_slab_plan_workspace_bytes: table sizing failed");
-  *bytes = align_up(std::max(w1, w2), 256) + align_up(tb, 256) + 1024 + 512;
+  *bytes = align_up(std::max(std::max(w1, w2), w3), 256) + align_up(tb, 256) + 1024 + 512;
   return JPS_OK;
 }
 
@@ -245,6 +260,7 @@ extern "C" int jps_slab_plan_destroy(jps_slab_plan_t* p) {
   if (!p) return JPS_OK;
   if (p->yz_ok) cufftDestroy(p->fft_yz);
   if (p->x_ok) cufftDestroy(p->fft_x);
+  if (p->yzc_ok) cufftDestroy(p->fft_yz_chunk);
   if (p->tables) jps_plan_destroy(p->tables);
   delete p;
   return JPS_OK;
@@ -268,7 +284,14 @@ extern "C" int jps_slab_plan_create(int n_mesh, int nranks, int rank, void* work
   rc = make_fft_x(n_mesh, p->nyl, &p->fft_x, &w2);
   if (rc) { jps_slab_plan_destroy(p); return rc; }
   p->x_ok = true;
-  const size_t wb = align_up(std::max(w1, w2), 256) + 1024;       // + the peer pointer table
+  size_t w3 = 0;
+  p->chunk_planes = chunk_planes_for(p->nxl);
+  if (p->chunk_planes) {
+    rc = make_fft_yz(n_mesh, p->chunk_planes, &p->fft_yz_chunk, &w3);
+    if (rc) { jps_slab_plan_destroy(p); return rc; }
+    p->yzc_ok = true;
+  }
+  const size_t wb = align_up(std::max(std::max(w1, w2), w3), 256) + 1024;       // + the peer pointer table
   const size_t tb = tables_bytes(n_mesh);
   if (workspace_bytes < wb + align_up(tb, 256)) {
     set_error("jps_slab_plan_create: workspace has %zu bytes, %zu needed", workspace_bytes, wb + align_up(tb, 256));
@@ -277,7 +300,8 @@ extern "C" int jps_slab_plan_create(int n_mesh, int nranks, int rank, void* work
   }
   p->work = workspace; p->work_bytes = wb - 1024;
   p->peer_dev = (void**)((char*)workspace + wb - 1024);
-  if (cufftSetWorkArea(p->fft_yz, p->work) != CUFFT_SUCCESS || cufftSetWorkArea(p->fft_x, p->work) != CUFFT_SUCCESS) {
+  if (cufftSetWorkArea(p->fft_yz, p->work) != CUFFT_SUCCESS || cufftSetWorkArea(p->fft_x, p->work) != CUFFT_SUCCESS ||
+      (p->yzc_ok && cufftSetWorkArea(p->fft_yz_chunk, p->work) != CUFFT_SUCCESS)) {
     set_error("jps_slab_plan_create: cufftSetWorkArea failed");
     jps_slab_plan_destroy(p);
     return JPS_ERR_CUFFT;
@@ -345,9 +369,12 @@ extern "C" int jps_enable_peer_access(int peer_device) {
   return JPS_OK;
 }
 
-extern "C" int jps_slab_pack_p2p(jps_slab_plan_t* p, const void* yz, void* const* peer_recv, void* stream) {
+extern "C" int jps_slab_pack_p2p_planes(jps_slab_plan_t* p, const void* yz, void* const* peer_recv, int x_begin,
+                                        int x_count, void* stream) {
   JPS_REQUIRE(p && yz && peer_recv, "jps_slab_pack_p2p: NULL argument");
   JPS_REQUIRE(p->nranks <= kMaxRanks, "jps_slab_pack_p2p: too many ranks");
+  JPS_REQUIRE(x_begin >= 0 && x_count >= 1 && x_begin + x_count <= p->nxl, "jps_slab_pack_p2p: plane range [%d, %d) outside [0, %d)",
+              x_begin, x_begin + x_count, p->nxl);
   cudaStream_t s = (cudaStream_t)stream;
   bool changed = false;
   for (int q = 0; q < p->nranks; ++q) {
@@ -359,11 +386,41 @@ extern "C" int jps_slab_pack_p2p(jps_slab_plan_t* p, const void* yz, void* const
   JPS_REQUIRE(((uintptr_t)yz & 15) == 0, "jps_slab_pack_p2p: yz must be 16-byte aligned");
   {
     ScopedLaunch L(K_MISC, s);
-    const long long nrun = (long long)p->nxl * p->nranks;
-    slab_pack_p2p_kernel<<<(int)std::min<long long>(nrun, (long long)kNumSMs * 8), 256, 0, s>>>(
-        (const float2*)yz, p->peer_dev, p->n, p->nz, p->nxl, p->nyl, p->nranks, p->rank);
+    const long long nrun = (long long)x_count * p->nranks;
+    // a partial range runs next to the 2-D FFT of the following chunk: it is NVLink bound, a
+    // quarter of the SMs' worth of CTAs keeps the links busy without starving cuFFT
+    const long long cap = (x_count == p->nxl) ? (long long)kNumSMs * 8 : (long long)kNumSMs * 2;
+    slab_pack_p2p_kernel<<<(int)std::min<long long>(nrun, cap), 256, 0, s>>>(
+        (const float2*)yz, p->peer_dev, p->n, p->nz, p->nxl, p->nyl, p->nranks, p->rank, x_begin, x_count);
   }
   JPS_CHECK_LAUNCH();
+  return JPS_OK;
+}
+
+extern "C" int jps_slab_pack_p2p(jps_slab_plan_t* p, const void* yz, void* const* peer_recv, void* stream) {
+  JPS_REQUIRE(p != nullptr, "jps_slab_pack_p2p: NULL argument");
+  return jps_slab_pack_p2p_planes(p, yz, peer_recv, 0, p->nxl, stream);
+}
+
+extern "C" int jps_slab_chunk_planes(jps_slab_plan_t* p) { return p ? p->chunk_planes : 0; }
+
+// 2-D transform of the owned planes [x_begin, x_begin + x_count): x_count is the whole slab or
+// jps_slab_chunk_planes() (the two batch sizes a cuFFT plan exists for).  `slab` / `yz` are the
+// BASE pointers of the owned planes / of the output.
+extern "C" int jps_slab_fft_yz_planes(jps_slab_plan_t* p, const float* slab, void* out, int x_begin, int x_count,
+                                      void* stream) {
+  JPS_REQUIRE(p && slab && out, "jps_slab_fft_yz_planes: NULL argument");
+  JPS_REQUIRE(x_begin >= 0 && x_begin + x_count <= p->nxl, "jps_slab_fft_yz_planes: plane range outside the slab");
+  cudaStream_t s = (cudaStream_t)stream;
+  cufftHandle h;
+  if (x_count == p->nxl) h = p->fft_yz;
+  else if (p->yzc_ok && x_count == p->chunk_planes) h = p->fft_yz_chunk;
+  else { set_error("jps_slab_fft_yz_planes: x_count=%d is neither the slab (%d) nor the chunk size (%d)", x_count, p->nxl, p->chunk_planes); return JPS_ERR_INVALID; }
+  JPS_CHECK_CUFFT(cufftSetStream(h, s));
+  ScopedLaunch L(K_FFT_R2C, s);
+  const size_t n = (size_t)p->n;
+  JPS_CHECK_CUFFT(cufftExecR2C(h, (cufftReal*)(slab + (size_t)x_begin * n * n),
+                               (cufftComplex*)((float2*)out + (size_t)x_begin * n * p->nz)));
   return JPS_OK;
 }
 

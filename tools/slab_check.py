@@ -16,6 +16,7 @@ ap.add_argument("--box", type=float, default=2000.0)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--method", default="auto")
 ap.add_argument("--transport", default="auto")
+ap.add_argument("--no-overlap", action="store_true")
 a = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -35,7 +36,8 @@ y = torch.rand(nloc, generator=g, device=dev) * box; y[y >= box] = 0
 z = torch.rand(nloc, generator=g, device=dev) * box; z[z >= box] = 0
 kF = 2 * np.pi / box
 ke = np.arange(kF, np.pi * n / box, kF).astype(np.float32)
-pipe = SlabPipeline(n, box, ke, order=a.order, compat="fixed", method=a.method, transport=a.transport)
+pipe = SlabPipeline(n, box, ke, order=a.order, compat="fixed", method=a.method, transport=a.transport,
+                    overlap=not a.no_overlap)
 
 def sync():
     if world > 1: dist.barrier()
