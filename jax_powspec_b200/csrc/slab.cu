@@ -14,6 +14,7 @@
 #include "fold.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 
 constexpr int kMaxRanks = 64;
@@ -389,7 +390,8 @@ extern "C" int jps_slab_pack_p2p_planes(jps_slab_plan_t* p, const void* yz, void
     const long long nrun = (long long)x_count * p->nranks;
     // a partial range runs next to the 2-D FFT of the following chunk: it is NVLink bound, a
     // quarter of the SMs' worth of CTAs keeps the links busy without starving cuFFT
-    const long long cap = (x_count == p->nxl) ? (long long)kNumSMs * 8 : (long long)kNumSMs * 2;
+    static const int per_sm_env = [] { const char* e = getenv("JPS_PACK_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+    const long long cap = (x_count == p->nxl) ? (long long)kNumSMs * 8 : (long long)kNumSMs * (per_sm_env > 0 ? per_sm_env : 2);
     slab_pack_p2p_kernel<<<(int)std::min<long long>(nrun, cap), 256, 0, s>>>(
         (const float2*)yz, p->peer_dev, p->n, p->nz, p->nxl, p->nyl, p->nranks, p->rank, x_begin, x_count);
   }
