@@ -917,7 +917,11 @@ __global__ void __launch_bounds__(1024) paint_tile_fx_kernel(const float4* __res
   const size_t n2 = (size_t)n * n;
   const bool vec_ok = (n % 4 == 0) && mesh_vec_ok;
   constexpr int NV = TILE / 4;
-  constexpr int ROW_ITEMS = NV + (ORDER - 1);
+  // per row: NV aligned quads + ONE more quad for the halo tail [TILE, L) -- its padding cells
+  // [L, LP) are zero in the tile, and adding +0.0 to the mesh is free, so the tail costs one vector
+  // red instead of order-1 scalar ones (the flush is a third of the kernel on sparse tiles)
+  constexpr int ROW_ITEMS = NV + 1;
+  static_assert(LP == TILE + 4, "tail quad = cells [TILE, TILE + 4)");
   auto cell = [&](int idx) -> float {
     const unsigned l = lo[idx], h = hi[idx];
     if ((l | h) == 0u) return 0.0f;
@@ -933,23 +937,17 @@ __global__ void __launch_bounds__(1024) paint_tile_fx_kernel(const float4* __res
     const int gy = (oy + j) % n;
     float* grow = mesh + (size_t)gx * n2 + (size_t)gy * n;
     const int tbase = (i * L + j) * LP;
-    if (q < NV) {
-      const int k = q * 4;
-      const float vx = cell(tbase + k), vy = cell(tbase + k + 1), vz = cell(tbase + k + 2), vw = cell(tbase + k + 3);
-      if (vx == 0.0f && vy == 0.0f && vz == 0.0f && vw == 0.0f) continue;
-      const int gz = oz + k;
-      if (vec_ok && gz + 3 < n) {
-        red_v4(grow + gz, vx, vy, vz, vw);
-      } else {
-        if (vx != 0.0f) atomicAdd(grow + (gz % n), vx);
-        if (vy != 0.0f) atomicAdd(grow + ((gz + 1) % n), vy);
-        if (vz != 0.0f) atomicAdd(grow + ((gz + 2) % n), vz);
-        if (vw != 0.0f) atomicAdd(grow + ((gz + 3) % n), vw);
-      }
+    const int k = q * 4;
+    const float vx = cell(tbase + k), vy = cell(tbase + k + 1), vz = cell(tbase + k + 2), vw = cell(tbase + k + 3);
+    if (vx == 0.0f && vy == 0.0f && vz == 0.0f && vw == 0.0f) continue;
+    const int gz = (oz + k) % n;
+    if (vec_ok && gz + 3 < n) {
+      red_v4(grow + gz, vx, vy, vz, vw);
     } else {
-      const int k = TILE + (q - NV);
-      const float v = cell(tbase + k);
-      if (v != 0.0f) atomicAdd(grow + ((oz + k) % n), v);
+      if (vx != 0.0f) atomicAdd(grow + gz, vx);
+      if (vy != 0.0f) atomicAdd(grow + ((gz + 1) % n), vy);
+      if (vz != 0.0f) atomicAdd(grow + ((gz + 2) % n), vz);
+      if (vw != 0.0f) atomicAdd(grow + ((gz + 3) % n), vw);
     }
   }
 }

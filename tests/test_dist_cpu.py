@@ -131,3 +131,13 @@ def test_slab_choreography_gloo(tmp_path, world_size):
     port = _free_port()
     mp.spawn(_slab_worker, args=(world_size, port, 16, str(tmp_path)), nprocs=world_size, join=True)
     assert (tmp_path / "ok").exists()
+
+
+def test_bind_near_gpu_is_best_effort_without_nvml():
+    """No GPU / no NVML here: the helper must report that and leave the affinity alone."""
+    import os
+    from jax_powspec_b200.dist import bind_near_gpu
+    before = os.sched_getaffinity(0)
+    info = bind_near_gpu(0)
+    assert info["bound"] is False and "error" in info
+    assert os.sched_getaffinity(0) == before
