@@ -419,7 +419,7 @@ def run_slab_arm(a, wl):
     for t in (y, z):
         t[t >= box] = 0.0
     pipe = SlabPipeline(n, box, k_edges_for(box, n), order=order, compat="fixed", method=a.method, transport=a.transport,
-                        overlap=not a.no_overlap)
+                        overlap=not a.no_overlap, layout=a.layout)
 
     def sync():
         if world > 1:
@@ -486,7 +486,7 @@ def run_slab_arm(a, wl):
                        "parallelism": f"{world} x-slabs, halo ring exchange + all-to-all + allreduce per step"},
             "clocks": clocks, "gpu_launches": int(launches), "stages_ms_max_over_ranks": stages,
             "kernels_ms_rank0": {k: round(ms_ / max(c, 1), 4) for k, (c, ms_) in prof.items()},
-            "transport": pipe.transport,
+            "transport": pipe.transport, "layout": "xfast" if pipe.xfast else "xslow",
             "all_to_all": {"bytes_per_rank": a2a,
                            "achieved_gbs_per_rank": (a2a / stages["all_to_all"] / 1e6) if "all_to_all" in stages else None,
                            "note": "p2p transport: the transfer is inside fft_yz_pack (one fused pack + peer-store kernel)"
@@ -521,6 +521,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-overlap", action="store_true", help="c4: do not overlap the 2-D FFT with the peer transfer")
+    ap.add_argument("--layout", default="auto", choices=["auto", "xfast", "xslow"], help="c4: layout of the transposed shard")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the CPUs nearest its GPU")
     ap.add_argument("--quick", action="store_true", help="stop after the device-resident timed region (ncu runs)")
     ap.add_argument("--quick-kernels", action="store_true", help="stop after the per-kernel pass (sweeps)")

@@ -243,6 +243,11 @@ JPS_API int jps_slab_pack_p2p(jps_slab_plan_t* plan, const void* yz, void* const
  * that the 2-D FFT of one chunk overlaps the NVLink transfer of the previous one (two streams on
  * the host side).  x_count must be the whole slab or jps_slab_chunk_planes() (0 = no chunking). */
 JPS_API int jps_slab_chunk_planes(jps_slab_plan_t* plan);
+/* Layout of the transposed shard (default 0).  0: [n][n/nranks][n/2+1], x slowest -- what jps_slab_pack +
+ * an all-to-all produce; the 1-D FFT along x is strided.  1: [n/nranks][n/2+1][n], x fastest -- produced
+ * by jps_slab_pack_p2p[_planes], which then transposes 32x32 tiles on the way to the peers; the 1-D
+ * FFT is contiguous and jps_slab_powspec_partial runs its lanes along kx.  Set before the first step. */
+JPS_API int jps_slab_set_layout(jps_slab_plan_t* plan, int xfast);
 JPS_API int jps_slab_fft_yz_planes(jps_slab_plan_t* plan, const float* slab, void* yz, int x_begin, int x_count,
                            void* stream);
 JPS_API int jps_slab_pack_p2p_planes(jps_slab_plan_t* plan, const void* yz, void* const* peer_recv, int x_begin,

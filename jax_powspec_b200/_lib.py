@@ -72,6 +72,7 @@ SIGNATURES = {
     "jps_enable_peer_access": (_i, [_i]),
     "jps_slab_pack_p2p": (_i, [_vp, _vp, C.POINTER(_vp), _vp]),
     "jps_slab_chunk_planes": (_i, [_vp]),
+    "jps_slab_set_layout": (_i, [_vp, _i]),
     "jps_slab_fft_yz_planes": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "jps_slab_pack_p2p_planes": (_i, [_vp, _vp, C.POINTER(_vp), _i, _i, _vp]),
     "jps_slab_fft_x": (_i, [_vp, _vp, _vp]),

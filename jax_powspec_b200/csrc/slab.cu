@@ -33,6 +33,12 @@ struct jps_slab_plan {
   cufftHandle fft_yz_chunk = 0;
   bool yzc_ok = false;
   int chunk_planes = 0;
+  // Layout of the transposed shard: 0 = [x][yl][kz] (x slowest; strided 1-D FFT, two passes over the
+  // shard inside cuFFT), 1 = [yl][kz][x] (x fastest; the peer-store kernel transposes 32x32 tiles on
+  // the way, the 1-D FFT is contiguous and the binning kernel runs its lanes along kx).
+  int xfast = 0;
+  cufftHandle fft_x_contig = 0;
+  bool xc_ok = false;
   void* work = nullptr;
   size_t work_bytes = 0;
   jps_plan* tables = nullptr;     // bin tables + accumulators (no 3-D FFT inside)
@@ -61,6 +67,16 @@ static int make_fft_x(int n, int nyl, cufftHandle* h, size_t* work) {
   const long long stride = (long long)nyl * nz;      // distance between consecutive x
   JPS_CHECK_CUFFT(cufftMakePlanMany64(*h, 1, dims, embed, stride, 1, embed, stride, 1, CUFFT_C2C,
                                       stride, work));
+  return JPS_OK;
+}
+
+static int make_fft_x_contig(int n, int nyl, cufftHandle* h, size_t* work) {
+  JPS_CHECK_CUFFT(cufftCreate(h));
+  JPS_CHECK_CUFFT(cufftSetAutoAllocation(*h, 0));
+  const int nz = n / 2 + 1;
+  long long dims[1] = {n};
+  long long embed[1] = {n};
+  JPS_CHECK_CUFFT(cufftMakePlanMany64(*h, 1, dims, embed, 1, n, embed, 1, n, CUFFT_C2C, (long long)nyl * nz, work));
   return JPS_OK;
 }
 
@@ -169,6 +185,139 @@ __global__ void __launch_bounds__(256) pk_bin_ysharded_kernel(SlabPkParams P) {
   }
 }
 
+// Same estimator on the x-fast layout dk[yl][kz][x]: one warp per (local y, kz) row, lanes along
+// a = |kx| (|k| is monotone in a, so the warp-segmented reduction applies unchanged); the partner
+// row element n - a is the same row read backwards.  The window product keeps the reference's
+// order (c(kx) c(ky)) c(kz).
+template <int MODE>
+__global__ void __launch_bounds__(256) pk_bin_xfast_kernel(SlabPkParams P) {
+  extern __shared__ float sacc[];
+  constexpr bool SMEM = (MODE != ACC_GLOBAL);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int nacc = P.nbc * 3;
+  float* my = sacc + (MODE == ACC_WARP ? (size_t)warp * nacc : 0);
+  if (MODE == ACC_WARP) {
+    for (int i = lane; i < nacc; i += 32) my[i] = 0.0f;
+    __syncwarp();
+  } else if (MODE == ACC_BLOCK) {
+    for (int i = threadIdx.x; i < nacc; i += blockDim.x) sacc[i] = 0.0f;
+    __syncthreads();
+  }
+  float scale2 = 1.0f;
+  if (P.normalise) {
+    const double s = (double)P.n * (double)P.n * (double)P.n / (double)P.dc[0];
+    scale2 = (float)(s * s);
+  }
+  const int n = P.n, nz = P.nz, mid = n / 2;
+  const long long items = (long long)P.nyl * nz;
+  for (long long it = (long long)blockIdx.x * nwarps + warp; it < items; it += (long long)gridDim.x * nwarps) {
+    const int yl = (int)(it / nz), kz = (int)(it % nz);
+    const int iy = P.y0 + yl;
+    const int ky = iy > mid ? iy - n : iy;
+    const float2* r = P.dk + (size_t)it * n;
+    const float wy = P.wl[iy], wz = P.wl[kz];
+    const int k2yz = ky * ky + kz * kz;
+    const float kz2 = (float)(kz * kz);
+    constexpr int UNR = 4;
+    for (int ab = 0; ab <= mid; ab += 32 * UNR) {
+      float2 d0[UNR], d1[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int a = ab + 32 * u + lane;
+        const bool in = a <= mid;
+        const bool two = in && a > 0 && 2 * a != n;
+        d0[u] = in ? __ldg(r + a) : make_float2(0.0f, 0.0f);
+        d1[u] = two ? __ldg(r + (n - a)) : make_float2(0.0f, 0.0f);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int a0 = ab + 32 * u;
+        if (a0 > mid) break;                       // warp-uniform
+        const int a = a0 + lane;
+        float v[3] = {0.0f, 0.0f, 0.0f};
+        int cb = -2;
+        if (a <= mid) {
+          const int k2 = k2yz + a * a;
+          cb = __ldg(P.lut + k2);
+          const float c = (P.wl[a] * wy) * wz;
+          float re = d0[u].x * c, im = d0[u].y * c;
+          float sum = re * re + im * im;
+          re = d1[u].x * c; im = d1[u].y * c;
+          sum += re * re + im * im;
+          sum *= scale2;
+          float mu2 = 0.0f;
+          if (k2 > 0) mu2 = kz2 / (float)k2;
+          else if (P.normalise) sum = 0.0f;
+          v[0] = sum;
+          v[1] = sum * (3.0f * mu2 - 1.0f) * 0.5f;
+          v[2] = sum * (35.0f * mu2 * mu2 - 30.0f * mu2 + 3.0f) * 0.125f;
+        }
+        const int prev = __shfl_up_sync(0xffffffffu, cb, 1);
+        const bool head = (lane == 0) || (cb != prev);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        segmented_reduce<3>(v, heads, lane);
+        if (head && cb >= 0) {
+          if (MODE == ACC_WARP) {
+            float* q = my + cb * 3;
+            q[0] += v[0]; q[1] += v[1]; q[2] += v[2];
+          } else if (MODE == ACC_BLOCK) {
+            float* q = my + cb * 3;
+            atomicAdd(q + 0, v[0]); atomicAdd(q + 1, v[1]); atomicAdd(q + 2, v[2]);
+          } else {
+            double* q = P.acc + (size_t)cb * 4;
+            atomicAdd(q + 0, (double)v[0]); atomicAdd(q + 1, (double)v[1]); atomicAdd(q + 2, (double)v[2]);
+          }
+        }
+        if (MODE == ACC_WARP) __syncwarp();
+      }
+    }
+  }
+  if (SMEM) {
+    __syncthreads();
+    const int nsets = (MODE == ACC_WARP) ? nwarps : 1;
+    for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
+      double s = 0.0;
+      for (int w = 0; w < nsets; ++w) s += (double)sacc[(size_t)w * nacc + i];
+      if (s != 0.0) atomicAdd(P.acc + (size_t)(i / 3) * 4 + (i % 3), s);
+    }
+  }
+}
+
+// Peer-store kernel for the x-fast layout: 32 (xl) x 32 (kz) tiles go through shared memory so that
+// the loads are coalesced along kz and the (remote) stores along x:
+//   dst_q[((yl * nz) + kz) * n + rank * nxl + xl] = yz[(xl * n + q * nyl + yl) * nz + kz]
+__global__ void __launch_bounds__(256) slab_pack_p2p_xfast_kernel(const float2* __restrict__ yz,
+                                                                  void* const* __restrict__ peers, int n, int nz,
+                                                                  int nxl, int nyl, int nranks, int rank,
+                                                                  int x_begin, int x_count) {
+  __shared__ float2 tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 8 rows of 32 lanes
+  const int ntx = (x_count + 31) / 32, ntz = (nz + 31) / 32;
+  const long long ntiles = (long long)n * ntx * ntz;                 // over all y = q * nyl + yl
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    // consecutive CTAs take consecutive y -> different yl of the same peer, then the next peer
+    const int y = (int)(t % n);
+    const long long rest = t / n;
+    const int bz = (int)(rest % ntz), bx = (int)(rest / ntz);
+    const int q = y / nyl, yl = y % nyl;
+    const int xl0 = x_begin + bx * 32, kz0 = bz * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int xl = xl0 + ty + 8 * i, kz = kz0 + tx;
+      if (xl < x_begin + x_count && kz < nz) tile[ty + 8 * i][tx] = __ldg(yz + ((size_t)xl * n + y) * nz + kz);
+    }
+    __syncthreads();
+    float2* dst = reinterpret_cast<float2*>(peers[q]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kz = kz0 + ty + 8 * i, xl = xl0 + tx;
+      if (kz < nz && xl < x_begin + x_count)
+        dst[((size_t)yl * nz + kz) * n + (size_t)rank * nxl + xl] = tile[tx][ty + 8 * i];
+    }
+    __syncthreads();
+  }
+}
+
 // Fused pack + all-to-all over NVLink peer memory: block q of this rank's yz-transformed planes is
 // written DIRECTLY into rank q's receive buffer (peer pointers obtained through CUDA IPC on the host
 // side), at the slot of this rank -- no packed send buffer, no NCCL copy kernels.  One launch moves
@@ -245,15 +394,18 @@ extern "C" int jps_slab_plan_workspace_bytes(int n_mesh, int nranks, size_t* byt
   rc = make_fft_x(n_mesh, n_mesh / nranks, &h, &w2);
   cufftDestroy(h);
   if (rc) return rc;
-  size_t w3 = 0;
+  size_t w3 = 0, w4 = 0;
   if (chunk_planes_for(n_mesh / nranks)) {
     rc = make_fft_yz(n_mesh, chunk_planes_for(n_mesh / nranks), &h, &w3);
     cufftDestroy(h);
     if (rc) return rc;
   }
+  rc = make_fft_x_contig(n_mesh, n_mesh / nranks, &h, &w4);
+  cufftDestroy(h);
+  if (rc) return rc;
   const size_t tb = tables_bytes(n_mesh);
   JPS_REQUIRE(tb > 0, "jps_slab_plan_workspace_bytes: table sizing failed");
-  *bytes = align_up(std::max(std::max(w1, w2), w3), 256) + align_up(tb, 256) + 1024 + 512;
+  *bytes = align_up(std::max(std::max(w1, w2), std::max(w3, w4)), 256) + align_up(tb, 256) + 1024 + 512;
   return JPS_OK;
 }
 
@@ -262,6 +414,7 @@ extern "C" int jps_slab_plan_destroy(jps_slab_plan_t* p) {
   if (p->yz_ok) cufftDestroy(p->fft_yz);
   if (p->x_ok) cufftDestroy(p->fft_x);
   if (p->yzc_ok) cufftDestroy(p->fft_yz_chunk);
+  if (p->xc_ok) cufftDestroy(p->fft_x_contig);
   if (p->tables) jps_plan_destroy(p->tables);
   delete p;
   return JPS_OK;
@@ -292,7 +445,11 @@ extern "C" int jps_slab_plan_create(int n_mesh, int nranks, int rank, void* work
     if (rc) { jps_slab_plan_destroy(p); return rc; }
     p->yzc_ok = true;
   }
-  const size_t wb = align_up(std::max(std::max(w1, w2), w3), 256) + 1024;       // + the peer pointer table
+  size_t w4 = 0;
+  rc = make_fft_x_contig(n_mesh, p->nyl, &p->fft_x_contig, &w4);
+  if (rc) { jps_slab_plan_destroy(p); return rc; }
+  p->xc_ok = true;
+  const size_t wb = align_up(std::max(std::max(w1, w2), std::max(w3, w4)), 256) + 1024;       // + the peer pointer table
   const size_t tb = tables_bytes(n_mesh);
   if (workspace_bytes < wb + align_up(tb, 256)) {
     set_error("jps_slab_plan_create: workspace has %zu bytes, %zu needed", workspace_bytes, wb + align_up(tb, 256));
@@ -302,7 +459,8 @@ extern "C" int jps_slab_plan_create(int n_mesh, int nranks, int rank, void* work
   p->work = workspace; p->work_bytes = wb - 1024;
   p->peer_dev = (void**)((char*)workspace + wb - 1024);
   if (cufftSetWorkArea(p->fft_yz, p->work) != CUFFT_SUCCESS || cufftSetWorkArea(p->fft_x, p->work) != CUFFT_SUCCESS ||
-      (p->yzc_ok && cufftSetWorkArea(p->fft_yz_chunk, p->work) != CUFFT_SUCCESS)) {
+      (p->yzc_ok && cufftSetWorkArea(p->fft_yz_chunk, p->work) != CUFFT_SUCCESS) ||
+      cufftSetWorkArea(p->fft_x_contig, p->work) != CUFFT_SUCCESS) {
     set_error("jps_slab_plan_create: cufftSetWorkArea failed");
     jps_slab_plan_destroy(p);
     return JPS_ERR_CUFFT;
@@ -392,8 +550,14 @@ extern "C" int jps_slab_pack_p2p_planes(jps_slab_plan_t* p, const void* yz, void
     // quarter of the SMs' worth of CTAs keeps the links busy without starving cuFFT
     static const int per_sm_env = [] { const char* e = getenv("JPS_PACK_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
     const long long cap = (x_count == p->nxl) ? (long long)kNumSMs * 8 : (long long)kNumSMs * (per_sm_env > 0 ? per_sm_env : 2);
-    slab_pack_p2p_kernel<<<(int)std::min<long long>(nrun, cap), 256, 0, s>>>(
-        (const float2*)yz, p->peer_dev, p->n, p->nz, p->nxl, p->nyl, p->nranks, p->rank, x_begin, x_count);
+    if (p->xfast) {
+      const long long ntiles = (long long)p->n * ((x_count + 31) / 32) * ((p->nz + 31) / 32);
+      slab_pack_p2p_xfast_kernel<<<(int)std::min<long long>(ntiles, cap * 4), 256, 0, s>>>(
+          (const float2*)yz, p->peer_dev, p->n, p->nz, p->nxl, p->nyl, p->nranks, p->rank, x_begin, x_count);
+    } else {
+      slab_pack_p2p_kernel<<<(int)std::min<long long>(nrun, cap), 256, 0, s>>>(
+          (const float2*)yz, p->peer_dev, p->n, p->nz, p->nxl, p->nyl, p->nranks, p->rank, x_begin, x_count);
+    }
   }
   JPS_CHECK_LAUNCH();
   return JPS_OK;
@@ -405,6 +569,13 @@ extern "C" int jps_slab_pack_p2p(jps_slab_plan_t* p, const void* yz, void* const
 }
 
 extern "C" int jps_slab_chunk_planes(jps_slab_plan_t* p) { return p ? p->chunk_planes : 0; }
+
+extern "C" int jps_slab_set_layout(jps_slab_plan_t* p, int xfast) {
+  JPS_REQUIRE(p != nullptr, "jps_slab_set_layout: NULL plan");
+  JPS_REQUIRE(!xfast || p->nranks > 1, "jps_slab_set_layout: the x-fast layout is produced by the peer-store kernel (nranks > 1)");
+  p->xfast = xfast ? 1 : 0;
+  return JPS_OK;
+}
 
 // 2-D transform of the owned planes [x_begin, x_begin + x_count): x_count is the whole slab or
 // jps_slab_chunk_planes() (the two batch sizes a cuFFT plan exists for).  `slab` / `yz` are the
@@ -429,9 +600,10 @@ extern "C" int jps_slab_fft_yz_planes(jps_slab_plan_t* p, const float* slab, voi
 extern "C" int jps_slab_fft_x(jps_slab_plan_t* p, void* data, void* stream) {
   JPS_REQUIRE(p && data, "jps_slab_fft_x: NULL argument");
   cudaStream_t s = (cudaStream_t)stream;
-  JPS_CHECK_CUFFT(cufftSetStream(p->fft_x, s));
+  const cufftHandle h = p->xfast ? p->fft_x_contig : p->fft_x;
+  JPS_CHECK_CUFFT(cufftSetStream(h, s));
   ScopedLaunch L(K_FFT_R2C, s);
-  JPS_CHECK_CUFFT(cufftExecC2C(p->fft_x, (cufftComplex*)data, (cufftComplex*)data, CUFFT_FORWARD));
+  JPS_CHECK_CUFFT(cufftExecC2C(h, (cufftComplex*)data, (cufftComplex*)data, CUFFT_FORWARD));
   return JPS_OK;
 }
 
@@ -460,33 +632,41 @@ extern "C" int jps_slab_powspec_partial(jps_slab_plan_t* p, const void* dk, cons
     P.lut = T->lut; P.wl = tp->wlut + (size_t)(mas_order - 2) * p->n; P.nbc = T->nbc; P.acc = tp->acc;
     P.dc = dc; P.normalise = normalise;
     const int threads = 256, warps = 8;
-    const long long items = (long long)(p->n / 2 + 1) * p->nyl;
+    const long long items = p->xfast ? (long long)p->nyl * p->nz : (long long)(p->n / 2 + 1) * p->nyl;
     const long long want = (items + warps - 1) / warps;
     static bool attr_set = false;
     if (!attr_set) {
-      JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)((size_t)warps * kMaxSmemBins * 3 * sizeof(float))));
-      JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)((size_t)kMaxBlockBins * 3 * sizeof(float))));
+      const int sw = (int)((size_t)warps * kMaxSmemBins * 3 * sizeof(float));
+      const int sb = (int)((size_t)kMaxBlockBins * 3 * sizeof(float));
+      JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw));
+      JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+      JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw));
+      JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
       attr_set = true;
     }
-    int per_sm = 1;
+    using KernelFn = void (*)(SlabPkParams);
+    KernelFn fn;
+    size_t smem = 0;
+    long long cap_per_sm = 0;
     if (T->nbc <= kMaxSmemBins) {
-      const size_t smem = (size_t)warps * T->nbc * 3 * sizeof(float);
-      JPS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_bin_ysharded_kernel<ACC_WARP>, threads, smem));
-      const int blocks = (int)std::min<long long>(want, (long long)kNumSMs * std::max(per_sm, 1));
-      ScopedLaunch L(K_PK_FOLD_BIN, s);
-      pk_bin_ysharded_kernel<ACC_WARP><<<blocks, threads, smem, s>>>(P);
+      fn = p->xfast ? pk_bin_xfast_kernel<ACC_WARP> : pk_bin_ysharded_kernel<ACC_WARP>;
+      smem = (size_t)warps * T->nbc * 3 * sizeof(float);
     } else if (T->nbc <= kMaxBlockBins) {
-      const size_t smem = (size_t)T->nbc * 3 * sizeof(float);
-      JPS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_bin_ysharded_kernel<ACC_BLOCK>, threads, smem));
-      const int blocks = (int)std::min<long long>(want, (long long)kNumSMs * std::max(per_sm, 1));
-      ScopedLaunch L(K_PK_FOLD_BIN, s);
-      pk_bin_ysharded_kernel<ACC_BLOCK><<<blocks, threads, smem, s>>>(P);
+      fn = p->xfast ? pk_bin_xfast_kernel<ACC_BLOCK> : pk_bin_ysharded_kernel<ACC_BLOCK>;
+      smem = (size_t)T->nbc * 3 * sizeof(float);
     } else {
-      const int blocks = (int)std::min<long long>(want, (long long)kNumSMs * 8);
+      fn = p->xfast ? pk_bin_xfast_kernel<ACC_GLOBAL> : pk_bin_ysharded_kernel<ACC_GLOBAL>;
+      cap_per_sm = 8;
+    }
+    if (!cap_per_sm) {
+      int per_sm = 1;
+      JPS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
+      cap_per_sm = std::max(per_sm, 1);
+    }
+    const int blocks = (int)std::min<long long>(want, (long long)kNumSMs * cap_per_sm);
+    {
       ScopedLaunch L(K_PK_FOLD_BIN, s);
-      pk_bin_ysharded_kernel<ACC_GLOBAL><<<blocks, threads, 0, s>>>(P);
+      fn<<<blocks, threads, smem, s>>>(P);
     }
     JPS_CHECK_LAUNCH();
   }

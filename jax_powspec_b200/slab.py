@@ -113,12 +113,16 @@ class SlabPipeline:
     """Per-rank object: owns the slab mesh, the two complex transpose buffers and the slab plan."""
 
     def __init__(self, n_mesh, box_size, k_edges, *, order=2, compat="fixed", method="auto", wrap=True,
-                 shot_noise=0.0, rank=None, world=None, device=None, transport="auto", overlap=True):
+                 shot_noise=0.0, rank=None, world=None, device=None, transport="auto", overlap=True,
+                 layout="auto"):
         """transport: how the transpose crosses GPUs -- "p2p": one fused pack + peer-store kernel
         over NVLink peer memory (receive buffers mapped into every rank with CUDA IPC); "nccl":
         pack kernel + ``all_to_all_single``; "auto": p2p when the mapping succeeds, else nccl.
         overlap (p2p only): split the owned planes into chunks and send chunk c on a side stream
-        while the 2-D FFT of chunk c+1 runs."""
+        while the 2-D FFT of chunk c+1 runs.
+        layout: "xfast" = the peer-store kernel transposes on the way so that the shard arrives as
+        [y_local][kz][x] and the 1-D FFT along x is contiguous (p2p only); "xslow" = [x][y_local][kz]
+        with a strided FFT; "auto" = xfast with p2p, xslow otherwise."""
         r, w = _world()
         self.rank = r if rank is None else rank
         self.world = w if world is None else world
@@ -174,6 +178,28 @@ class SlabPipeline:
         self.overlap = bool(overlap)
         self.chunk_planes = int(lib.jps_slab_chunk_planes(self.handle))
         self._side, self._events = None, None
+        self._local_peers = False
+        self._force_chunks = False                      # tests: take the chunked path on small meshes
+        if layout not in ("auto", "xfast", "xslow"):
+            raise ValueError("layout must be 'auto', 'xfast' or 'xslow'")
+        if layout == "xfast" and self.transport != "p2p" and rank is None:
+            raise _lib.JpsError("SlabPipeline: layout='xfast' needs the p2p transport")
+        self._want_xfast = layout in ("auto", "xfast")
+        self.xfast = False
+        if self.transport == "p2p":
+            self._set_layout(self._want_xfast)
+
+    def _set_layout(self, xfast):
+        check(lib.jps_slab_set_layout(self.handle, int(bool(xfast))), "jps_slab_set_layout")
+        self.xfast = bool(xfast)
+
+    def use_local_peers(self, pipes, xfast=True):
+        """Test harness: all virtual ranks live on THIS device, so their receive buffers are plain
+        device pointers and the fused peer-store kernels (both layouts) run without IPC or NCCL."""
+        self.peer_ptrs = (C.c_void_p * self.world)(*[q.buf_a.data_ptr() for q in pipes])
+        self.transport = "p2p"
+        self._local_peers = True
+        self._set_layout(xfast)
 
     def _map_peer_buffers(self) -> bool:
         """Map every rank's receive buffer (buf_a) into this process through CUDA IPC, opened on THIS
@@ -256,7 +282,7 @@ class SlabPipeline:
         allreduce below makes every rank's stores visible before anyone starts the 1-D FFT."""
         # chunking pays when a chunk is tens of MB or more (2048^3 on 2-8 GPUs: 37.1 -> 24.7 ms for this
         # stage on 2 GPUs); on a 512^3 mesh the extra launches and stream hops cost more than they hide
-        big = self.buf_b.numel() * 8 >= (1 << 30)
+        big = self._force_chunks or self.buf_b.numel() * 8 >= (1 << 30)
         cp = self.chunk_planes if (self.overlap and big) else 0
         if cp and cp < self.nxl:
             # chunked: the transfer of chunk c (side stream) runs under the 2-D FFT of chunk c+1
@@ -277,7 +303,8 @@ class SlabPipeline:
         else:
             check(lib.jps_slab_fft_yz(self.handle, ptr(self.owned()), ptr(self.buf_b), stream_ptr()), "jps_slab_fft_yz")
             check(lib.jps_slab_pack_p2p(self.handle, ptr(self.buf_b), self.peer_ptrs, stream_ptr()), "jps_slab_pack_p2p")
-        dist.all_reduce(self._sync_flag)
+        if not self._local_peers:
+            dist.all_reduce(self._sync_flag)
 
     def stage_fft_x(self):
         check(lib.jps_slab_fft_x(self.handle, ptr(self.buf_a), stream_ptr()), "jps_slab_fft_x")
@@ -317,10 +344,15 @@ class SlabPipeline:
         return self.stage_finalize()
 
 
-def run_virtual_ranks(pipes, catalogs, xmin=0.0):
+def run_virtual_ranks(pipes, catalogs, xmin=0.0, p2p=None):
     """Drive P SlabPipeline objects that live on ONE device through the distributed algorithm,
-    doing the three exchanges with tensor copies (test harness for the per-rank kernels)."""
+    doing the three exchanges with tensor copies (test harness for the per-rank kernels).
+    p2p = "xslow" / "xfast": the transpose goes through the fused peer-store kernel instead (the
+    "peers" are the other pipes' receive buffers on the same device), in that layout."""
     P = len(pipes)
+    if p2p is not None and P > 1:
+        for p in pipes:
+            p.use_local_peers(pipes, xfast=(p2p == "xfast"))
     for p, (x, y, z, w) in zip(pipes, catalogs):
         p.stage_paint(x, y, z, w, xmin, xmin, xmin)
     if P > 1:
@@ -331,7 +363,7 @@ def run_virtual_ranks(pipes, catalogs, xmin=0.0):
             p.mesh[p.gl: p.gl + GHOST_HI] += his[(r - 1) % P]
     for p in pipes:
         p.stage_fft_yz_pack()
-    if P > 1:
+    if P > 1 and pipes[0].transport != "p2p":
         for q, dst in enumerate(pipes):                  # all-to-all: block q of rank r -> rank q, slot r
             for r, src in enumerate(pipes):
                 dst.buf_a[r].copy_(src.buf_b[q])

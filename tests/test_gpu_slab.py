@@ -64,6 +64,33 @@ def test_virtual_ranks_match_single_gpu_and_oracle(jps, world, order, method):
         q.close()
 
 
+@pytest.mark.parametrize("layout", ["xslow", "xfast"])
+@pytest.mark.parametrize("world,n", [(2, 64), (4, 64), (2, 96), (8, 64)])
+def test_fused_peer_store_transpose_both_layouts(jps, world, n, layout):
+    """The p2p transport on one device (peers = the other virtual ranks' receive buffers): the plain
+    peer-store kernel and the transposing one (x-fast shard, contiguous 1-D FFT, kx-lane binning)
+    must reproduce the tensor-copy exchange bit for bit in the counts and to rounding in P."""
+    from jax_powspec_b200.slab import SlabPipeline, run_virtual_ranks
+    box, npart, order = 1000.0, 200_000, 3
+    p = clustered_particles(300 + world, npart, box)
+    kF = 2 * np.pi / box
+    ke = np.arange(kF, np.pi * n / box, kF).astype(F32)
+    cats = _split_by_slab(p, box, n, world)
+    ref_pipes = [SlabPipeline(n, box, ke, order=order, compat="fixed", rank=r, world=world) for r in range(world)]
+    k0, pk0, nm0 = (t.cpu().numpy() for t in run_virtual_ranks(ref_pipes, cats)[0])
+    pipes = [SlabPipeline(n, box, ke, order=order, compat="fixed", rank=r, world=world) for r in range(world)]
+    for q in pipes:
+        q._force_chunks = (n == 96)                      # also the chunked FFT / transfer overlap path
+    outs = run_virtual_ranks(pipes, cats, p2p=layout)
+    assert all(q.transport == "p2p" and q.xfast == (layout == "xfast") for q in pipes)
+    k1, pk1, nm1 = (t.cpu().numpy() for t in outs[0])
+    np.testing.assert_array_equal(nm1, nm0)
+    np.testing.assert_array_equal(k1, k0)
+    assert rel_to_monopole(pk1.astype(np.float64), pk0.astype(np.float64)).max() < 2e-6
+    for q in pipes + ref_pipes:
+        q.close()
+
+
 def test_single_rank_pipeline_call(jps):
     """world_size 1 through SlabPipeline.__call__ (no process group): same code path the multi-GPU run takes."""
     from jax_powspec_b200.slab import SlabPipeline

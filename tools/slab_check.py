@@ -17,6 +17,7 @@ ap.add_argument("--check", action="store_true")
 ap.add_argument("--method", default="auto")
 ap.add_argument("--transport", default="auto")
 ap.add_argument("--no-overlap", action="store_true")
+ap.add_argument("--layout", default="auto")
 a = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -37,7 +38,7 @@ z = torch.rand(nloc, generator=g, device=dev) * box; z[z >= box] = 0
 kF = 2 * np.pi / box
 ke = np.arange(kF, np.pi * n / box, kF).astype(np.float32)
 pipe = SlabPipeline(n, box, ke, order=a.order, compat="fixed", method=a.method, transport=a.transport,
-                    overlap=not a.no_overlap)
+                    overlap=not a.no_overlap, layout=a.layout)
 
 def sync():
     if world > 1: dist.barrier()
@@ -65,7 +66,7 @@ timed("fft_yz_pack", pipe.stage_fft_yz_pack)
 if world > 1 and pipe.transport == "nccl": timed("all_to_all", lambda: transpose_all_to_all(pipe.buf_b, pipe.buf_a))
 timed("fft_x", pipe.stage_fft_x)
 timed("bin", lambda: pipe.stage_partial(True))
-res = {"transport": pipe.transport, "p2p_error": getattr(pipe, "_p2p_error", None), "n_gpus": world, "n_mesh": n, "n_part": npart, "order": a.order, "ms_per_step": ms,
+res = {"transport": pipe.transport, "xfast": pipe.xfast, "p2p_error": getattr(pipe, "_p2p_error", None), "n_gpus": world, "n_mesh": n, "n_part": npart, "order": a.order, "ms_per_step": ms,
        "gparticles_per_s": npart / ms / 1e6, "stages_ms_rank0": stages,
        "a2a_bytes_per_rank": (world - 1) / world ** 2 * 8 * n * n * (n // 2 + 1)}
 if a.check:
