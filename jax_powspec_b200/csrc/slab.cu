@@ -5,7 +5,8 @@
 //   (1) jps_slab_fft_yz : batched 2-D R2C over (y,z) of the owned planes   [nxl][N][N] -> [nxl][N][nz]
 //   (2) jps_slab_pack   : regroup by destination rank                       -> [P][nxl][nyl][nz]
 //       + ONE all-to-all of (P-1)/P^2 * 8 N^2 nz bytes per rank (host side: torch.distributed / NCCL)
-//   (3) jps_slab_fft_x  : strided batched 1-D C2C along x, in place          [N][nyl][nz]
+//   (3) jps_slab_fft_x  : batched 1-D C2C along x, in place: strided on [N][nyl][nz] (x-slow layout) or
+//                         contiguous on [nyl][nz][N] (x-fast layout, jps_slab_set_layout)
 // and the spectrum stays y-sharded: the binning kernel only needs each element's (kx,ky,kz).
 //   (4) jps_slab_powspec_partial : fold +-kx, window, Legendre weights, k-bin sums of the local shard
 //       + allreduce of nb*3 float64 (host side), then jps_slab_powspec_finalize.
