@@ -34,6 +34,21 @@ def clustered_particles(rng, n_part, box, n_blobs=12):
     return p
 
 
+def helpers(corr):
+    """xi_vec_coords / s_edges_conv (src/correlations.py:262-272): 1-d host helpers of the xi path."""
+    out = {}
+    cases = [(256, 2500.0, np.arange(1e-3, 200.0, 2.0)), (64, 1000.0, np.arange(0.0, 150.0, 7.5)),
+             (15, 250.0, np.linspace(0.5, 90.0, 23))]
+    for i, (dims, box, se) in enumerate(cases):
+        se = se.astype(F32)
+        ke = np.asarray(corr.s_edges_conv(dims, box, se))
+        out[f"h{i}_dims"], out[f"h{i}_box"], out[f"h{i}_s_edges"] = dims, box, se
+        out[f"h{i}_s_edges_conv"] = ke
+        out[f"h{i}_xi_vec_coords"] = np.asarray(corr.xi_vec_coords(dims, box, ke))
+    np.savez_compressed(os.path.join(GOLD, "ref_helpers.npz"), **out)
+    print("wrote helpers")
+
+
 def main():
     sys.path.insert(0, os.path.dirname(HERE))
     from oracle import jaxshim
@@ -41,6 +56,9 @@ def main():
     mas, corr = jaxshim.load_reference()
     os.makedirs(GOLD, exist_ok=True)
     warnings.simplefilter("ignore")
+    helpers(corr)
+    if "--helpers-only" in sys.argv:
+        return
 
     # ---------------------------------------------------------------- painting
     rng = np.random.default_rng(20261017)

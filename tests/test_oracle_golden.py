@@ -129,3 +129,17 @@ def test_composites(golden_dir, tag):
         m = np.isfinite(want)
         scale = max(np.abs(want[m]).max(), 1e-30)
         np.testing.assert_allclose(got[m] / scale, want[m] / scale, rtol=0, atol=3e-5)
+
+
+def test_xi_host_helpers_match_the_shim_run_reference(golden_dir):
+    """xi_vec_coords / s_edges_conv (/root/reference/src/correlations.py:262-272): the product's host
+    helpers (pure NumPy float32, importable without a GPU) against the shim-run reference, bit for bit."""
+    from jax_powspec_b200.correlations import s_edges_conv, xi_vec_coords
+    g = np.load(os.path.join(golden_dir, "ref_helpers.npz"))
+    for i in range(3):
+        dims, box, se = int(g[f"h{i}_dims"]), float(g[f"h{i}_box"]), g[f"h{i}_s_edges"]
+        ke = s_edges_conv(dims, box, se)
+        assert ke.dtype == np.float32
+        np.testing.assert_array_equal(ke.view(np.uint32), g[f"h{i}_s_edges_conv"].view(np.uint32))
+        r = np.asarray(xi_vec_coords(dims, box, ke), dtype=np.float32)
+        np.testing.assert_array_equal(r.view(np.uint32), g[f"h{i}_xi_vec_coords"].view(np.uint32))
