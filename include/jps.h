@@ -193,6 +193,17 @@ JPS_API int jps_bispec(jps_plan_t* plan, const float* mesh, int normalise, float
                float k1, float k2, const float* theta, int nbins, int mas_order,
                float* k_all, float* pk, float* B, float* Q, void* stream);
 
+/* BASELINE.json configs[2] ("all triangle bins up to k_max"): the reference's bispec() evaluated for
+ * npairs (k1, k2) pairs -- what a caller's double loop over shell centres does
+ * (tests/bispec.py:53-56 is one such call) -- sharing ONE forward FFT and the cached indicator sums.
+ * Pair p gives exactly what jps_bispec(k1[p], k2[p]) gives.
+ *   k1, k2 : HOST float32 [npairs];  theta : HOST float32 [nbins]
+ * Outputs (device float32, row p = pair p): k_all[npairs][nbins+2], pk[npairs][nbins+2],
+ * B[npairs][nbins], Q[npairs][nbins]. */
+JPS_API int jps_bispec_pairs(jps_plan_t* plan, const float* mesh, int normalise, float box_size,
+                     const float* k1, const float* k2, int npairs, const float* theta, int nbins,
+                     int mas_order, float* k_all, float* pk, float* B, float* Q, void* stream);
+
 /* ------------------------------------------------------------------ composites ------- */
 /* src/correlations.py:640-712: P(k) + xi(s) sharing ONE forward FFT (n_shell_fields >= 1). */
 JPS_API int jps_compute_2pt_correlations(jps_plan_t* plan, const float* mesh, int normalise, float box_size,

@@ -58,6 +58,7 @@ SIGNATURES = {
     "jps_xi": (_i, [_vp, _vp, _i, _f, _fp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "jps_xi_fundamental": (_i, [_vp, _vp, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "jps_bispec": (_i, [_vp, _vp, _i, _f, _f, _f, _fp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "jps_bispec_pairs": (_i, [_vp, _vp, _i, _f, _fp, _fp, _i, _fp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "jps_compute_2pt_correlations": (_i, [_vp, _vp, _i, _f, _fp, _i, _fp, _i, _i,
                                           _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "jps_compute_all_correlations": (_i, [_vp, _vp, _i, _f, _fp, _i, _fp, _i, _f, _f, _fp, _i, _i,

@@ -23,7 +23,7 @@ from .mas import _common_stride, _paint_workspace
 from .plan import ArrayKind, get_plan, ptr, require_cuda, stream_ptr, to_device_f32
 
 __all__ = ["powspec_vec", "powspec_vec_fundamental", "xi_vec", "xi_vec_fundamental", "xi_vec_coords",
-           "s_edges_conv", "bispec", "compute_2pt_correlations", "compute_all_correlations",
+           "s_edges_conv", "bispec", "bispec_pairs", "triangle_pairs", "compute_2pt_correlations", "compute_all_correlations",
            "paint_powspec", "PaintPowspec", "HostPipeline"]
 
 
@@ -176,6 +176,37 @@ def bispec(delta, box_size, k1, k2, theta, *, mas_order=2, normalise=False):
     check(lib.jps_bispec(plan.handle, ptr(mesh), int(bool(normalise)), float(box_size), float(k1), float(k2),
                          _edge_ptr(t), nb, int(mas_order), ptr(k_all), ptr(pk), ptr(B), ptr(Q), stream_ptr()),
           "jps_bispec")
+    th = torch.from_numpy(t).to(device) if kind.on_device else (torch.from_numpy(t) if kind.is_torch else t)
+    return kind.out(k_all), kind.out(pk), th, kind.out(B), kind.out(Q)
+
+
+def triangle_pairs(k_centres):
+    """All (k1 <= k2) pairs of the shell centres, in row-major order of the upper triangle: the
+    "all triangle bins up to k_max" sweep of BASELINE.json configs[2]."""
+    kc = np.asarray(k_centres, dtype=np.float32).ravel()
+    i, j = np.triu_indices(kc.size)
+    return kc[i].copy(), kc[j].copy()
+
+
+def bispec_pairs(delta, box_size, k1, k2, theta, *, mas_order=2, normalise=False):
+    """``bispec`` (/root/reference/src/correlations.py:335) for many (k1, k2) pairs with ONE forward
+    FFT: returns ``(k_all[np, bins+2], Pk[np, bins+2], theta, B[np, bins], Q[np, bins])``; row p is
+    what ``bispec(delta, box_size, k1[p], k2[p], theta)`` returns."""
+    device = require_cuda()
+    kind = ArrayKind(delta)
+    mesh, n = _mesh_arg(delta, device)
+    t = _theta_arg(theta)
+    a = np.ascontiguousarray(np.asarray(k1, dtype=np.float32).ravel())
+    b = np.ascontiguousarray(np.asarray(k2, dtype=np.float32).ravel())
+    if a.size != b.size or a.size < 1:
+        raise ValueError("k1 and k2 must be equally long, non-empty 1-d arrays")
+    nb, npairs = t.size, a.size
+    plan = get_plan(n, device, n_shell_fields=6)
+    k_all, pk = _f32(device, npairs, nb + 2), _f32(device, npairs, nb + 2)
+    B, Q = _f32(device, npairs, nb), _f32(device, npairs, nb)
+    check(lib.jps_bispec_pairs(plan.handle, ptr(mesh), int(bool(normalise)), float(box_size), _edge_ptr(a),
+                               _edge_ptr(b), npairs, _edge_ptr(t), nb, int(mas_order), ptr(k_all), ptr(pk),
+                               ptr(B), ptr(Q), stream_ptr()), "jps_bispec_pairs")
     th = torch.from_numpy(t).to(device) if kind.on_device else (torch.from_numpy(t) if kind.is_torch else t)
     return kind.out(k_all), kind.out(pk), th, kind.out(B), kind.out(Q)
 

@@ -303,6 +303,26 @@ extern "C" int jps_bispec(jps_plan_t* plan, const float* mesh, int normalise, fl
   return bispec_from_dk(plan, normalise, box_size, k1, k2, theta, nbins, mas_order, k_all, pk, B, Q, s);
 }
 
+extern "C" int jps_bispec_pairs(jps_plan_t* plan, const float* mesh, int normalise, float box_size,
+                                const float* k1, const float* k2, int npairs, const float* theta,
+                                int nbins, int mas_order, float* k_all, float* pk, float* B, float* Q,
+                                void* stream) {
+  JPS_REQUIRE(plan && mesh && k1 && k2 && theta && k_all && pk && B && Q, "jps_bispec_pairs: NULL argument");
+  JPS_REQUIRE(mas_order >= 2 && mas_order <= 4, "jps_bispec_pairs: mas_order must be 2, 3 or 4");
+  JPS_REQUIRE(box_size > 0.0f && npairs >= 1, "jps_bispec_pairs: box_size must be > 0 and npairs >= 1");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = forward_fft(plan, mesh, s);                     // ONE rfftn for every pair
+  if (rc) return rc;
+  const size_t nshell = (size_t)nbins + 2;
+  for (int p = 0; p < npairs; ++p) {
+    rc = bispec_from_dk(plan, normalise, box_size, k1[p], k2[p], theta, nbins, mas_order,
+                        k_all + (size_t)p * nshell, pk + (size_t)p * nshell, B + (size_t)p * (size_t)nbins,
+                        Q + (size_t)p * (size_t)nbins, s);
+    if (rc) return rc;
+  }
+  return JPS_OK;
+}
+
 extern "C" int jps_compute_2pt_correlations(jps_plan_t* plan, const float* mesh, int normalise,
                                             float box_size, const float* s_edges, int ns,
                                             const float* k_edges, int nk, int mas_order,

@@ -95,7 +95,7 @@ constexpr int kMaxSmemBins = 576;
 // Up to this many bins one shared accumulator set per CTA is used (shared atomics by segment
 // heads); above it the kernels fall back to global float64 reds.
 constexpr int kMaxBlockBins = 8192;
-constexpr int kIsumSlots = 4096;
+constexpr int kIsumSlots = 32768;   // 256 KB; an all-triangles run at 256^3 (276 pairs x 20 angles) uses ~12k
 enum AccMode { ACC_WARP = 0, ACC_BLOCK = 1, ACC_GLOBAL = 2 };
 constexpr int kMaxUserBins = 1 << 18;
 
