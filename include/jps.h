@@ -345,6 +345,40 @@ JPS_API int jps_text_parse(const char* text, int64_t nbytes, int64_t n_lines, in
                    float* out, int64_t* counters, int64_t* slow_rows, int64_t slow_capacity,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ mock generator --- */
+/* the reference's input pipeline (tests/create_lognormal.py:44-55) on the device.
+ *
+ * jps_mock_gaussian_field replaces gaussian_field(grid, kf, Pkf, Rayleigh_sampling, seed, BoxSize)
+ * (src/gauss_field.py:5-80): delta_k (device complex64 [n][n][n/2+1]) with amplitude
+ * sqrt(P(|k|) (n^2/box)^3) (times sqrt(-log u) when rayleigh != 0), uniform random phase, the
+ * reference's Hermitian pairing on the kz = 0 and kz = n/2 planes and delta_k[0,0,0] = 0.  P(|k|) is
+ * interpolated linearly in the HOST table (kf, pkf)[nk] exactly as the reference's bisection does
+ * (extrapolating along the end segments).  The random stream is Philox4x32-10 with one counter per
+ * mode -- NOT the reference's sequential Mersenne-Twister draws, which no parallel generator can
+ * follow -- so fields agree with the reference in distribution, not draw by draw.
+ *
+ * jps_mock_populate_count / _fill replace populate_field(rho, n_bins, box_size, density, key)
+ * (src/populate_field.py:11-29, NumPy twin src/gauss_field.py:90-110): Poisson counts with mean
+ * rho * (box/n)^3 * density / mean(rho) per cell, every particle at its cell centre plus the
+ * triangular offset sign(r)(1 - sqrt|r|) * bin_size per axis, wrapped into [0, box).  lognormal != 0
+ * samples exp(bias * rho) instead (rho = the Gaussian field in real space; tests/create_lognormal.py:49).
+ * Two calls because the particle number is data dependent: _count leaves the per-cell counts and
+ * offsets in the workspace and the total in *total (device int64); after reading it the caller
+ * allocates pos[total][3] (device float32) and calls _fill with the SAME workspace and seed.
+ * Particles come out grouped by cell in C order. */
+JPS_API size_t jps_mock_field_workspace_bytes(int nk);
+JPS_API int jps_mock_gaussian_field(int n_mesh, const double* kf /* host */, const double* pkf /* host */, int nk,
+                            int rayleigh, unsigned long long seed, float box_size, void* delta_k,
+                            void* workspace, size_t workspace_bytes, void* stream);
+JPS_API size_t jps_mock_populate_workspace_bytes(int n_mesh);
+/* byte offset, inside the populate workspace, of the per-cell counts (uint32 [n][n][n]) _count leaves there */
+JPS_API size_t jps_mock_populate_counts_offset(int n_mesh);
+JPS_API int jps_mock_populate_count(const float* rho, int n_mesh, float box_size, float density, int lognormal,
+                            float bias, unsigned long long seed, void* workspace, size_t workspace_bytes,
+                            int64_t* total, void* stream);
+JPS_API int jps_mock_populate_fill(int n_mesh, float box_size, unsigned long long seed, const void* workspace,
+                           size_t workspace_bytes, int64_t n_out, float* pos, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,13 @@ SIGNATURES = {
     "jps_text_count_lines": (_i, [_vp, _i64, _vp, _vp, _sz, _vp]),
     "jps_text_parse": (_i, [_vp, _i64, _i64, _i, _i, C.POINTER(_i), _i, _i, _f, _f, _vp, _vp, _vp, _i64,
                             _vp, _sz, _vp]),
+    "jps_mock_field_workspace_bytes": (_sz, [_i]),
+    "jps_mock_gaussian_field": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), _i, _i, C.c_ulonglong, _f,
+                                     _vp, _vp, _sz, _vp]),
+    "jps_mock_populate_workspace_bytes": (_sz, [_i]),
+    "jps_mock_populate_counts_offset": (_sz, [_i]),
+    "jps_mock_populate_count": (_i, [_vp, _i, _f, _f, _i, _f, C.c_ulonglong, _vp, _sz, _vp, _vp]),
+    "jps_mock_populate_fill": (_i, [_i, _f, C.c_ulonglong, _vp, _sz, _i64, _vp, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -76,6 +76,8 @@ enum KernelId {
   K_TEXT_INDEX,
   K_TEXT_PARSE,
   K_TEXT_COMPACT,
+  K_MOCK_FIELD,
+  K_MOCK_POPULATE,
   K_NUM
 };
 

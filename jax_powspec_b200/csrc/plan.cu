@@ -18,7 +18,8 @@ void set_error(const char* fmt, ...) {
 static const char* kKernelNames[K_NUM] = {
     "paint_atomic", "bucket_count", "bucket_scan", "bucket_scatter", "bucket_fine", "paint_tile", "pk_fold_bin",
     "pk_count_modes", "pk_finalize", "cufft_r2c", "cufft_c2r", "memset", "shell_filter",
-    "triple_reduce", "xi_bin", "misc", "text_index", "text_parse", "text_compact"};
+    "triple_reduce", "xi_bin", "misc", "text_index", "text_parse", "text_compact",
+    "mock_field", "mock_populate"};
 
 struct Pending { int id; cudaEvent_t e0, e1; };
 static bool g_prof_on = false;
