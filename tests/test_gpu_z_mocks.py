@@ -151,7 +151,7 @@ def test_lognormal_mock_end_to_end(mocks):
     a = (mesh / mesh.mean() - 1).flatten()
     b = (rho / rho.mean() - 1).flatten()
     r = float((a * b).mean() / (a.std() * b.std()))
-    assert r > 0.3, r
+    assert r > 0.35, r                                                   # 0.437 with the host build of the same generator
     # power on large scales: b^2 P_lin within sample variance (fixed amplitudes, a dozen modes per bin)
     kF = 2 * np.pi / box
     edges = np.arange(1.5, 8.5, 1.0) * kF
@@ -159,4 +159,4 @@ def test_lognormal_mock_end_to_end(mocks):
     pk0 = pk[:, 0].cpu().numpy() - 1.0 / density
     lin = np.interp(k3d.cpu().numpy(), kf, pkf)
     ratio = pk0 / lin
-    assert 0.5 < np.median(ratio) < 3.0, ratio
+    assert 0.8 < np.median(ratio) < 1.6, ratio                           # b^2 = 1.21; host build: 1.06 .. 1.21
