@@ -165,16 +165,33 @@ JPS_HD double cell_density(float v, int lognormal, double bias) {
 // ------------------------------------------------------------------ one particle
 // centre + triangular in-cell offset, wrapped into [0, box): populate_field.py:4-9,20,27-29, float32
 // as jnp computes it.  `cell` = C-order flat index, `j` = running index of the particle in the cell.
+// separately rounded float32 product / sum (jnp evaluates op by op; nvcc would otherwise contract
+// a * b + c into one FMA and the device would differ from the host build in the last bit)
+JPS_HD float mulf(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+JPS_HD float addf(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+
 JPS_HD float tri_offset(uint32_t bits, float bin_size) {
-  const float r = 2.0f * uniform_f32(bits) - 1.0f;
+  const float r = addf(mulf(2.0f, uniform_f32(bits)), -1.0f);
   const float a = fabsf(r);
-  const float m = 1.0f - sqrtf(a);
+  const float m = addf(1.0f, -sqrtf(a));
   const float sg = (r > 0.0f) ? 1.0f : (r < 0.0f ? -1.0f : 0.0f);
-  return (sg * m) * bin_size;
+  return mulf(mulf(sg, m), bin_size);
 }
 
 JPS_HD float wrap_coord(float c, float box) {
-  float v = fmodf(c + box, box);
+  float v = fmodf(addf(c, box), box);
   if (v < 0.0f) v += box;                         // jnp's % is a floor-mod
   if (v >= box) v = 0.0f;
   return v;
@@ -183,10 +200,10 @@ JPS_HD float wrap_coord(float c, float box) {
 JPS_HD void particle_position(int ix, int iy, int iz, uint64_t particle, uint64_t seed, float bin_size,
                               float box, float& x, float& y, float& z) {
   const U4 r = draw(seed, STREAM_OFFSET, particle, 0u);
-  const float half = 0.5f * bin_size;
-  x = wrap_coord(((float)ix * bin_size + half) + tri_offset(r.x, bin_size), box);
-  y = wrap_coord(((float)iy * bin_size + half) + tri_offset(r.y, bin_size), box);
-  z = wrap_coord(((float)iz * bin_size + half) + tri_offset(r.z, bin_size), box);
+  const float half = mulf(0.5f, bin_size);
+  x = wrap_coord(addf(addf(mulf((float)ix, bin_size), half), tri_offset(r.x, bin_size)), box);
+  y = wrap_coord(addf(addf(mulf((float)iy, bin_size), half), tri_offset(r.y, bin_size)), box);
+  z = wrap_coord(addf(addf(mulf((float)iz, bin_size), half), tri_offset(r.z, bin_size)), box);
 }
 
 }  // namespace mock
