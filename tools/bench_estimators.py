@@ -68,6 +68,32 @@ res["C3"] = {"bispec_gpu_ms": ms_b, "xi_gpu_ms": ms_x, "compute_all_gpu_ms": ms_
              "speedup_vs_cpu_port": t_cpu * 1e3 / ms_b, "c2r_ffts_per_call": 44,
              "max_rel_B": float(np.max(np.abs(B - B_ref)) / np.max(np.abs(B_ref)))}
 
+# ---------------- C3, the whole sweep: all (k1 <= k2) pairs of shells centred at 2 kF j up to 0.3 h/Mpc
+if "--no-sweep" not in sys.argv:
+    kF = 2 * np.pi / box
+    centres = np.arange(2 * kF, 0.3, 2 * kF).astype(F32)
+    k1s, k2s = jps.triangle_pairs(centres)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    sweep = jps.bispec_pairs(delta, box, k1s, k2s, theta)          # cold: indicator sums of every shell / triple computed
+    torch.cuda.synchronize(); t_cold = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    sweep = jps.bispec_pairs(delta, box, k1s, k2s, theta)          # warm: indicator sums cached on the device
+    torch.cuda.synchronize(); t_warm = time.perf_counter() - t0
+    res["C3_all_triangles"] = {"pairs": int(k1s.size), "angles": int(theta.size), "triangle_bins": int(k1s.size * theta.size),
+                               "cold_s": t_cold, "warm_s": t_warm,
+                               "finite_B": int(np.isfinite(sweep[3].cpu().numpy()).sum())}
+
+# ---------------- mock generator (row f-3): the reference's recipe at its own size (tests/create_lognormal.py:13-19)
+from jax_powspec_b200 import mocks
+kf_t = np.linspace(1e-4, 10, 4056)
+pk_t = 2.0e4 * (kf_t / 0.02) / (1.0 + (kf_t / 0.02) ** 2) ** 1.7
+ms_field, dk_m = gpu_time(lambda: mocks.gaussian_field(256, kf_t, pk_t, 0, 100, 1000.0), reps=5, warm=2)
+g_m = torch.fft.irfftn(dk_m, s=(256, 256, 256)).contiguous()
+ms_pop, pos_m = gpu_time(lambda: mocks.populate_field(g_m, 256, 1000.0, 3.5e-3, 101, lognormal_bias=1.1), reps=5, warm=2)
+ms_mock, pos_m = gpu_time(lambda: mocks.lognormal_mock(256, kf_t, pk_t, 1.1, 3.5e-3, 100, 1000.0), reps=5, warm=2)
+res["mock_256"] = {"gaussian_field_ms": ms_field, "populate_ms": ms_pop, "lognormal_mock_ms": ms_mock,
+                   "particles": int(pos_m.shape[0])}
+
 # ---------------- C5 (one GPU): realisations/s
 n, box, npart = 512, 1000.0, 10_000_000
 ke = np.arange(0.003, np.pi * n / box, 0.0025).astype(F32)
@@ -83,4 +109,16 @@ torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 res["C5"] = {"realisations": 32, "seconds": dt, "realisations_per_s": 32 / dt, "cov_shape": list(cov.shape),
              "note": "paint+FFT+multipoles only (4 pre-generated catalogues cycled); mock generation excluded"}
+# the same with every realisation GENERATED on the device first (lognormal_mock at 256^3, ~1e7 particles)
+dens = npart / box ** 3
+def measure_gen(seed):
+    p = mocks.lognormal_mock(256, kf_t, pk_t, 1.1, dens, seed, box)
+    m = min(p.shape[0], npart)
+    return pipe(p[:m, 0], p[:m, 1], p[:m, 2])[1].clone()
+measure_gen(0); torch.cuda.synchronize()
+t0 = time.perf_counter()
+rows, mean, cov = jd.covariance_batch(list(range(16)), measure_gen)
+torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+res["C5_with_mock_generation"] = {"realisations": 16, "seconds": dt, "realisations_per_s": 16 / dt}
 print(json.dumps(res))
