@@ -52,6 +52,18 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 constexpr int kNumSMs = 148;  // B200
 
+// cudaFuncSetAttribute applies to the CURRENT device only.  The product runs one process per GPU, but
+// nothing in the C ABI forbids one process driving several: keep one "already set" flag per device.
+struct PerDeviceFlag {
+  bool done[64] = {};
+  static int dev() {
+    int d = 0;
+    return (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) ? d : 0;
+  }
+  bool get() const { return done[dev()]; }
+  void set() { done[dev()] = true; }
+};
+
 // ---------------------------------------------------------------- launch accounting
 // Every kernel launch of the library goes through a ScopedLaunch: it counts launches (always)
 // and, when profiling is enabled with jps_profile_enable(1), brackets the launch with CUDA

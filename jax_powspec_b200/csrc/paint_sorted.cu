@@ -1041,12 +1041,12 @@ static int run_bucket(const PaintParams& p, const TileGeom& g, const SortedLayou
   }
   if (g.rep == 1 && g.ntiles <= kSmemCountMaxTiles) {
     const int smem = (g.ntiles + 1) * (int)sizeof(unsigned);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceFlag attr_set;
+    if (!attr_set.get()) {
       JPS_CHECK_CUDA(cudaFuncSetAttribute(bucket_count_smem_kernel<ORDER, REFCIC>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (kSmemCountMaxTiles + 1) * (int)sizeof(unsigned)));
-      attr_set = true;
+      attr_set.set();
     }
     const int64_t w1 = (p.n_part + 1024 * BUCKET_UNROLL - 1) / (1024 * BUCKET_UNROLL);
     ScopedLaunch T(K_BUCKET_COUNT, s);
@@ -1105,12 +1105,12 @@ static int run_bucket_two_level(const PaintParams& p, const TileGeom& g, const S
     }
     {
       const int smem = (g.ntiles + 1) * (int)sizeof(unsigned);
-      static bool attr_set = false;
-      if (!attr_set) {
+      static PerDeviceFlag attr_set;
+      if (!attr_set.get()) {
         JPS_CHECK_CUDA(cudaFuncSetAttribute(bucket_count_smem_kernel<ORDER, REFCIC>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (kSmemCountMaxTiles + 1) * (int)sizeof(unsigned)));
-        attr_set = true;
+        attr_set.set();
       }
       const int64_t w1 = (p.n_part + 1024 * BUCKET_UNROLL - 1) / (1024 * BUCKET_UNROLL);
       ScopedLaunch T(K_BUCKET_COUNT, s);
@@ -1147,11 +1147,11 @@ static int run_bucket_two_level(const PaintParams& p, const TileGeom& g, const S
   }
   {
     const size_t smem = (size_t)COARSE_CHUNK * (sizeof(float4) + 2) + (size_t)ngroups * 8 + 33 * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceFlag attr_set;
+    if (!attr_set.get()) {
       JPS_CHECK_CUDA(cudaFuncSetAttribute(coarse_scatter_kernel<ORDER, REFCIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)((size_t)COARSE_CHUNK * (sizeof(float4) + 2) + (size_t)kMaxGroups * 8 + 33 * 4)));
-      attr_set = true;
+      attr_set.set();
     }
     const int64_t nchunks = (p.n_part + COARSE_CHUNK - 1) / COARSE_CHUNK;
     ScopedLaunch T(K_BUCKET_SCATTER, s);
@@ -1186,11 +1186,11 @@ static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayo
                                                               mesh_vec_ok, p.mesh);
     } else {
       constexpr int smem = 2 * TileDims<ORDER>::CELLS * (int)sizeof(unsigned);
-      static bool attr_set = false;
-      if (!attr_set) {
+      static PerDeviceFlag attr_set;
+      if (!attr_set.get()) {
         JPS_CHECK_CUDA(cudaFuncSetAttribute(paint_tile_fx_kernel<ORDER, REFCIC>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+        attr_set.set();
       }
       // CTA size (measured, C2 / a C4 rank): 256 threads 1.94 ms, 384 1.56, 512 1.61, 768 1.89 for TSC;
       // PCS on sparse tiles 9.2 (256), 6.67 (384), 6.41 (512) ms; CIC flat between 320 and 512.

@@ -1,7 +1,9 @@
 // Plan object: cuFFT plans + partition of the caller's workspace.
 #include "common.cuh"
 
+#include <atomic>
 #include <cmath>
+#include <mutex>
 
 namespace jps {
 
@@ -21,37 +23,52 @@ static const char* kKernelNames[K_NUM] = {
     "triple_reduce", "xi_bin", "misc", "text_index", "text_parse", "text_compact",
     "mock_field", "mock_populate"};
 
+// Distinct plans may be driven from distinct host threads (include/jps.h), so the process-wide
+// accounting is atomic counters + one mutex around the event lists.
 struct Pending { int id; cudaEvent_t e0, e1; };
-static bool g_prof_on = false;
-static unsigned long long g_launches[K_NUM];
-static double g_ms[K_NUM];
-static std::vector<Pending> g_pending;
-static std::vector<cudaEvent_t> g_pool;
+static std::atomic<bool> g_prof_on{false};
+static std::atomic<unsigned long long> g_launches[K_NUM];
+static double g_ms[K_NUM];                        // guarded by g_prof_mutex
+static std::vector<Pending> g_pending;            // guarded by g_prof_mutex
+static std::vector<cudaEvent_t> g_pool;           // guarded by g_prof_mutex
+static std::mutex g_prof_mutex;
 
 static cudaEvent_t get_event() {
-  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  }
   cudaEvent_t e;
   cudaEventCreate(&e);
   return e;
 }
 
-ScopedLaunch::ScopedLaunch(int id_, cudaStream_t s_) : id(id_), s(s_), e0(nullptr), e1(nullptr), timed(g_prof_on) {
-  ++g_launches[id];
+ScopedLaunch::ScopedLaunch(int id_, cudaStream_t s_) : id(id_), s(s_), e0(nullptr), e1(nullptr), timed(g_prof_on.load()) {
+  g_launches[id].fetch_add(1, std::memory_order_relaxed);
   if (timed) { e0 = get_event(); e1 = get_event(); cudaEventRecord(e0, s); }
 }
 
 ScopedLaunch::~ScopedLaunch() {
-  if (timed) { cudaEventRecord(e1, s); g_pending.push_back({id, e0, e1}); }
+  if (timed) {
+    cudaEventRecord(e1, s);
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    g_pending.push_back({id, e0, e1});
+  }
 }
 
 static void drain_pending() {
-  for (auto& p : g_pending) {
+  std::vector<Pending> todo;
+  {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    todo.swap(g_pending);
+  }
+  for (auto& p : todo) {                          // synchronise outside the lock
     float ms = 0.f;
-    if (cudaEventSynchronize(p.e1) == cudaSuccess && cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess)
-      g_ms[p.id] += ms;
+    const bool ok = cudaEventSynchronize(p.e1) == cudaSuccess && cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess;
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    if (ok) g_ms[p.id] += ms;
     g_pool.push_back(p.e0); g_pool.push_back(p.e1);
   }
-  g_pending.clear();
 }
 
 // (1/sinc(pi k/N))^p per axis in float32, operation by operation as
@@ -156,13 +173,14 @@ using namespace jps;
 
 extern "C" int jps_profile_enable(int on) {
   drain_pending();
-  g_prof_on = on != 0;
+  g_prof_on.store(on != 0);
   return JPS_OK;
 }
 
 extern "C" int jps_profile_reset(void) {
   drain_pending();
-  for (int i = 0; i < K_NUM; ++i) { g_launches[i] = 0; g_ms[i] = 0.0; }
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  for (int i = 0; i < K_NUM; ++i) { g_launches[i].store(0); g_ms[i] = 0.0; }
   return JPS_OK;
 }
 
@@ -172,8 +190,8 @@ extern "C" int jps_profile_get(int id, const char** name, unsigned long long* la
   JPS_REQUIRE(id >= 0 && id < K_NUM, "jps_profile_get: id out of range");
   drain_pending();                       // synchronises on the recorded events
   if (name) *name = kKernelNames[id];
-  if (launches) *launches = g_launches[id];
-  if (ms) *ms = g_ms[id];
+  if (launches) *launches = g_launches[id].load();
+  if (ms) { std::lock_guard<std::mutex> lock(g_prof_mutex); *ms = g_ms[id]; }
   return JPS_OK;
 }
 

@@ -369,13 +369,13 @@ static int bin_from_dk(jps_plan* plan, const BinTable& T, int normalise, int mas
   P.nbc = nbc; P.acc = plan->acc; P.normalise = normalise; P.npairs = npairs_for(plan->n);
   const int threads = 256, warps = threads / 32;
   const int want = (P.npairs + warps - 1) / warps;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  if (!attr_set.get()) {
     JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_fold_bin_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)((size_t)warps * kMaxSmemBins * 3 * sizeof(float))));
     JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_fold_bin_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)((size_t)kMaxBlockBins * 3 * sizeof(float))));
-    attr_set = true;
+    attr_set.set();
   }
   int per_sm = 1;
   if (nbc <= kMaxSmemBins) {

@@ -635,15 +635,15 @@ extern "C" int jps_slab_powspec_partial(jps_slab_plan_t* p, const void* dk, cons
     const int threads = 256, warps = 8;
     const long long items = p->xfast ? (long long)p->nyl * p->nz : (long long)(p->n / 2 + 1) * p->nyl;
     const long long want = (items + warps - 1) / warps;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceFlag attr_set;
+    if (!attr_set.get()) {
       const int sw = (int)((size_t)warps * kMaxSmemBins * 3 * sizeof(float));
       const int sb = (int)((size_t)kMaxBlockBins * 3 * sizeof(float));
       JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw));
       JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
       JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw));
       JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-      attr_set = true;
+      attr_set.set();
     }
     using KernelFn = void (*)(SlabPkParams);
     KernelFn fn;

@@ -188,10 +188,10 @@ int xi_from_dk(jps_plan* plan, const BinTable& T, int normalise, int mas_order, 
   const size_t smem = (size_t)T.nbc * 3 * sizeof(float);
   const long long want = ((long long)n * n + 7) / 8;
   if (smem <= 160 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceFlag attr_set;
+    if (!attr_set.get()) {
       JPS_CHECK_CUDA(cudaFuncSetAttribute(xi_bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      attr_set = true;
+      attr_set.set();
     }
     int per_sm = 1;
     JPS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xi_bin_kernel<true>, 256, smem));
