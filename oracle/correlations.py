@@ -135,19 +135,51 @@ def _binned_multipoles(v, kf, mu2, kedges, precision):
     return s0, s2, s4, counts
 
 
-def powspec(delta, box_size, k_edges, *, mas_order=2, precision="f64", shot_noise=0.0):
+def interlace_phase(n, dtype=np.complex128):
+    """exp(-i pi (kx + ky + kz) / N) on the half-space array, frequencies as k_index() (index N/2 is +N/2,
+    Q15).  No reference counterpart (the reference has no interlacing): second mesh painted on a grid
+    displaced by +half a cell, i.e. with xmin + cell/2 (Sefusatti et al. 2016, eq. 17-18)."""
+    ki = k_index(n).astype(np.float64)
+    ph = np.exp(-1j * np.pi * ki / n)
+    mid = n // 2
+    return (ph[:, None, None] * ph[None, :, None] * ph[None, None, : mid + 1]).astype(dtype)
+
+
+def powspec(delta, box_size, k_edges, *, mas_order=2, precision="f64", shot_noise=0.0, delta2=None,
+            mode_weighting="half"):
     """P0, P2, P4 in user k-bins.  correlations.py:7-56.
     Returns (k3D f32[nb], Pk3D [nb,3], Nmodes int64[nb]).  ``shot_noise`` (absent in the
-    reference, Q12) is subtracted from the monopole only."""
+    reference, Q12) is subtracted from the monopole only.
+
+    Extensions without a reference counterpart (parity unpinned):
+    ``delta2`` = the same particles painted on the grid displaced by half a cell -> interlaced
+    spectrum (dk1 + dk2 * phase)/2, odd aliases cancel; ``mode_weighting='hermitian'`` counts every
+    stored mode with 0 < kz < N/2 twice (the full-space average the reference's half-space sum
+    only approximates, Q7)."""
     delta = np.asarray(delta)
     n = delta.shape[0]
     dt = np.float64 if precision == "f64" else F32
     kedges = grid_edges(k_edges, box_size)
     kx, ky, kz, k2 = _half_grids(n)
     dk = deconvolved_dk(delta, mas_order, precision)
+    if delta2 is not None:
+        dk2 = deconvolved_dk(np.asarray(delta2), mas_order, precision)
+        ct = np.complex128 if precision == "f64" else np.complex64
+        dk = ((dk + dk2 * interlace_phase(n, ct)) * dt(0.5)).astype(ct)
     d2 = (dk.real * dk.real + dk.imag * dk.imag)
-    kf, mu2 = _mu2_half(n, k2, np.broadcast_to(kz, k2.shape), precision)
-    s0, s2, s4, counts = _binned_multipoles(d2, kf, mu2, kedges, precision)
+    kzb = np.broadcast_to(kz, k2.shape)
+    kf, mu2 = _mu2_half(n, k2, kzb, precision)
+    if mode_weighting == "hermitian":
+        twice = (kzb > 0) & (2 * kzb != n)
+        mult = np.where(twice, 2, 1)
+        s0, s2, s4, counts = _binned_multipoles(d2 * mult.astype(d2.dtype), kf, mu2, kedges, precision)
+        bins = bin_index_from_k(kf.ravel(), kedges)
+        ok = bins >= 0
+        counts = np.bincount(bins[ok], weights=mult.ravel()[ok], minlength=len(kedges) - 1)[: len(kedges) - 1].astype(np.int64)
+    elif mode_weighting == "half":
+        s0, s2, s4, counts = _binned_multipoles(d2, kf, mu2, kedges, precision)
+    else:
+        raise ValueError("mode_weighting must be 'half' or 'hermitian'")
     vol = (dt(box_size) / dt(n * n)) ** 3 if precision == "f64" else (F32(box_size) / F32(n * n)) ** 3
     nm = counts.astype(dt)
     with np.errstate(invalid="ignore", divide="ignore"):

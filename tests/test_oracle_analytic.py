@@ -197,3 +197,77 @@ def test_bispectrum_indicator_sum_identity():
         ind = np.fft.irfftn(msk.astype(np.complex128), s=(n, n, n), axes=(0, 1, 2))
         weight = np.where((kz == 0) | (kz == n // 2), 1, 2) * np.ones_like(k2)
         assert (ind * ind).sum() == pytest.approx((msk * weight).sum() / n ** 3, rel=1e-10)
+
+
+# ------------------------------------------------------------------ extensions (no reference counterpart)
+def test_hermitian_weighting_is_the_full_space_average():
+    rng = np.random.default_rng(5)
+    n, box = 12, 240.0
+    delta = rng.normal(size=(n, n, n)).astype(F32)
+    kF = 2 * np.pi / box
+    edges = (np.arange(1, 7) * kF).astype(F32)
+    _, pk, counts = oc.powspec(delta, box, edges, precision="f64", mode_weighting="hermitian")
+    full = np.fft.fftn(delta.astype(np.float64))
+    freq = np.array([i - n if i > n // 2 else i for i in range(n)])
+    win = 1.0 / np.sinc(freq / n) ** 2
+    p2 = np.abs(full * win[:, None, None] * win[None, :, None] * win[None, None, :]) ** 2
+    kx, ky, kz = np.meshgrid(freq, freq, freq, indexing="ij")
+    kmag = np.sqrt((kx * kx + ky * ky + kz * kz).astype(F32))
+    ge = (edges / F32(kF)).astype(F32)
+    # the full n^3 grid holds every mode of the half space once plus the mirror images of the interior planes;
+    # index N/2 along z is its own mirror, so the full grid IS the Hermitian-weighted half space
+    for b in range(len(edges) - 1):
+        last = b == len(edges) - 2
+        sel = (kmag >= ge[b]) & ((kmag <= ge[b + 1]) if last else (kmag < ge[b + 1]))
+        assert sel.sum() == counts[b]
+        assert pk[b, 0] == pytest.approx(p2[sel].mean() * (box / n ** 2) ** 3, rel=1e-10)
+    half_counts = oc.powspec(delta, box, edges, precision="f64")[2]
+    assert (counts > half_counts).all() and (counts <= 2 * half_counts).all()
+
+
+def test_interlacing_leaves_a_band_limited_field_alone():
+    """Sampled (not painted) plane waves on the two grids: no aliases to cancel, so the interlaced spectrum
+    equals the plain one -- this fixes the SIGN of the phase factor and of the half-cell displacement."""
+    n, box = 16, 100.0
+    g = np.arange(n, dtype=np.float64)
+    gx, gy, gz = g[:, None, None], g[None, :, None], g[None, None, :]
+    def field(shift):
+        x, y, z = gx + shift, gy + shift, gz + shift
+        return (0.3 * np.cos(2 * np.pi * (2 * x - 3 * y + 1 * z) / n + 0.4)
+                + 0.2 * np.sin(2 * np.pi * (5 * x + 0 * y + 4 * z) / n)).astype(np.float64)
+    d1, d2 = field(0.0), field(0.5)                                       # grid 2 displaced by +half a cell
+    kF = 2 * np.pi / box
+    edges = (np.arange(1, 9) * kF).astype(F32)
+    _, plain, _ = oc.powspec(d1, box, edges, precision="f64")
+    _, inter, _ = oc.powspec(d1, box, edges, precision="f64", delta2=d2)
+    np.testing.assert_allclose(inter, plain, rtol=1e-9, atol=1e-9 * np.abs(plain).max())
+    # displaced the other way the odd-sum modes flip sign instead: power is NOT preserved
+    _, wrong, _ = oc.powspec(d1, box, edges, precision="f64", delta2=field(-0.5))
+    assert np.abs(wrong - plain).max() > 0.1 * np.abs(plain).max()
+
+
+@pytest.mark.parametrize("order", [2, 3])
+def test_interlacing_suppresses_aliasing(order):
+    """Poisson particles: the painted + deconvolved spectrum rises above the shot-noise level towards
+    Nyquist (aliased images); interlacing removes the odd images and brings it back down."""
+    rng = np.random.default_rng(17)
+    n, box, npart = 24, 240.0, 40_000
+    p = (rng.random((npart, 3)) * box).astype(F32)
+    cell = F32(box / n)
+    half = F32(0.5) * cell
+    def paint(xmin):
+        rho = om.paint(np.zeros((n, n, n)), p[:, 0], p[:, 1], p[:, 2], None, xmin, xmin, xmin, box, n, True,
+                       order=order, compat="fixed", precision="f64")
+        return rho / rho.mean() - 1.0
+    d1, d2 = paint(F32(0.0)), paint(half)
+    kF = 2 * np.pi / box
+    edges = (np.arange(1, 16) * kF).astype(F32)                           # through Nyquist (12 kF) into the corners
+    shot = box ** 3 / npart
+    _, plain, _ = oc.powspec(d1, box, edges, mas_order=order, precision="f64")
+    _, inter, _ = oc.powspec(d1, box, edges, mas_order=order, precision="f64", delta2=d2)
+    at_nyq = slice(10, 13)                                                # the bins around k_Nyquist
+    excess_plain = np.abs(plain[at_nyq, 0] / shot - 1).mean()             # CIC 0.41, TSC 0.25
+    excess_inter = np.abs(inter[at_nyq, 0] / shot - 1).mean()             # CIC 0.02, TSC 0.02
+    assert excess_plain > 0.15 and excess_inter < 0.25 * excess_plain, (excess_plain, excess_inter)
+    # large scales are untouched
+    np.testing.assert_allclose(inter[:5, 0], plain[:5, 0], rtol=2e-2)
