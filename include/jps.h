@@ -160,6 +160,18 @@ JPS_API int jps_powspec(jps_plan_t* plan, const float* mesh, int normalise, floa
                 float* k3d, float* pk3d, float* nmodes,
                 double* sums, int64_t* counts, void* stream);
 
+/* jps_powspec with the two estimator options the reference lacks (parity unpinned,
+ * defined by oracle/correlations.py:powspec and the analytic tests):
+ *   mesh2 : NULL, or the SAME particles painted on the grid displaced by +half a cell (jps_paint with
+ *           xmin + cell/2 on every axis) -> interlaced spectrum (dk1 + dk2 e^{-i pi (kx+ky+kz)/N}) / 2,
+ *           the aliased images with odd m_x+m_y+m_z cancel; needs n_shell_fields >= 1
+ *   flags : JPS_PK_HERMITIAN counts every stored mode with 0 < kz < N/2 twice (its mirror image is not
+ *           stored), i.e. the full-space shell average; 0 = the reference's half-space counting (Q7). */
+#define JPS_PK_HERMITIAN 1
+JPS_API int jps_powspec_ex(jps_plan_t* plan, const float* mesh, const float* mesh2, int normalise, float box_size,
+                   const float* k_edges, int nb, int mas_order, float shot_noise, int flags,
+                   float* k3d, float* pk3d, float* nmodes, double* sums, int64_t* counts, void* stream);
+
 /* Number of rows powspec_vec_fundamental returns for an n_mesh grid: floor(sqrt(3)*(n/2)). */
 JPS_API int jps_fundamental_nbins(int n_mesh);
 

@@ -16,6 +16,7 @@ ORDER_CIC, ORDER_TSC, ORDER_PCS = 2, 3, 4
 COMPAT_REFERENCE, COMPAT_FIXED = 0, 1
 VARIANT_VEC, VARIANT_SCAN = 0, 1
 PAINT_AUTO, PAINT_ATOMIC, PAINT_SORTED = 0, 1, 2
+PK_HERMITIAN = 1
 
 COMPAT = {"reference": COMPAT_REFERENCE, "fixed": COMPAT_FIXED}
 METHOD = {"auto": PAINT_AUTO, "atomic": PAINT_ATOMIC, "sorted": PAINT_SORTED}
@@ -53,6 +54,7 @@ SIGNATURES = {
     "jps_paint_slab": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _f, _f, _i, _i, _i, _i, _i,
                             _vp, _vp, _sz, _vp]),
     "jps_powspec": (_i, [_vp, _vp, _i, _f, _fp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "jps_powspec_ex": (_i, [_vp, _vp, _vp, _i, _f, _fp, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "jps_fundamental_nbins": (_i, [_i]),
     "jps_powspec_fundamental": (_i, [_vp, _vp, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "jps_xi": (_i, [_vp, _vp, _i, _f, _fp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -41,29 +41,49 @@ def _edge_ptr(e):
 
 
 def powspec_vec(delta, box_size, k_edges, *, mas_order=2, shot_noise=0.0, normalise=False,
-                return_raw=False):
+                return_raw=False, mode_weighting="half", delta2=None):
     """P0, P2, P4 in the user's k bins: returns ``(k3D[nb], Pk3D[nb,3], Nmodes3D[nb])`` float32.
 
     mas_order / shot_noise / normalise extend the reference (which hard-codes the CIC window,
     never subtracts shot noise and expects ``delta`` already normalised).  With
-    ``return_raw=True`` a 4th item ``(sums float64[nb,3], counts int64[nb])`` is appended."""
+    ``return_raw=True`` a 4th item ``(sums float64[nb,3], counts int64[nb])`` is appended.
+
+    Two estimator options the reference lacks (defaults = the reference's behaviour):
+    ``mode_weighting="hermitian"`` counts every stored mode with 0 < kz < N/2 twice, i.e. the
+    full-space shell average instead of the reference's half-space one (Q7);
+    ``delta2`` = the same particles painted on the grid displaced by half a cell
+    (:func:`jax_powspec_b200.mas.paint_interlaced`) gives the interlaced, alias-suppressed spectrum."""
     device = require_cuda()
     kind = ArrayKind(delta)
     mesh = to_device_f32(delta, device)
     n = mesh.shape[0]
     if mesh.dim() != 3 or tuple(mesh.shape) != (n, n, n):
         raise ValueError("delta must be a cubic 3-d mesh")
+    if mode_weighting not in ("half", "hermitian"):
+        raise ValueError("mode_weighting must be 'half' or 'hermitian'")
+    mesh2 = None
+    if delta2 is not None:
+        mesh2 = to_device_f32(delta2, device)
+        if tuple(mesh2.shape) != (n, n, n):
+            raise ValueError("delta2 must have the shape of delta")
     e = _host_edges(k_edges)
     nb = e.size - 1
-    plan = get_plan(n, device)
+    extended = mesh2 is not None or mode_weighting != "half"
+    plan = get_plan(n, device, n_shell_fields=1 if mesh2 is not None else 0)
     k3d = torch.empty(nb, dtype=torch.float32, device=device)
     pk = torch.empty((nb, 3), dtype=torch.float32, device=device)
     nm = torch.empty(nb, dtype=torch.float32, device=device)
     sums = torch.empty((nb, 3), dtype=torch.float64, device=device) if return_raw else None
     counts = torch.empty(nb, dtype=torch.int64, device=device) if return_raw else None
-    check(lib.jps_powspec(plan.handle, ptr(mesh), int(bool(normalise)), float(box_size), _edge_ptr(e), nb,
-                          int(mas_order), float(shot_noise), ptr(k3d), ptr(pk), ptr(nm), ptr(sums),
-                          ptr(counts), stream_ptr()), "jps_powspec")
+    if extended:
+        flags = _lib.PK_HERMITIAN if mode_weighting == "hermitian" else 0
+        check(lib.jps_powspec_ex(plan.handle, ptr(mesh), ptr(mesh2), int(bool(normalise)), float(box_size),
+                                 _edge_ptr(e), nb, int(mas_order), float(shot_noise), flags, ptr(k3d), ptr(pk),
+                                 ptr(nm), ptr(sums), ptr(counts), stream_ptr()), "jps_powspec_ex")
+    else:
+        check(lib.jps_powspec(plan.handle, ptr(mesh), int(bool(normalise)), float(box_size), _edge_ptr(e), nb,
+                              int(mas_order), float(shot_noise), ptr(k3d), ptr(pk), ptr(nm), ptr(sums),
+                              ptr(counts), stream_ptr()), "jps_powspec")
     out = (kind.out(k3d), kind.out(pk), kind.out(nm))
     if return_raw:
         out = out + ((kind.out(sums), kind.out(counts)),)

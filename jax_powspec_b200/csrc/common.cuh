@@ -90,6 +90,7 @@ enum KernelId {
   K_TEXT_COMPACT,
   K_MOCK_FIELD,
   K_MOCK_POPULATE,
+  K_INTERLACE,
   K_NUM
 };
 
@@ -118,7 +119,8 @@ enum TableMode {
   TABLE_PK_EDGES = 0,        // powspec_vec: user edges, half-space mode counts
   TABLE_PK_FUNDAMENTAL = 1,  // powspec_vec_fundamental: bin = int(|k|)
   TABLE_XI_EDGES = 2,        // xi_vec: user edges, full-grid pair counts
-  TABLE_XI_FUNDAMENTAL = 3   // xi_vec_fundamental
+  TABLE_XI_FUNDAMENTAL = 3,  // xi_vec_fundamental
+  TABLE_PK_EDGES_HERM = 4    // user edges, stored modes with 0 < kz < N/2 counted twice (Q7 corrected)
 };
 
 constexpr int kNumTables = 4;

@@ -21,7 +21,7 @@ static const char* kKernelNames[K_NUM] = {
     "paint_atomic", "bucket_count", "bucket_scan", "bucket_scatter", "bucket_fine", "paint_tile", "pk_fold_bin",
     "pk_count_modes", "pk_finalize", "cufft_r2c", "cufft_c2r", "memset", "shell_filter",
     "triple_reduce", "xi_bin", "misc", "text_index", "text_parse", "text_compact",
-    "mock_field", "mock_populate"};
+    "mock_field", "mock_populate", "interlace_combine"};
 
 // Distinct plans may be driven from distinct host threads (include/jps.h), so the process-wide
 // accounting is atomic counters + one mutex around the event lists.

@@ -18,7 +18,7 @@ from . import _lib
 from ._lib import check, lib
 from .plan import ArrayKind, ptr, require_cuda, stream_ptr, to_device_f32
 
-__all__ = ["cic_mas_vec", "cic_mas", "tsc_mas_vec", "pcs_mas_vec", "paint"]
+__all__ = ["cic_mas_vec", "cic_mas", "tsc_mas_vec", "pcs_mas_vec", "paint", "paint_interlaced"]
 
 _WS: dict = {}
 
@@ -100,3 +100,17 @@ def pcs_mas_vec(delta, x, y, z, w, n_part, xmin, ymin, zmin, box_size, n_bins, w
     """Piecewise-cubic-spline painter (absent from the reference; same signature)."""
     kw.setdefault("compat", "fixed")
     return paint(delta, x, y, z, w, xmin, ymin, zmin, box_size, n_bins, wrap, order=4, **kw)
+
+
+def paint_interlaced(delta, x, y, z, w, xmin, ymin, zmin, box_size, n_bins, *, order=2, method="auto"):
+    """The two meshes of an interlaced estimate (no reference counterpart): the particles painted on the
+    grid at ``(xmin, ymin, zmin)`` and on the grid displaced by +half a cell, both periodic, textbook
+    weights (``compat="fixed"``).  ``delta`` is the starting mesh of both (zeros, as a rule).  Feed the
+    pair to ``powspec_vec(mesh1, ..., delta2=mesh2)``."""
+    import numpy as np
+    half = np.float32(0.5) * (np.float32(box_size) / np.float32(n_bins))          # float32, as the painters work
+    m1 = paint(delta, x, y, z, w, xmin, ymin, zmin, box_size, n_bins, True, order=order, compat="fixed",
+               method=method)
+    m2 = paint(delta, x, y, z, w, float(np.float32(xmin) + half), float(np.float32(ymin) + half),
+               float(np.float32(zmin) + half), box_size, n_bins, True, order=order, compat="fixed", method=method)
+    return m1, m2

@@ -138,7 +138,9 @@ def _binned_multipoles(v, kf, mu2, kedges, precision):
 def interlace_phase(n, dtype=np.complex128):
     """exp(-i pi (kx + ky + kz) / N) on the half-space array, frequencies as k_index() (index N/2 is +N/2,
     Q15).  No reference counterpart (the reference has no interlacing): second mesh painted on a grid
-    displaced by +half a cell, i.e. with xmin + cell/2 (Sefusatti et al. 2016, eq. 17-18)."""
+    displaced by +half a cell, i.e. with xmin + cell/2 (Sefusatti et al. 2016, eq. 17-18).  Modes on the
+    Nyquist planes are their own mirror images up to the sign of N/2, so their phase is ambiguous: as in
+    other implementations they are not meaningful in an interlaced estimate."""
     ki = k_index(n).astype(np.float64)
     ph = np.exp(-1j * np.pi * ki / n)
     mid = n // 2
