@@ -1,5 +1,5 @@
+#!/bin/bash
+# Last GPU call of round 1: the whole GPU suite on the final tree, then the 1-GPU point of the C4 series.
 mkdir -p gpurun_out
-( timeout 150 python -m pytest tests/test_gpu_z_bispec_pairs.py tests/test_gpu_z_mocks.py -m gpu -q -p no:cacheprovider 2>&1 | tail -60 ) > gpurun_out/late_tests.log 2>&1
-( timeout 60 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 ) > gpurun_out/late_smoke.log 2>&1
-( timeout 90 python tools/bench_round_late.py 2>&1 | tail -5 ) > gpurun_out/late_bench.log 2>&1
-( timeout 600 python -m pytest tests -m gpu -x -q -p no:cacheprovider 2>&1 | tail -15 ) > gpurun_out/full_gpu_tests.log 2>&1
+( timeout 110 python -m pytest tests -m gpu -x -q -p no:cacheprovider 2>&1 | tail -25 ) > gpurun_out/final_gpu_tests.log 2>&1
+( timeout 70 python bench.py --workload c4 --gpus 1 --steps 3 --warmup 3 2>&1 | tail -5 ) > gpurun_out/c4_1gpu.log 2>&1
