@@ -144,3 +144,55 @@ def covariance_batch(seeds: Sequence[int], measure: Callable[[int], torch.Tensor
     arr = full.cpu().numpy()
     mean, cov = sample_covariance(arr)
     return arr.reshape(len(seeds), -1, 3), mean, cov
+
+
+def sharded_rows(n_items: int, compute: Callable[[list], "torch.Tensor | tuple"]):
+    """Units that need no communication (triangle bins of the bispectrum sweep,
+    realisations of a batch): rank r evaluates items r, r+W, ... with ONE call ``compute(indices)``, which
+    returns a tensor -- or a tuple of tensors -- whose leading dimension is ``len(indices)``; rank 0 gets
+    the same structure with ``n_items`` rows in global order, the other ranks ``None``.  The only exchange
+    is the final gather.  ``compute`` is not called on a rank whose shard is empty."""
+    r, w = world()
+    mine = shard_indices(n_items)
+    out = compute(mine) if mine else None
+    single = isinstance(out, torch.Tensor)
+    parts = None if out is None else ([out] if single else list(out))
+    if w == 1:
+        return out
+    # ranks with an empty shard need the row shapes / dtypes / device kind of the others
+    meta = None if parts is None else [(tuple(p.shape[1:]), str(p.dtype).replace("torch.", ""), single) for p in parts]
+    metas = [None] * w
+    dist.all_gather_object(metas, meta)
+    ref = next(m for m in metas if m is not None)
+    single = ref[0][2]
+    if parts is None:
+        dev = (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl"
+               else torch.device("cpu"))
+        parts = [torch.zeros((0,) + shp, dtype=getattr(torch, dt), device=dev) for shp, dt, _ in ref]
+    full = [gather_rows(p.contiguous(), n_items) for p in parts]
+    if r != 0:
+        return None
+    return full[0] if single else tuple(full)
+
+
+def bispec_pairs_sharded(delta, box_size, k1, k2, theta, **kw):
+    """BASELINE.json configs[2] on several GPUs: the (k1, k2) pairs of ``correlations.bispec_pairs`` are
+    independent, so every rank holds the (small) mesh and evaluates its round-robin share of the pairs;
+    rank 0 returns ``(k_all[np, bins+2], Pk[np, bins+2], theta, B[np, bins], Q[np, bins])`` in the order
+    of ``k1``/``k2``, the other ranks ``None``.  No mesh sharding, no data-path collective."""
+    from .correlations import bispec_pairs
+    k1 = np.asarray(k1, dtype=np.float32).ravel()
+    k2 = np.asarray(k2, dtype=np.float32).ravel()
+    if k1.size != k2.size or k1.size < 1:
+        raise ValueError("k1 and k2 must be equally long, non-empty 1-d arrays")
+    th = np.asarray(theta, dtype=np.float32).ravel()
+
+    def compute(idx):
+        k_all, pk, _, B, Q = bispec_pairs(delta, box_size, k1[idx], k2[idx], th, **kw)
+        return tuple(torch.as_tensor(a) for a in (k_all, pk, B, Q))
+
+    res = sharded_rows(k1.size, compute)
+    if res is None:
+        return None
+    k_all, pk, B, Q = res
+    return k_all, pk, th, B, Q

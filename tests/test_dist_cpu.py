@@ -37,6 +37,26 @@ def _worker(rank, world_size, port, n_items, out_dir):
         assert torch.equal(full, torch.tensor([[float(i), float(i) * 2] for i in range(n_items)]))
     else:
         assert full is None
+    # generic sharded units (the bispectrum sweep's host logic): tuple of row tensors, one call per rank
+    calls = []
+
+    def compute(idx):
+        calls.append(list(idx))
+        i = torch.tensor(idx, dtype=torch.float32)
+        return i[:, None] * torch.ones(1, 4), (i * 10).to(torch.float64)[:, None, None].expand(-1, 2, 3).contiguous()
+
+    res = jd.sharded_rows(n_items, compute)
+    assert calls == ([mine] if mine else [])                  # one call, none for an empty shard
+    if rank == 0:
+        a, b = res
+        want = torch.arange(n_items, dtype=torch.float32)
+        assert torch.equal(a, want[:, None] * torch.ones(1, 4))
+        assert b.dtype == torch.float64 and torch.equal(b, (want * 10).to(torch.float64)[:, None, None].expand(-1, 2, 3))
+    else:
+        assert res is None
+    one = jd.sharded_rows(n_items, lambda idx: torch.tensor(idx, dtype=torch.int64)[:, None])
+    if rank == 0:
+        assert torch.equal(one, torch.arange(n_items)[:, None])
     res = jd.covariance_batch(list(range(100, 100 + n_items)), _fake_measure)
     if rank == 0:
         rows, mean, cov = res
@@ -68,6 +88,8 @@ def test_single_process_paths():
     assert jd.max_over_ranks(3.5) == 3.5
     res = jd.covariance_batch([1, 2, 3], _fake_measure)
     assert res[0].shape == (3, 5, 3) and res[2].shape == (15, 15)
+    a, b = jd.sharded_rows(4, lambda idx: (torch.tensor(idx)[:, None], torch.tensor(idx) * 2))
+    assert a.tolist() == [[0], [1], [2], [3]] and b.tolist() == [0, 2, 4, 6]
 
 
 # --------------------------------------------------------------------------- slab choreography
