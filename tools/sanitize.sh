@@ -1,0 +1,17 @@
+#!/bin/bash
+# compute-sanitizer passes over the hand-written kernels at small sizes (race detection).
+# Run on the GPU box:   gpurun --timeout 900 -- 'bash tools/sanitize.sh'
+# memcheck: out-of-bounds / misaligned accesses; racecheck: shared-memory hazards in the tile painters,
+# the bucketing passes, the binning kernels and the block scans of the mock generator.
+# Each pass runs a SMALL selection of the GPU tests (the sanitizer slows kernels down 10-100x).
+set -u
+mkdir -p gpurun_out
+SAN=/usr/local/cuda/bin/compute-sanitizer
+SEL='test_known_answers or test_translation_by_whole_cells or test_plane_wave_known_answer or test_golden_bispec or test_populate_device_in_device_out_and_empty or test_golden_gaussian_field or test_interlacing_leaves_a_band_limited_field_alone'
+for tool in memcheck racecheck; do
+  timeout 400 $SAN --tool $tool --error-exitcode 99 --print-limit 20 \
+      python -m pytest tests -m gpu -q -x -p no:cacheprovider -k "$SEL" \
+      > gpurun_out/sanitize_$tool.log 2>&1
+  echo "$tool exit code $?" >> gpurun_out/sanitize_$tool.log
+  tail -5 gpurun_out/sanitize_$tool.log
+done
