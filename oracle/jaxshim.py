@@ -347,6 +347,52 @@ def _scan(f, init, xs):
     return carry, (_tree_stack(ys) if ys else None)
 
 
+# --------------------------------------------------------------------------- jax.random (injected draws)
+# /root/reference/src/populate_field.py draws from jax.random (threefry).  That stream cannot be
+# reproduced without JAX, and the device generator does not try to (it uses Philox counters): what the
+# golden vectors pin for that file is its ARITHMETIC.  So the stand-ins below hand out whatever the
+# caller queued in RANDOM_FEED -- uniforms and Poisson counts chosen by oracle/make_mock_golden.py --
+# with JAX's dtypes (float32 uniforms, int32 counts).
+RANDOM_FEED = {"uniform": [], "poisson": []}
+
+
+class _Key:
+    def __init__(self, tag):
+        self.tag = tag
+
+
+def _prng_key(seed):
+    return _Key((int(seed),))
+
+
+def _split(key, num=2):
+    return tuple(_Key(key.tag + (i,)) for i in range(num))
+
+
+def _uniform(key, shape=(), dtype=_F32, minval=0.0, maxval=1.0):
+    u = np.asarray(RANDOM_FEED["uniform"].pop(0), dtype=_F32)
+    assert u.shape == tuple(shape), (u.shape, shape)
+    return _wrap(u)
+
+
+def _poisson(key, lam, shape=None, dtype=_I32):
+    k = np.asarray(RANDOM_FEED["poisson"].pop(0)).astype(_I32)
+    assert shape is None or k.shape == tuple(shape), (k.shape, shape)
+    return _wrap(k)
+
+
+def _argsort(a, axis=-1):
+    return _wrap(np.argsort(np.asarray(_raw(a)), axis=axis, kind="stable"))
+
+
+def _unravel_index(idx, shape):
+    return tuple(_wrap(i) for i in np.unravel_index(np.asarray(_raw(idx)), tuple(shape)))
+
+
+def _repeat(a, repeats, axis=None):
+    return _wrap(np.repeat(np.asarray(_raw(a)), np.asarray(_raw(repeats)), axis=axis))
+
+
 def install():
     """Register the fake modules.  Idempotent."""
     if "jax" in sys.modules and getattr(sys.modules["jax"], "__is_jps_shim__", False):
@@ -368,6 +414,11 @@ def install():
     jnp.where, jnp.sinc, jnp.histogram, jnp.nansum = _where, _sinc, _histogram, _nansum
     jnp.sqrt, jnp.sin, jnp.cos, jnp.exp = _unary(np.sqrt), _unary(np.sin), _unary(np.cos), _unary(np.exp)
     jnp.broadcast_to, jnp.logical_and, jnp.einsum = _broadcast_to, _logical_and, _einsum
+    jnp.argsort, jnp.unravel_index, jnp.repeat = _argsort, _unravel_index, _repeat
+    jnp.sign, jnp.abs = _unary(np.sign), _unary(np.abs)
+    random = types.ModuleType("jax.random")
+    random.PRNGKey, random.split, random.uniform, random.poisson = _prng_key, _split, _uniform, _poisson
+    jax.random = random
     fft.rfftn, fft.irfftn = _rfftn, _irfftn
     jnp.fft = fft
     lax.cond, lax.scan = _cond, _scan
@@ -376,7 +427,7 @@ def install():
 
     sys.modules.update({
         "jax": jax, "jax.numpy": jnp, "jax.numpy.fft": fft, "jax.lax": lax,
-        "jax.experimental": exp, "jax.experimental.loops": loops,
+        "jax.experimental": exp, "jax.experimental.loops": loops, "jax.random": random,
     })
 
     # /root/reference/src/correlations.py:1 imports a private numpy symbol that no
@@ -411,3 +462,17 @@ def load_reference(ref_root="/root/reference"):
         spec.loader.exec_module(mod)
         mods.append(mod)
     return tuple(mods)
+
+
+def load_reference_module(name, ref_root="/root/reference"):
+    """Import one more unmodified reference source (e.g. ``populate_field``) under the shim."""
+    import importlib.util
+    import os
+
+    install()
+    sys.dont_write_bytecode = True
+    path = os.path.join(ref_root, "src", f"{name}.py")
+    spec = importlib.util.spec_from_file_location(f"_jps_reference_{name}", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

@@ -8,11 +8,13 @@ device generator gives every mode its own Philox counter instead, so to compare 
 our generator assigns to each mode -- np.random.random is replaced by an iterator over them, nothing
 else is touched -- and stores what the reference then returns.
 
-populate_field() (gauss_field.py:90-110, NumPy twin of src/populate_field.py) is run the same way on a
-small mesh: np.random.poisson returns our per-cell counts (in the reference's descending-density cell
-order) and np.random.random our per-particle uniforms; stored are its coordinates re-ordered to C cell
-order.  The reference computes those in float64 (float32 cell centres + float64 offsets); the device
-follows the JAX twin's float32 arithmetic, hence the 1e-6 relative tolerance in the tests.
+populate_field() is run the same way on a small mesh, in both of its versions: the NumPy twin
+(gauss_field.py:90-110) directly, with np.random.poisson returning our per-cell counts (in the
+reference's descending-density cell order) and np.random.random our per-particle uniforms; and the JAX
+one (src/populate_field.py:11-29) through oracle/jaxshim.py with the same draws injected for jax.random.
+Stored are their coordinates re-ordered to C cell order.  The NumPy twin mixes float32 cell centres with
+float64 offsets (hence a 2e-7 relative tolerance in the tests); the JAX twin is float32 throughout, which
+is the arithmetic the device follows -- its rows are reproduced bit for bit.
 
     python -m oracle.make_mock_golden        (needs /root/reference; writes tests/golden/ref_mock.npz)
 """
@@ -93,6 +95,22 @@ def main():
         out.update({"pf_n": n, "pf_box": box, "pf_density": density, "pf_seed": seed, "pf_rho": rho0,
                     "pf_counts": counts, "pf_coords_ref": back, "pf_coords_host": pos})
         print(f"populate_field: {total} particles, max |ref - host| = {np.abs(back - pos).max():.3g}")
+
+        # ---- the JAX twin, src/populate_field.py:11-29, UNMODIFIED, on NumPy through oracle/jaxshim.py with
+        # the same counts and uniforms injected for jax.random (float32 arithmetic throughout, as under JAX)
+        np.random.random, np.random.seed, np.random.poisson = real_random, real_seed, real_poisson
+        from oracle import jaxshim
+        refj = jaxshim.load_reference_module("populate_field")
+        jaxshim.RANDOM_FEED["poisson"].append(counts[order])
+        jaxshim.RANDOM_FEED["uniform"].append(uni[rows].astype(np.float32))
+        key = sys.modules["jax"].random.PRNGKey(seed)
+        coords_j = np.asarray(refj.populate_field(jaxshim._wrap(rho0.copy()), n, box, density, key))
+        assert coords_j.dtype == np.float32
+        back_j = np.empty_like(coords_j)
+        back_j[rows] = coords_j
+        out["pf_coords_ref_jax"] = back_j
+        print(f"populate_field (JAX twin): bit-identical rows {np.mean(np.all(back_j == pos, axis=1)):.6f}, "
+              f"max |ref - host| = {np.abs(back_j - pos).max():.3g}")
     finally:
         np.random.random, np.random.seed, np.random.poisson = real_random, real_seed, real_poisson
     np.savez_compressed(os.path.join(GOLD, "ref_mock.npz"), **out)

@@ -296,3 +296,6 @@ def test_golden_populate_field(host, golden_dir):
     d = np.abs(pos.astype(np.float64) - g["pf_coords_ref"])
     d = np.minimum(d, box - d)                                            # a wrap decided at the box edge
     assert d.max() <= 2e-7 * box
+    # the JAX twin (src/populate_field.py, unmodified, run under oracle/jaxshim.py with the same draws injected)
+    # is float32 throughout, like the device: bit for bit
+    np.testing.assert_array_equal(pos, g["pf_coords_ref_jax"])
