@@ -75,3 +75,47 @@ def test_no_cpu_fallback():
     import jax_powspec_b200 as jps
     with pytest.raises(jps._lib.JpsError):
         jps.powspec_vec(np.zeros((8, 8, 8), np.float32), 100.0, np.arange(0.1, 1, 0.1))
+
+
+def _declared_prototypes():
+    """name -> (return type, [parameter types]) parsed from include/jps.h (comments stripped)."""
+    text = open(os.path.join(ROOT, "include", "jps.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"JPS_API\s+([\w\s\*]+?)\b(jps_\w+)\s*\((.*?)\)\s*;", text, flags=re.S):
+        ret, name, params = m.group(1).strip(), m.group(2), m.group(3).strip()
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        types = []
+        for p in plist:
+            p = re.sub(r"\s+", " ", p)
+            if "*" in p:
+                types.append("ptr")
+            else:
+                types.append(re.sub(r"\s*\w+$", "", p).replace("const ", "").strip())   # drop the parameter name
+        protos[name] = (ret, types)
+    return protos
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every binding in _lib.SIGNATURES has the header's arity, scalar kinds and pointer positions:
+    a wrong argtypes list corrupts the call silently."""
+    import ctypes as C
+    from jax_powspec_b200 import _lib
+    scalar = {"int": C.c_int, "float": C.c_float, "int64_t": C.c_int64, "size_t": C.c_size_t,
+              "unsigned long long": C.c_ulonglong, "double": C.c_double}
+    protos = _declared_prototypes()
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, (ret, types) in protos.items():
+        res, args = _lib.SIGNATURES[name]
+        assert len(args) == len(types), f"{name}: header has {len(types)} parameters, binding {len(args)}"
+        for i, (t, a) in enumerate(zip(types, args)):
+            if t == "ptr":
+                is_ptr = a in (C.c_void_p, C.c_char_p) or hasattr(a, "contents") or issubclass(a, C._Pointer)
+                assert is_ptr, f"{name} arg {i}: header pointer, binding {a}"
+            else:
+                assert t in scalar, f"{name} arg {i}: unknown scalar type '{t}' in the header"
+                assert a is scalar[t], f"{name} arg {i}: header {t}, binding {a}"
+        if "*" in ret:
+            assert res in (C.c_char_p, C.c_void_p), name
+        else:
+            assert res is scalar[ret.replace("const ", "").strip()], f"{name}: return {ret} vs {res}"
