@@ -119,3 +119,27 @@ def test_ctypes_signatures_match_the_header():
             assert res in (C.c_char_p, C.c_void_p), name
         else:
             assert res is scalar[ret.replace("const ", "").strip()], f"{name}: return {ret} vs {res}"
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path, lib):
+    """include/jps.h is the drop-in boundary: it must be consumable by a C compiler (no C++-isms, no torch
+    types) and libjps.so must link from plain C.  The program only calls entry points that need no GPU."""
+    import subprocess
+    src = tmp_path / "caller.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "jps.h"\n'
+        "int main(void) {\n"
+        "  size_t bytes = 123;\n"
+        "  if (jps_version() != JPS_VERSION) return 1;\n"
+        "  if (jps_paint_workspace_bytes(64, 1000, 2, JPS_PAINT_ATOMIC, &bytes) != JPS_OK || bytes != 0) return 2;\n"
+        "  if (jps_paint_workspace_bytes(64, 1000, 9, JPS_PAINT_ATOMIC, &bytes) != JPS_ERR_INVALID) return 3;\n"
+        "  if (jps_last_error()[0] == 0) return 4;\n"
+        "  if (jps_fundamental_nbins(256) != 221) return 5;\n"
+        "  if (jps_mock_field_workspace_bytes(100) < 1600) return 6;\n"
+        '  puts("ok");\n  return 0;\n}\n')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(LIB)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-L", libdir, "-ljps", f"-Wl,-rpath,{libdir}", "-o", str(exe)])
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", (out.returncode, out.stdout)
