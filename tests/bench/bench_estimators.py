@@ -2,9 +2,10 @@
   C1: CIC (reference compat) on 256^3, 5e6 particles, P(k) with tests/correlations.py:76 edges
   C3: FFT bispectrum on a 256^3 CIC mesh, (k1,k2)=(0.1,0.2), 20 angles (tests/bispec.py:53-54); xi(s) too
   C5: covariance batch throughput (realisations/s) with 1e7 particles on 512^3 CIC
-Prints one JSON object; CPU columns time oracle/ (C + NumPy restatement) on the host cores."""
+Prints one JSON object; CPU columns time oracle/ (C + NumPy restatement) on the host cores.
+Lives under tests/ because it uses oracle/ as its checker (only tests/, smoke() and bench.py may)."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import jax_powspec_b200 as jps
 from jax_powspec_b200.mocks import lognormal_catalog

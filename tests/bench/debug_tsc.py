@@ -1,6 +1,6 @@
 """Debug: atomic vs sorted TSC painter vs f64 oracle on a 512^3 mesh (run on the GPU box)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import jax_powspec_b200 as jps
 from jax_powspec_b200.mocks import lognormal_catalog
