@@ -187,12 +187,20 @@ def bispec_pairs_sharded(delta, box_size, k1, k2, theta, **kw):
         raise ValueError("k1 and k2 must be equally long, non-empty 1-d arrays")
     th = np.asarray(theta, dtype=np.float32).ravel()
 
+    on_nccl = dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"
+
     def compute(idx):
         k_all, pk, _, B, Q = bispec_pairs(delta, box_size, k1[idx], k2[idx], th, **kw)
-        return tuple(torch.as_tensor(a) for a in (k_all, pk, B, Q))
+        rows = tuple(torch.as_tensor(a) for a in (k_all, pk, B, Q))
+        if on_nccl:                                   # NCCL gathers device tensors only (NumPy in -> host rows)
+            dev = torch.device("cuda", torch.cuda.current_device())
+            rows = tuple(t.to(dev) for t in rows)
+        return rows
 
     res = sharded_rows(k1.size, compute)
     if res is None:
         return None
     k_all, pk, B, Q = res
+    if not isinstance(delta, torch.Tensor):           # same container kind as the input, like bispec_pairs
+        k_all, pk, B, Q = (t.cpu().numpy() for t in (k_all, pk, B, Q))
     return k_all, pk, th, B, Q
