@@ -57,6 +57,29 @@ def _worker(rank, world_size, port, n_items, out_dir):
     one = jd.sharded_rows(n_items, lambda idx: torch.tensor(idx, dtype=torch.int64)[:, None])
     if rank == 0:
         assert torch.equal(one, torch.arange(n_items)[:, None])
+    # the bispectrum sweep over ranks, with the GPU call replaced by a stand-in of the same shape contract
+    import jax_powspec_b200.correlations as jc
+
+    def fake_pairs(delta, box_size, a, b, theta, **kw):
+        a, b, theta = (np.asarray(v, dtype=np.float32) for v in (a, b, theta))
+        k_all = np.concatenate([a[:, None], b[:, None], a[:, None] + b[:, None] * np.cos(theta)[None, :]], axis=1)
+        return k_all, 2 * k_all, theta, a[:, None] * theta[None, :], b[:, None] * theta[None, :]
+
+    real_pairs, jc.bispec_pairs = jc.bispec_pairs, fake_pairs
+    try:
+        k1 = np.arange(1, n_items + 1, dtype=np.float32) * 0.01
+        k2 = k1 * 2
+        theta = np.linspace(0, 3, 4).astype(np.float32)
+        got = jd.bispec_pairs_sharded(np.zeros((4, 4, 4), np.float32), 100.0, k1, k2, theta)
+        if rank == 0:
+            want = fake_pairs(None, 100.0, k1, k2, theta)
+            assert isinstance(got[0], np.ndarray)
+            for g_, w_ in zip(got, want):
+                np.testing.assert_array_equal(g_, w_)
+        else:
+            assert got is None
+    finally:
+        jc.bispec_pairs = real_pairs
     res = jd.covariance_batch(list(range(100, 100 + n_items)), _fake_measure)
     if rank == 0:
         rows, mean, cov = res
