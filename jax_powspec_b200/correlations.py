@@ -275,7 +275,12 @@ def compute_all_correlations(delta, box_size, s_edges, k_edges, k1, k2, theta, *
 
 class PaintPowspec:
     """Reusable end-to-end pipeline (what bench.py times): particles -> mesh -> delta_k ->
-    multipoles, one C-ABI call per step, every buffer allocated once."""
+    multipoles, one C-ABI call per step, every buffer allocated once.
+
+    The object keeps the plan that was current for (n_mesh, device) when it was built.  Plans are shared
+    per mesh size and are REPLACED when an estimator needs more shell fields than the cached one has
+    (``xi_vec``, ``bispec``, interlacing): build the pipeline after the first such call, or build a new
+    one -- a stale pipeline fails with a ``JpsError`` (NULL plan), it never touches freed memory."""
 
     def __init__(self, n_mesh, box_size, k_edges, *, order=2, compat="fixed", method="auto",
                  n_part_max=0, shot_noise=0.0, wrap=True, device=None):
