@@ -19,8 +19,8 @@ import torch
 
 from . import _lib
 from ._lib import check, lib
-from .mas import _common_stride, _paint_workspace
-from .plan import ArrayKind, get_plan, ptr, require_cuda, stream_ptr, to_device_f32
+from .mas import new_paint_workspace, paint_workspace_bytes
+from .plan import ArrayKind, Plan, check_particles, get_plan, ptr, require_cuda, stream_ptr, to_device_f32
 
 __all__ = ["powspec_vec", "powspec_vec_fundamental", "xi_vec", "xi_vec_fundamental", "xi_vec_coords",
            "s_edges_conv", "bispec", "bispec_pairs", "triangle_pairs", "compute_2pt_correlations", "compute_all_correlations",
@@ -277,13 +277,15 @@ class PaintPowspec:
     """Reusable end-to-end pipeline (what bench.py times): particles -> mesh -> delta_k ->
     multipoles, one C-ABI call per step, every buffer allocated once.
 
-    The object keeps the plan that was current for (n_mesh, device) when it was built.  Plans are shared
-    per mesh size and are REPLACED when an estimator needs more shell fields than the cached one has
-    (``xi_vec``, ``bispec``, interlacing): build the pipeline after the first such call, or build a new
-    one -- a stale pipeline fails with a ``JpsError`` (NULL plan), it never touches freed memory."""
+    Every pipeline OWNS its plan (cuFFT plans, delta_k buffer, accumulators, bin tables) and its
+    bucketing workspace: two pipelines may run concurrently on two CUDA streams of one GPU (the
+    covariance batch of BASELINE.json configs[4] does), and nothing the functional API does can
+    invalidate a live pipeline.  One pipeline must be driven from one stream at a time
+    (include/jps.h).  Inputs are validated (float32, CUDA, same device, equal lengths); the
+    weights are read with stride 1, strided views are made contiguous."""
 
     def __init__(self, n_mesh, box_size, k_edges, *, order=2, compat="fixed", method="auto",
-                 n_part_max=0, shot_noise=0.0, wrap=True, device=None):
+                 n_part_max=0, shot_noise=0.0, wrap=True, device=None, plan=None):
         self.device = device or require_cuda()
         self.n = int(n_mesh)
         self.box = float(box_size)
@@ -291,7 +293,7 @@ class PaintPowspec:
         self.nb = self.edges.size - 1
         self.order, self.compat, self.method = int(order), compat, method
         self.wrap, self.shot_noise = bool(wrap), float(shot_noise)
-        self.plan = get_plan(self.n, self.device)
+        self.plan = plan if plan is not None else Plan(self.n, 0, self.device)
         d = self.device
         self.mesh = torch.empty((self.n,) * 3, dtype=torch.float32, device=d)
         self.k3d = torch.empty(self.nb, dtype=torch.float32, device=d)
@@ -304,16 +306,14 @@ class PaintPowspec:
             self.reserve(n_part_max)
 
     def reserve(self, n_part):
-        self.ws, self.ws_bytes = _paint_workspace(self.n, n_part, self.order, _lib.METHOD[self.method], self.device)
+        self.ws, self.ws_bytes = new_paint_workspace(self.n, n_part, self.order, _lib.METHOD[self.method], self.device)
 
     def __call__(self, x, y, z, w=None, xmin=0.0, ymin=0.0, zmin=0.0):
         """x,y,z[,w]: float32 CUDA tensors.  Returns (k3D, Pk3D, Nmodes3D) device tensors that are
         overwritten by the next call."""
-        x, y, z, stride = _common_stride(x, y, z)
+        x, y, z, w, stride = check_particles(x, y, z, w, self.device)
         npart = x.numel()
-        need = C.c_size_t(0)
-        check(lib.jps_paint_workspace_bytes(self.n, npart, self.order, _lib.METHOD[self.method], C.byref(need)))
-        if need.value > self.ws_bytes:
+        if paint_workspace_bytes(self.n, npart, self.order, _lib.METHOD[self.method]) > self.ws_bytes:
             self.reserve(npart)
         check(lib.jps_paint_powspec(self.plan.handle, ptr(x), ptr(y), ptr(z), ptr(w), stride, npart,
                                     float(xmin), float(ymin), float(zmin), self.box, self.order,
@@ -326,11 +326,9 @@ class PaintPowspec:
     # ---- the same pipeline in pieces (HostPipeline streams the catalogue through these)
     def paint_chunk(self, x, y, z, w=None, xmin=0.0, ymin=0.0, zmin=0.0):
         """self.mesh += deposit of one piece of the catalogue (zero self.mesh before the first piece)."""
-        x, y, z, stride = _common_stride(x, y, z)
+        x, y, z, w, stride = check_particles(x, y, z, w, self.device)
         npart = x.numel()
-        need = C.c_size_t(0)
-        check(lib.jps_paint_workspace_bytes(self.n, npart, self.order, _lib.METHOD[self.method], C.byref(need)))
-        if need.value > self.ws_bytes:
+        if paint_workspace_bytes(self.n, npart, self.order, _lib.METHOD[self.method]) > self.ws_bytes:
             self.reserve(npart)
         check(lib.jps_paint(self.n, ptr(x), ptr(y), ptr(z), ptr(w), stride, npart, float(xmin), float(ymin),
                             float(zmin), self.box, self.order, int(self.wrap), _lib.COMPAT[self.compat],
@@ -370,7 +368,8 @@ class HostPipeline:
         pipe.reserve(chunk)
 
     def __call__(self, x, y, z, w=None, xmin=0.0, ymin=0.0, zmin=0.0):
-        """x, y, z[, w]: host arrays (NumPy or torch, ideally pinned).  Returns NumPy arrays."""
+        """x, y, z[, w]: host arrays (NumPy or torch, ideally pinned).  Returns NumPy arrays (copies:
+        the pinned staging buffers are reused by the next call)."""
         host = [x, y, z] + ([w] if w is not None else [])
         n = len(x)
         if n > self.cap or len(host) > len(self.dev):
@@ -405,7 +404,7 @@ class HostPipeline:
         self.pk.copy_(pk, non_blocking=True)
         self.nm.copy_(nm, non_blocking=True)
         compute.synchronize()
-        return self.k3d.numpy(), self.pk.numpy(), self.nm.numpy()
+        return self.k3d.numpy().copy(), self.pk.numpy().copy(), self.nm.numpy().copy()
 
 
 def paint_powspec(x, y, z, w, xmin, ymin, zmin, box_size, n_bins, k_edges, *, order=2,
@@ -418,6 +417,7 @@ def paint_powspec(x, y, z, w, xmin, ymin, zmin, box_size, n_bins, k_edges, *, or
     zd = to_device_f32(z, device, allow_strided=True)
     wd = None if w is None else to_device_f32(w, device)
     pipe = PaintPowspec(n_bins, box_size, k_edges, order=order, compat=compat, method=method,
-                        n_part_max=xd.numel(), shot_noise=shot_noise, wrap=wrap, device=device)
+                        n_part_max=xd.numel(), shot_noise=shot_noise, wrap=wrap, device=device,
+                        plan=get_plan(int(n_bins), device))      # the functional API's per-stream plan
     k3d, pk, nm = pipe(xd, yd, zd, wd, xmin, ymin, zmin)
     return kind.out(k3d.clone()), kind.out(pk.clone()), kind.out(nm.clone())

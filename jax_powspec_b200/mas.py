@@ -23,18 +23,33 @@ __all__ = ["cic_mas_vec", "cic_mas", "tsc_mas_vec", "pcs_mas_vec", "paint", "pai
 _WS: dict = {}
 
 
-def _paint_workspace(n_mesh, n_part, order, method, device):
+def paint_workspace_bytes(n_mesh, n_part, order, method) -> int:
     nbytes = C.c_size_t(0)
     check(lib.jps_paint_workspace_bytes(int(n_mesh), int(n_part), int(order), int(method), C.byref(nbytes)),
           "jps_paint_workspace_bytes")
-    if nbytes.value == 0:
+    return int(nbytes.value)
+
+
+def new_paint_workspace(n_mesh, n_part, order, method, device):
+    """A PRIVATE bucketing workspace (pipelines own theirs: two pipelines on two streams of one GPU
+    must not share scratch)."""
+    nbytes = paint_workspace_bytes(n_mesh, n_part, order, method)
+    if nbytes == 0:
         return None, 0
-    key = device.index
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
+
+
+def _paint_workspace(n_mesh, n_part, order, method, device):
+    """Scratch of the functional API: cached per (device, CUDA stream), grown on demand."""
+    nbytes = paint_workspace_bytes(n_mesh, n_part, order, method)
+    if nbytes == 0:
+        return None, 0
+    key = (device.index, int(torch.cuda.current_stream(device).cuda_stream))
     ws = _WS.get(key)
-    if ws is None or ws.numel() < nbytes.value:
-        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
         _WS[key] = ws
-    return ws, nbytes.value
+    return ws, nbytes
 
 
 def _common_stride(x, y, z):
@@ -63,7 +78,7 @@ def paint(delta, x, y, z, w, xmin, ymin, zmin, box_size, n_bins, wrap=True, *, o
     xd, yd, zd, stride = _common_stride(xd, yd, zd)
     wd = None
     if w is not None:
-        wd = to_device_f32(w, device)
+        wd = to_device_f32(w, device)          # contiguous: the C ABI reads w with stride 1
         if wd.dim() != 1 or wd.numel() != xd.numel():
             raise ValueError("w must be a 1-d array as long as x")
     npart = xd.numel()

@@ -63,12 +63,14 @@ _PLANS: dict = {}
 
 
 def get_plan(n_mesh: int, device: torch.device, n_shell_fields: int = 0) -> Plan:
-    key = (int(n_mesh), device.index)
+    """Plan of the functional API, one per (mesh size, device, CUDA stream): a plan's delta_k buffer and
+    accumulators belong to the stream its calls are enqueued on (include/jps.h: "one plan per host
+    thread/stream"), so two streams of one GPU never share one.  A plan that is too small (fewer shell
+    fields than this call needs) is REPLACED in the cache but never destroyed here: objects that still
+    hold it keep a valid plan, and it is freed when the last of them drops it."""
+    key = (int(n_mesh), device.index, int(torch.cuda.current_stream(device).cuda_stream))
     p = _PLANS.get(key)
-    if p is None or p.n_shell_fields < n_shell_fields:
-        if p is not None:
-            torch.cuda.synchronize(device)
-            p.close()
+    if p is None or p.handle is None or p.n_shell_fields < n_shell_fields:
         p = Plan(n_mesh, n_shell_fields, device)
         _PLANS[key] = p
     return p
@@ -92,6 +94,38 @@ class ArrayKind:
         if self.is_torch:
             return t if self.on_device else t.cpu()
         return t.cpu().numpy()
+
+
+def check_particles(x, y, z, w, device):
+    """Fast-path argument check (the C ABI takes raw pointers and reads ``w`` with stride 1): x, y, z
+    [, w] must be 1-d float32 CUDA tensors of equal length on ``device``; x, y, z may be equally strided
+    column views, ``w`` is made contiguous.  Returns (x, y, z, w, stride).  Raises instead of
+    misreading memory."""
+    n = None
+    for name, t in (("x", x), ("y", y), ("z", z), ("w", w)):
+        if t is None and name == "w":
+            continue
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name} must be a torch tensor (got {type(t).__name__}); use paint()/paint_powspec() for NumPy input")
+        if t.dtype != torch.float32:
+            raise TypeError(f"{name} must be float32 (got {t.dtype})")
+        if not t.is_cuda or t.device != device:
+            raise ValueError(f"{name} lives on {t.device}, the pipeline on {device}")
+        if t.dim() != 1:
+            raise ValueError(f"{name} must be 1-d (got shape {tuple(t.shape)})")
+        if n is None:
+            n = t.numel()
+        elif t.numel() != n:
+            raise ValueError(f"{name} has {t.numel()} elements, x has {n}")
+    strides = {t.stride(0) if t.numel() > 1 else 1 for t in (x, y, z)}
+    if len(strides) > 1 or min(strides) < 1:
+        x, y, z = x.contiguous(), y.contiguous(), z.contiguous()
+        stride = 1
+    else:
+        stride = strides.pop()
+    if w is not None and w.numel() > 1 and w.stride(0) != 1:
+        w = w.contiguous()
+    return x, y, z, w, stride
 
 
 def to_device_f32(a, device, *, allow_strided=False):

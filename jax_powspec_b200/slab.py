@@ -25,9 +25,9 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import check, lib
-from .correlations import _edge_ptr, _host_edges
-from .mas import _common_stride, _paint_workspace
-from .plan import ptr, stream_ptr
+from .correlations import HostPipeline, PaintPowspec, _edge_ptr, _host_edges
+from .mas import new_paint_workspace, paint_workspace_bytes
+from .plan import check_particles, ptr, stream_ptr
 
 GHOST_LO, GHOST_HI = 1, 2
 
@@ -82,15 +82,24 @@ def pack_blocks_torch(yz: torch.Tensor, world: int) -> torch.Tensor:
     return yz.reshape(nxl, world, nyl, nz).permute(1, 0, 2, 3).contiguous()
 
 
-def route_particles(x, y, z, w, box_size: float, n_mesh: int):
-    """Send every particle to the rank that owns floor(x/cell) (variable-size all-to-all).
+def slab_owner(x: torch.Tensor, xmin: float, box_size: float, n_mesh: int, world: int) -> torch.Tensor:
+    """Rank that must paint each particle: owner of the x-plane floor(pos), pos = (x - xmin) * inv with
+    inv = 1 / (box_size / n_mesh) evaluated in float32 exactly as the painters do
+    (csrc/paint_common.cuh ``grid_pos``, /root/reference/src/mas.py:100-105) -- a particle a rounding
+    away from a slab boundary must land on the rank whose ghost planes cover its stencil."""
+    inv = np.float32(1.0) / (np.float32(box_size) / np.float32(n_mesh))
+    pos = (x - float(np.float32(xmin))) * float(inv)
+    cell = torch.floor(pos).to(torch.int64).remainder_(n_mesh)
+    return torch.div(cell, n_mesh // world, rounding_mode="floor")
+
+
+def route_particles(x, y, z, w, box_size: float, n_mesh: int, xmin: float = 0.0):
+    """Send every particle to the rank that owns its x-plane (variable-size all-to-all).
     Catalogues generated in place (BASELINE configs[3]) skip this."""
     rank, world = _world()
     if world == 1:
         return x, y, z, w
-    nxl = n_mesh // world
-    cell = torch.floor(x * (n_mesh / box_size)).to(torch.int64).remainder_(n_mesh)
-    owner = torch.div(cell, nxl, rounding_mode="floor")
+    owner = slab_owner(x, xmin, box_size, n_mesh, world)
     order = torch.argsort(owner)
     counts = torch.bincount(owner, minlength=world)
     recv_counts = torch.empty_like(counts)
@@ -140,6 +149,20 @@ class SlabPipeline:
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         d = self.device
         self.single = self.world == 1
+        # One real rank (not a virtual rank of the test harness): the whole mesh lives on this GPU, so
+        # the step is the single-GPU pipeline -- ONE monolithic 3-D R2C plan instead of 2-D + strided
+        # 1-D transforms (2048^3: 93.6 ms of FFT against ~55 ms) and the 8-fold binning kernel.
+        self.local = None
+        if self.single and rank is None:
+            self.local = PaintPowspec(self.n, self.box, self.edges, order=self.order, compat=self.compat,
+                                      method=self.method, shot_noise=self.shot_noise, wrap=self.wrap,
+                                      device=self.device)
+            self.transport, self.xfast, self.handle = "local", False, None
+            self.mesh, self.k3d, self.pk, self.nm = self.local.mesh, self.local.k3d, self.local.pk, self.local.nm
+            self.gl = self.gh = 0
+            self.nxa, self.x0 = self.n, 0
+            self.peer_ptrs, self._ipc_bases = None, []
+            return
         self.gl, self.gh = (0, 0) if self.single else (GHOST_LO, GHOST_HI)
         self.nxa = self.nxl + self.gl + self.gh
         self.x0 = self.rank * self.nxl - self.gl
@@ -251,15 +274,16 @@ class SlabPipeline:
 
     # ---- stages (each enqueues on the current stream; exchanges are separate so that a test can
     #      drive several virtual ranks on one device)
-    def stage_paint(self, x, y, z, w=None, xmin=0.0, ymin=0.0, zmin=0.0):
-        x, y, z, stride = _common_stride(x, y, z)
+    def stage_paint(self, x, y, z, w=None, xmin=0.0, ymin=0.0, zmin=0.0, zero=True):
+        """Deposit this rank's particles into its planes (+ ghosts).  zero=False accumulates on top of the
+        planes as they are (a catalogue streamed in pieces, SlabHostPipeline)."""
+        x, y, z, w, stride = check_particles(x, y, z, w, self.device)
         npart = x.numel()
         meth = _lib.METHOD[self.method]
-        need = C.c_size_t(0)
-        check(lib.jps_paint_workspace_bytes(self.n, npart, self.order, meth, C.byref(need)))
-        if need.value > self.pws_bytes:
-            self.pws, self.pws_bytes = _paint_workspace(self.n, npart, self.order, meth, self.device)
-        self.mesh.zero_()
+        if paint_workspace_bytes(self.n, npart, self.order, meth) > self.pws_bytes:
+            self.pws, self.pws_bytes = new_paint_workspace(self.n, npart, self.order, meth, self.device)
+        if zero:
+            self.mesh.zero_()
         check(lib.jps_paint_slab(self.n, self.x0, self.nxa, ptr(x), ptr(y), ptr(z), ptr(w), stride, npart,
                                  float(xmin), float(ymin), float(zmin), self.box, self.order, int(self.wrap),
                                  _lib.COMPAT[self.compat], _lib.VARIANT_VEC, meth, ptr(self.mesh), ptr(self.pws),
@@ -327,7 +351,15 @@ class SlabPipeline:
     # ---- the distributed call
     def __call__(self, x, y, z, w=None, xmin=0.0, ymin=0.0, zmin=0.0):
         """x, y, z[, w]: this rank's particles (x inside its slab; use route_particles otherwise)."""
+        if self.local is not None:
+            return self.local(x, y, z, w, xmin, ymin, zmin)
         self.stage_paint(x, y, z, w, xmin, ymin, zmin)
+        return self.finish()
+
+    def finish(self):
+        """Everything after the deposit: halo exchange, distributed FFT, binning, allreduce."""
+        if self.local is not None:
+            return self.local.finish()
         if not self.single:
             halo_exchange_add(self.mesh, self.nxl)
         self.stage_fft_yz_pack()
@@ -342,6 +374,90 @@ class SlabPipeline:
         if self.world > 1:
             dist.all_reduce(self.sums)
         return self.stage_finalize()
+
+    # ---- NVLink reference rate of the transpose (bench.py reports the fused stage against it)
+    def probe_transpose(self, xfast: bool, repeats: int = 3) -> float:
+        """Milliseconds of ONE peer-store launch alone (no FFT next to it) moving this rank's
+        (P-1)/P of the 2-D-transformed planes to the peers: xfast=False is the straight contiguous
+        copy kernel (the achievable peer-copy rate of this box), xfast=True the transposing store the
+        pipeline uses.  Collective (every rank must call it); overwrites the receive buffers."""
+        if self.transport != "p2p":
+            raise _lib.JpsError("probe_transpose needs the p2p transport")
+        was = self.xfast
+        self._set_layout(xfast)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = float("inf")
+        for _ in range(repeats):
+            dist.barrier()
+            torch.cuda.synchronize(self.device)
+            e0.record()
+            check(lib.jps_slab_pack_p2p(self.handle, ptr(self.buf_b), self.peer_ptrs, stream_ptr()), "jps_slab_pack_p2p")
+            e1.record()
+            torch.cuda.synchronize(self.device)
+            best = min(best, e0.elapsed_time(e1))
+        dist.barrier()
+        self._set_layout(was)
+        return best
+
+
+class SlabHostPipeline:
+    """End-to-end call for a catalogue that lives in HOST memory on every rank (its slab's particles):
+    host->device copy in pieces on a copy stream while the compute stream deposits the previous piece,
+    then halo exchange, distributed FFT, binning, allreduce, and the device->host read of
+    (k3D, Pk3D, Nmodes3D).  This is what bench.py's ``e2e`` times on the sharded path."""
+
+    def __init__(self, pipe: SlabPipeline, n_part_max: int, weighted: bool = False, n_chunks: int = 8):
+        self.pipe = pipe
+        if pipe.local is not None:                       # one rank: the single-GPU host pipeline
+            self.inner = HostPipeline(pipe.local, n_part_max, weighted=weighted, n_chunks=n_chunks)
+            return
+        self.inner = None
+        d = pipe.device
+        self.cap, self.n_chunks = int(n_part_max), max(1, int(n_chunks))
+        self.dev = [torch.empty(self.cap, dtype=torch.float32, device=d) for _ in range(4 if weighted else 3)]
+        self.k3d = torch.empty(pipe.nb, dtype=torch.float32).pin_memory()
+        self.pk = torch.empty((pipe.nb, 3), dtype=torch.float32).pin_memory()
+        self.nm = torch.empty(pipe.nb, dtype=torch.float32).pin_memory()
+        self.copy_stream = torch.cuda.Stream(device=d)
+        self.paint_done = None
+
+    def __call__(self, x, y, z, w=None, xmin=0.0, ymin=0.0, zmin=0.0):
+        if self.inner is not None:
+            return self.inner(x, y, z, w, xmin, ymin, zmin)
+        host = [x, y, z] + ([w] if w is not None else [])
+        n = len(x)
+        if n > self.cap or len(host) > len(self.dev):
+            raise ValueError("SlabHostPipeline: catalogue larger than the buffers it was built for")
+        host = [h if isinstance(h, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(h, dtype=np.float32))
+                for h in host]
+        p = self.pipe
+        compute = torch.cuda.current_stream(p.device)
+        nchunks = min(self.n_chunks, max(1, n // 65536))
+        bounds = [n * c // nchunks for c in range(nchunks + 1)]
+        ready = []
+        with torch.cuda.stream(self.copy_stream):
+            if self.paint_done is not None:
+                self.copy_stream.wait_event(self.paint_done)
+            for c in range(nchunks):
+                lo, hi = bounds[c], bounds[c + 1]
+                for h, d in zip(host, self.dev):
+                    d[lo:hi].copy_(h[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+                ready.append(ev)
+        for c in range(nchunks):
+            lo, hi = bounds[c], bounds[c + 1]
+            compute.wait_event(ready[c])
+            wd = self.dev[3][lo:hi] if w is not None else None
+            p.stage_paint(self.dev[0][lo:hi], self.dev[1][lo:hi], self.dev[2][lo:hi], wd, xmin, ymin, zmin, zero=(c == 0))
+        self.paint_done = torch.cuda.Event()
+        self.paint_done.record(compute)
+        k3d, pk, nm = p.finish()
+        self.k3d.copy_(k3d, non_blocking=True)
+        self.pk.copy_(pk, non_blocking=True)
+        self.nm.copy_(nm, non_blocking=True)
+        compute.synchronize()
+        return self.k3d.numpy().copy(), self.pk.numpy().copy(), self.nm.numpy().copy()
 
 
 def run_virtual_ranks(pipes, catalogs, xmin=0.0, p2p=None):

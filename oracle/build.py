@@ -17,7 +17,7 @@ def build(force: bool = False) -> str:
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
     # -ffp-contract=off: keep float32 products and sums separately rounded, as XLA CPU does
-    cmd = ["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", LIB, SRC, "-lm"]
+    cmd = ["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-o", LIB, SRC, "-lm"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"gcc failed:\n{r.stdout}")

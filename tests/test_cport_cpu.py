@@ -73,3 +73,50 @@ def test_c_binning_other_windows(mas_order):
     _, pk64, counts = oc.powspec(delta, box, ke, mas_order=mas_order, precision="f64")
     np.testing.assert_array_equal(nm.astype(np.int64), counts)
     np.testing.assert_allclose(pk / np.abs(pk64[:, :1]), pk64 / np.abs(pk64[:, :1]), rtol=0, atol=2e-5)
+
+
+# ---- the float64 C + OpenMP restatement used by the FULL-SIZE GPU parity tests (tests/test_gpu_fullsize.py):
+#      pinned here on the NumPy float64 oracle, which is itself pinned on the shim-run reference
+@pytest.mark.parametrize("order,compat", [(2, "reference"), (2, "fixed"), (3, "fixed"), (4, "fixed")])
+@pytest.mark.parametrize("wrap", [True, False])
+def test_c_f64_painter_equals_numpy_f64_oracle(order, compat, wrap):
+    rng = np.random.default_rng(10 * order + wrap)
+    n, box = 24, 500.0
+    p = (rng.random((20000, 3)) * box * 1.04 - 0.02 * box).astype(F32)      # a few particles outside the box
+    if compat == "fixed" or wrap:
+        pass
+    w = rng.random(20000).astype(F32) + F32(0.5)
+    pre = rng.random((n, n, n))
+    for variant in (("vec", "scan") if compat == "reference" else ("vec",)):
+        got = cport.paint_f64(pre, p[:, 0], p[:, 1], p[:, 2], w, -1.5, 0.25, 0.0, box, n, wrap, order=order,
+                              compat=compat, variant=variant)
+        want = om.paint(pre, p[:, 0], p[:, 1], p[:, 2], w, -1.5, 0.25, 0.0, box, n, wrap, order=order,
+                        compat=compat, variant=variant, precision="f64")
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * want.max())
+
+
+@pytest.mark.parametrize("mas_order", [2, 3, 4])
+def test_c_f64_binning_equals_numpy_f64_oracle(mas_order):
+    rng = np.random.default_rng(mas_order)
+    n, box = 36, 700.0
+    delta = rng.normal(size=(n, n, n)).astype(F32)
+    for ke in (np.arange(2 * np.pi / box, np.pi * n / box, 2 * np.pi / box).astype(F32),
+               np.arange(1e-4, 5, 0.2e-2).astype(F32)):
+        k3d, pk, cnt = cport.powspec_f64(delta, box, ke, mas_order=mas_order)
+        k64, pk64, c64 = oc.powspec(delta, box, ke, mas_order=mas_order, precision="f64")
+        np.testing.assert_array_equal(cnt, c64)
+        np.testing.assert_array_equal(k3d, k64)
+        ok = c64 > 0
+        np.testing.assert_allclose(pk[ok], pk64[ok], rtol=1e-11, atol=0)
+
+
+def test_c_multicore_painter_equals_serial_port():
+    rng = np.random.default_rng(3)
+    n, box = 32, 100.0
+    p = (rng.random((50000, 3)) * box).astype(F32)
+    p[p >= F32(box)] = 0.0
+    for order in (2, 3, 4):
+        a = cport.paint(np.zeros((n, n, n), F32), p[:, 0], p[:, 1], p[:, 2], None, 0., 0., 0., box, n, True,
+                        order=order, compat="fixed")
+        b = cport.paint_mt(np.zeros((n, n, n), F32), p[:, 0], p[:, 1], p[:, 2], None, 0., 0., 0., box, n, True, order=order)
+        np.testing.assert_allclose(a, b, rtol=0, atol=2e-5 * a.max())
