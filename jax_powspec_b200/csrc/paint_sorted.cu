@@ -14,6 +14,7 @@
 // and cell choice stays bit-identical to the reference's float32 arithmetic.
 #include "paint_common.cuh"
 
+#include <cuda.h>      // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cstdlib>
 
 namespace jps {
@@ -233,6 +234,47 @@ __global__ void __launch_bounds__(1024) bucket_count_smem_kernel(PaintParams p, 
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
   if ((threadIdx.x & 31) == 0) atomicMax(wmax_bits, __float_as_uint(wmax));    // 32 per CTA, 148 CTAs
+}
+
+// K1a, big-mesh variant (N > 576: the tile table no longer fits one SM's shared memory): the same
+// 16-byte quad loads, one global red per particle into the per-tile counters.  The table is small
+// against the L2 (2048^3: 2.1 M tiles = 8.4 MB), so the reds stay on chip.  With the tile offsets known
+// before the partition, the fine pass reads its records ONCE instead of twice (2048^3 on one GPU:
+// 30.4 -> ~15 ms), which is worth far more than the reds cost over the shared-memory group histogram.
+template <int ORDER, bool REFCIC>
+__global__ void __launch_bounds__(256) bucket_count_global_kernel(PaintParams p, TileGeom g,
+                                                                  unsigned* __restrict__ counts,
+                                                                  unsigned* __restrict__ wmax_bits) {
+  const int64_t T = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nquads = (p.n_part + 3) >> 2;
+  const bool aos = catalogue_is_aos(p);
+  float wmax = p.w ? 0.0f : 1.0f;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += T) {
+    const int64_t i = q << 2;
+    const int cnt = (int)min((int64_t)4, p.n_part - i);
+    Quad c;
+    load_quad(p, aos, i, cnt, c);
+    if (p.w) {
+      float w[4];
+      load_quad_weights(p, i, cnt, w);
+      wmax = quad_wmax(w, cnt, wmax);
+    }
+    int tile[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      tile[u] = tile_of<ORDER, REFCIC>(grid_pos(c.x[u], p.xmin, p.inv), grid_pos(c.y[u], p.ymin, p.inv),
+                                       grid_pos(c.z[u], p.zmin, p.inv), g, 0u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (u < cnt) atomicAdd(counts + tile[u], 1u);
+  }
+  if (!p.w) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(wmax_bits, __float_as_uint(1.0f));
+    return;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
+  if ((threadIdx.x & 31) == 0) atomicMax(wmax_bits, __float_as_uint(wmax));
 }
 
 // ---------------------------------------------------------------- K1b: exclusive scan
@@ -825,6 +867,49 @@ __device__ __forceinline__ void fx_add_batch(unsigned* __restrict__ lo, unsigned
   }
 }
 
+// One axis of a particle that is KNOWN to belong to the tile whose local cell 0 is the global node
+// `origin` (the bucketing put it there): the B-spline weights exactly as bspline_axis() forms them, and
+// the anchor as a TILE-LOCAL index in [0, TILE).  Because the answer is known to lie in the tile, the
+// periodic wrap is one compare (taken only by the few particles whose stencil straddles the box edge)
+// instead of ORDER general wraps per axis: the deposit's preamble shrinks from ~170 to ~60 instructions.
+template <int ORDER>
+__device__ __forceinline__ int tile_local_axis(float pos, int n, int origin, int wrap, float (&w)[ORDER]) {
+  int base;
+  if (ORDER == 2) {
+    const float f = floorf(pos);
+    const float d = pos - f;
+    w[0] = 1.0f - d;
+    w[1] = d;
+    base = (int)f;
+  } else if (ORDER == 3) {
+    const float f = floorf(pos + 0.5f);
+    const float d = pos - f;
+    const float a = 0.5f - d, b = 0.5f + d;
+    w[0] = 0.5f * a * a;
+    w[1] = 0.75f - d * d;
+    w[2] = 0.5f * b * b;
+    base = (int)f - 1;
+  } else {
+    const float f = floorf(pos);
+    const float d = pos - f;
+    const float e = 1.0f - d;
+    const float sixth = 1.0f / 6.0f;
+    w[0] = e * e * e * sixth;
+    w[1] = (4.0f - 6.0f * d * d + 3.0f * d * d * d) * sixth;
+    w[2] = (4.0f - 6.0f * e * e + 3.0f * e * e * e) * sixth;
+    w[ORDER - 1] = d * d * d * sixth;
+    base = (int)f - 1;
+  }
+  if (!wrap) {                                   // non-periodic: drop nodes outside the mesh
+#pragma unroll
+    for (int s = 0; s < ORDER; ++s)
+      if (base + s < 0 || base + s >= n) w[s] = 0.0f;
+  }
+  int l = base - origin;
+  if ((unsigned)l >= (unsigned)TILE) l = pymod(l, n);
+  return l;
+}
+
 template <int ORDER, bool REFCIC, bool NEG>
 __device__ __forceinline__ void fx_deposit(const float4& r, float ws, unsigned* lo, unsigned* hi,
                                            const TileGeom& g, int wrap, int variant, int ox, int oy, int oz) {
@@ -851,12 +936,11 @@ __device__ __forceinline__ void fx_deposit(const float4& r, float ws, unsigned* 
                          ((ddx * ddy) * ddz) * ws};
     fx_add_batch<NEG, 4>(lo, hi, ib, vb);
   } else {
-    int ax, ay, az;
     float wx[ORDER], wy[ORDER], wz[ORDER];
-    tile_axis<ORDER>(r.x, n, wrap, ax, wx);
-    tile_axis<ORDER>(r.y, n, wrap, ay, wy);
-    tile_axis<ORDER>(r.z, n, wrap, az, wz);
-    const int c = ((local_plane(ax, g.x0, g.nx, n) - ox) * L + (ay - oy)) * LP + (az - oz);
+    const int lx = tile_local_axis<ORDER>(r.x, n, g.x0 + ox, wrap, wx);   // ox is a local plane: global node g.x0 + ox
+    const int ly = tile_local_axis<ORDER>(r.y, n, oy, wrap, wy);
+    const int lz = tile_local_axis<ORDER>(r.z, n, oz, wrap, wz);
+    const int c = (lx * L + ly) * LP + lz;
 #pragma unroll
     for (int cc = 0; cc < ORDER; ++cc) wz[cc] *= ws;   // one multiply per update instead of two
 #pragma unroll
@@ -877,15 +961,32 @@ __device__ __forceinline__ void fx_deposit(const float4& r, float ws, unsigned* 
   }
 }
 
+// ---- tile flush through the TMA: cp.reduce.async.bulk.tensor (.add.f32), shared -> global
+// After the deposit the fixed-point tile is converted IN PLACE to float32 (the low-word array becomes a
+// dense [L][L][LP] float box).  One elected thread then hands the whole box to the TMA unit, which adds
+// it to the mesh in L2 -- one instruction per tile instead of L*L*5 per-thread red.global.add.v4 (1 805
+// for PCS), and no per-thread address arithmetic.  Box elements outside the tensor (the ghost planes a
+// slab does not hold) are clipped by the hardware.  Tiles whose box would have to WRAP around the periodic
+// box (last tile of an axis), meshes with N % 4 != 0 and unaligned meshes take the per-thread red path.
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1, int c2) {
+  const unsigned src = (unsigned)__cvta_generic_to_shared(smem_src);
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(tmap), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the box has been read: smem may be released
+}
+
 template <int ORDER, bool REFCIC>
 __global__ void __launch_bounds__(1024) paint_tile_fx_kernel(const float4* __restrict__ sorted,
                                                             const unsigned* __restrict__ offsets,
                                                             TileGeom g, int wrap, int variant,
                                                             int mesh_vec_ok,
                                                             const unsigned* __restrict__ wmax_bits,
-                                                            float* __restrict__ mesh) {
+                                                            float* __restrict__ mesh,
+                                                            const __grid_constant__ CUtensorMap tmap, int use_tma) {
   constexpr int L = TileDims<ORDER>::L, LP = TileDims<ORDER>::LP, NC = TileDims<ORDER>::CELLS;
-  extern __shared__ __align__(16) unsigned fx_smem[];
+  extern __shared__ __align__(128) unsigned fx_smem[];
   unsigned* lo = fx_smem;
   unsigned* hi = fx_smem + NC;
   const int t = blockIdx.x;
@@ -894,7 +995,8 @@ __global__ void __launch_bounds__(1024) paint_tile_fx_kernel(const float4* __res
   const int tz = t % g.nt, ty = (t / g.nt) % g.nt, tx = t / (g.nt * g.nt);
   const int ox = tx * TILE, oy = ty * TILE, oz = tz * TILE;
   const int n = g.n;
-  for (int i = threadIdx.x; i < 2 * NC; i += blockDim.x) fx_smem[i] = 0u;
+  static_assert((2 * NC) % 4 == 0, "tile words are zeroed 16 bytes at a time");
+  for (int i = threadIdx.x; i < (2 * NC) / 4; i += blockDim.x) reinterpret_cast<uint4*>(fx_smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   // power-of-two scale: 2^e >= max|w|  ->  |contribution| * 2^(31-e) <= 2^31 fits one 32-bit word
   float wmax = __uint_as_float(*wmax_bits);
   if (!(wmax > 0.0f) || !(wmax < 3.0e38f)) wmax = 1.0f;
@@ -912,21 +1014,34 @@ __global__ void __launch_bounds__(1024) paint_tile_fx_kernel(const float4* __res
   }
   __syncthreads();
 
-  // flush: fixed point -> float32 (one rounding), 16-byte vector reds where aligned
+  // fixed point -> float32 (one rounding), in place over the low words: lo[] becomes a dense float box
   const double inv_scale = (double)ldexpf(1.0f, e - 31);
+  float* ftile = reinterpret_cast<float*>(lo);
+  for (int i = threadIdx.x; i < NC; i += blockDim.x) {
+    const unsigned l = lo[i], h = hi[i];
+    float v = 0.0f;
+    if ((l | h) != 0u) v = (float)((double)(long long)(((unsigned long long)h << 32) | l) * inv_scale);
+    ftile[i] = v;
+  }
+  // whole box inside the mesh along y, z (and x for a full mesh; a slab's missing planes are clipped)?
+  const bool inside = (oz + LP <= n) && (oy + L <= n) && (g.nx != n || ox + L <= n);
+  if (use_tma && inside) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the TMA
+    __syncthreads();
+    if (threadIdx.x == 0) tma_reduce_add_3d(&tmap, ftile, oz, oy, ox);
+    return;
+  }
+  __syncthreads();
+
+  // per-thread flush: 16-byte vector reds where aligned (boundary tiles and meshes the TMA cannot take)
   const size_t n2 = (size_t)n * n;
   const bool vec_ok = (n % 4 == 0) && mesh_vec_ok;
   constexpr int NV = TILE / 4;
   // per row: NV aligned quads + ONE more quad for the halo tail [TILE, L) -- its padding cells
   // [L, LP) are zero in the tile, and adding +0.0 to the mesh is free, so the tail costs one vector
-  // red instead of order-1 scalar ones (the flush is a third of the kernel on sparse tiles)
+  // red instead of order-1 scalar ones
   constexpr int ROW_ITEMS = NV + 1;
   static_assert(LP == TILE + 4, "tail quad = cells [TILE, TILE + 4)");
-  auto cell = [&](int idx) -> float {
-    const unsigned l = lo[idx], h = hi[idx];
-    if ((l | h) == 0u) return 0.0f;
-    return (float)((double)(long long)(((unsigned long long)h << 32) | l) * inv_scale);
-  };
   for (int item = threadIdx.x; item < L * L * ROW_ITEMS; item += blockDim.x) {
     const int q = item % ROW_ITEMS;
     const int row = item / ROW_ITEMS;
@@ -936,18 +1051,17 @@ __global__ void __launch_bounds__(1024) paint_tile_fx_kernel(const float4* __res
     else if (gx >= g.nx) continue;                 // slab: ghost planes are part of the allocation
     const int gy = (oy + j) % n;
     float* grow = mesh + (size_t)gx * n2 + (size_t)gy * n;
-    const int tbase = (i * L + j) * LP;
     const int k = q * 4;
-    const float vx = cell(tbase + k), vy = cell(tbase + k + 1), vz = cell(tbase + k + 2), vw = cell(tbase + k + 3);
-    if (vx == 0.0f && vy == 0.0f && vz == 0.0f && vw == 0.0f) continue;
+    const float4 v = *reinterpret_cast<const float4*>(ftile + (i * L + j) * LP + k);
+    if (v.x == 0.0f && v.y == 0.0f && v.z == 0.0f && v.w == 0.0f) continue;
     const int gz = (oz + k) % n;
     if (vec_ok && gz + 3 < n) {
-      red_v4(grow + gz, vx, vy, vz, vw);
+      red_v4(grow + gz, v.x, v.y, v.z, v.w);
     } else {
-      if (vx != 0.0f) atomicAdd(grow + gz, vx);
-      if (vy != 0.0f) atomicAdd(grow + ((gz + 1) % n), vy);
-      if (vz != 0.0f) atomicAdd(grow + ((gz + 2) % n), vz);
-      if (vw != 0.0f) atomicAdd(grow + ((gz + 3) % n), vw);
+      if (v.x != 0.0f) atomicAdd(grow + gz, v.x);
+      if (v.y != 0.0f) atomicAdd(grow + ((gz + 1) % n), v.y);
+      if (v.z != 0.0f) atomicAdd(grow + ((gz + 2) % n), v.z);
+      if (v.w != 0.0f) atomicAdd(grow + ((gz + 3) % n), v.w);
     }
   }
 }
@@ -1093,7 +1207,12 @@ static int run_bucket_two_level(const PaintParams& p, const TileGeom& g, const S
   int gshift = 0;
   while (((nbuckets + (1 << gshift) - 1) >> gshift) > kMaxGroups) ++gshift;
   const int ngroups = (nbuckets + (1 << gshift) - 1) >> gshift;
-  const bool have_offsets = g.ntiles <= kSmemCountMaxTiles;     // tile histogram fits one SM's shared memory
+  // Tile offsets BEFORE the partition (the fine pass then reads its records once): from the per-SM
+  // shared-memory histogram when the tile table fits it, from global reds into the (L2-resident) table
+  // otherwise.  JPS_FINE_TWOPASS=1 restores round 1's big-mesh path (group histogram, fine pass reads twice).
+  static const bool two_pass = [] { const char* e = getenv("JPS_FINE_TWOPASS"); return e && atoi(e) != 0; }();
+  const bool smem_hist = g.ntiles <= kSmemCountMaxTiles;        // tile histogram fits one SM's shared memory
+  const bool have_offsets = smem_hist || !two_pass;
   if (have_offsets) {
     // tile-level histogram (shared-memory privatised) + scan -> offsets[]; group bases are a sample of it
     unsigned* counts = (unsigned*)(ws + L.counts);
@@ -1103,7 +1222,7 @@ static int run_bucket_two_level(const PaintParams& p, const TileGeom& g, const S
       JPS_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)(nbuckets + 1) * 4, s));
       JPS_CHECK_CUDA(cudaMemsetAsync(wmax_bits, 0, 4, s));
     }
-    {
+    if (smem_hist) {
       const int smem = (g.ntiles + 1) * (int)sizeof(unsigned);
       static PerDeviceFlag attr_set;
       if (!attr_set.get()) {
@@ -1115,6 +1234,10 @@ static int run_bucket_two_level(const PaintParams& p, const TileGeom& g, const S
       const int64_t w1 = (p.n_part + 1024 * BUCKET_UNROLL - 1) / (1024 * BUCKET_UNROLL);
       ScopedLaunch T(K_BUCKET_COUNT, s);
       bucket_count_smem_kernel<ORDER, REFCIC><<<(int)std::min<int64_t>(w1, kNumSMs), 1024, smem, s>>>(p, g, counts, wmax_bits);
+    } else {
+      const int64_t want = (p.n_part + 256 * 4 - 1) / (256 * 4);
+      ScopedLaunch T(K_BUCKET_COUNT, s);
+      bucket_count_global_kernel<ORDER, REFCIC><<<(int)std::min<int64_t>(want, (int64_t)kNumSMs * 8), 256, 0, s>>>(p, g, counts, wmax_bits);
     }
     JPS_CHECK_LAUNCH();
     {
@@ -1171,6 +1294,34 @@ static int run_bucket_two_level(const PaintParams& p, const TileGeom& g, const S
   return JPS_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// float32 mesh [nx][n][n] as a 3-D tensor (z fastest) with a [L][L][LP] box; false if the TMA cannot take it
+static bool make_mesh_tensor_map(CUtensorMap* tm, float* mesh, int n, int nx, int L, int LP) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc || n % 4 != 0 || ((uintptr_t)mesh & 15) != 0) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)n, (cuuint64_t)nx};
+  const cuuint64_t strides[2] = {(cuuint64_t)n * 4, (cuuint64_t)n * n * 4};     // bytes, dims 1 and 2
+  const cuuint32_t box[3] = {(cuuint32_t)LP, (cuuint32_t)L, (cuuint32_t)L};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, mesh, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // deposit a bucketed piece into the mesh on stream `s`
 template <int ORDER, bool REFCIC>
 static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayout& L, char* ws, cudaStream_t s) {
@@ -1196,8 +1347,13 @@ static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayo
       // PCS on sparse tiles 9.2 (256), 6.67 (384), 6.41 (512) ms; CIC flat between 320 and 512.
       static const int tpb_env = [] { const char* e = getenv("JPS_TILE_THREADS"); return e ? atoi(e) : 0; }();
       const int tpb = tpb_env > 0 ? tpb_env : (ORDER == 3 ? 384 : 512);
+      // JPS_TILE_FLUSH=red forces the per-thread red flush everywhere (A/B runs, tests)
+      static const bool no_tma = [] { const char* e = getenv("JPS_TILE_FLUSH"); return e && !strcmp(e, "red"); }();
+      CUtensorMap tmap;
+      memset(&tmap, 0, sizeof(tmap));
+      const int use_tma = (!no_tma && make_mesh_tensor_map(&tmap, p.mesh, g.n, g.nx, TileDims<ORDER>::L, TileDims<ORDER>::LP)) ? 1 : 0;
       paint_tile_fx_kernel<ORDER, REFCIC><<<g.ntiles, tpb, smem, s>>>(sorted, offsets, g, p.wrap, p.variant,
-                                                                    mesh_vec_ok, wmax_bits, p.mesh);
+                                                                    mesh_vec_ok, wmax_bits, p.mesh, tmap, use_tma);
     }
   }
   JPS_CHECK_LAUNCH();

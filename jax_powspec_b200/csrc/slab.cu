@@ -319,6 +319,63 @@ __global__ void __launch_bounds__(256) slab_pack_p2p_xfast_kernel(const float2* 
   }
 }
 
+// Same transposing peer-store with the TMA doing the remote writes (cp.async.bulk, shared -> global):
+// a CTA stages a TX (x) x 32 (kz) tile in shared memory in OUTPUT order [kz][x] (loads coalesced along
+// kz), then 32 lanes each hand ONE row -- TX * 8 bytes, contiguous along x in the peer's shard -- to the
+// bulk-copy engine.  The stores are asynchronous: with two tile buffers the loads of tile i+1 run while
+// the NVLink writes of tile i drain, every remote write is a 256/512-byte burst, and no thread waits on
+// a store.  (The plain kernel above issues 8-byte stores per thread and two barriers per 8 KB tile.)
+//   dst_q[((yl * nz) + kz) * n + rank * nxl + xl] = yz[(xl * n + q * nyl + yl) * nz + kz]
+__device__ __forceinline__ void bulk_store_row(void* gdst, const void* ssrc, unsigned bytes) {
+  const unsigned src = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(src), "r"(bytes) : "memory");
+}
+
+template <int TX>
+__global__ void __launch_bounds__(256) slab_pack_p2p_xfast_tma_kernel(const float2* __restrict__ yz,
+                                                                      void* const* __restrict__ peers, int n, int nz,
+                                                                      int nxl, int nyl, int nranks, int rank,
+                                                                      int x_begin, int x_count) {
+  constexpr int TZ = 32, PITCH = TX + 2;               // pitch: rows stay 16-byte aligned, 2-way bank conflicts at most
+  __shared__ __align__(128) float2 tile[2][TZ][PITCH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ntx = x_count / TX, ntz = (nz + TZ - 1) / TZ;
+  const long long ntiles = (long long)n * ntx * ntz;                 // over all y = q * nyl + yl
+  int it = 0;
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    // consecutive CTAs take consecutive y -> different yl of the same peer, then the next peer
+    const int y = (int)(t % n);
+    const long long rest = t / n;
+    const int bz = (int)(rest % ntz), bx = (int)(rest / ntz);
+    const int q = y / nyl, yl = y % nyl;
+    const int xl0 = x_begin + bx * TX, kz0 = bz * TZ;
+    const int b = it & 1;
+    // buffer b was handed to the bulk engine two tiles ago: wait until it has been READ (one younger group may be in flight)
+    if (warp == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncthreads();
+    const int kz = kz0 + lane;
+    constexpr int ROWS = TX / 8;                                     // x rows per warp
+    float2 v[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+      const int xl = xl0 + warp + 8 * i;
+      v[i] = (kz < nz) ? __ldg(yz + ((size_t)xl * n + y) * nz + kz) : make_float2(0.0f, 0.0f);
+    }
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) tile[b][lane][warp + 8 * i] = v[i];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // these writes -> visible to the bulk-copy engine
+    __syncthreads();
+    if (warp == 0) {
+      if (kz < nz) {
+        float2* dst = reinterpret_cast<float2*>(peers[q]) + ((size_t)yl * nz + kz) * n + (size_t)rank * nxl + xl0;
+        bulk_store_row(dst, &tile[b][lane][0], TX * (unsigned)sizeof(float2));
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");      // every lane commits (possibly empty) groups in step
+    }
+  }
+  if (warp == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all writes performed before the grid retires
+}
+
 // Fused pack + all-to-all over NVLink peer memory: block q of this rank's yz-transformed planes is
 // written DIRECTLY into rank q's receive buffer (peer pointers obtained through CUDA IPC on the host
 // side), at the slot of this rank -- no packed send buffer, no NCCL copy kernels.  One launch moves
@@ -551,7 +608,20 @@ extern "C" int jps_slab_pack_p2p_planes(jps_slab_plan_t* p, const void* yz, void
     // quarter of the SMs' worth of CTAs keeps the links busy without starving cuFFT
     static const int per_sm_env = [] { const char* e = getenv("JPS_PACK_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
     const long long cap = (x_count == p->nxl) ? (long long)kNumSMs * 8 : (long long)kNumSMs * (per_sm_env > 0 ? per_sm_env : 2);
-    if (p->xfast) {
+    // JPS_PACK_KERNEL=ldst forces the plain load/store transposing kernel (A/B runs)
+    static const bool no_tma = [] { const char* e = getenv("JPS_PACK_KERNEL"); return e && !strcmp(e, "ldst"); }();
+    static const int tma_ctas = [] { const char* e = getenv("JPS_PACK_TMA_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+    if (p->xfast && !no_tma && x_count % 32 == 0 && p->nxl % 2 == 0 && p->n % 2 == 0) {
+      const int tx = (x_count % 64 == 0) ? 64 : 32;
+      const long long ntiles = (long long)p->n * (x_count / tx) * ((p->nz + 31) / 32);
+      const int blocks = (int)std::min<long long>(ntiles, (long long)kNumSMs * (tma_ctas > 0 ? tma_ctas : 2));
+      if (tx == 64)
+        slab_pack_p2p_xfast_tma_kernel<64><<<blocks, 256, 0, s>>>((const float2*)yz, p->peer_dev, p->n, p->nz, p->nxl, p->nyl,
+                                                                 p->nranks, p->rank, x_begin, x_count);
+      else
+        slab_pack_p2p_xfast_tma_kernel<32><<<blocks, 256, 0, s>>>((const float2*)yz, p->peer_dev, p->n, p->nz, p->nxl, p->nyl,
+                                                                 p->nranks, p->rank, x_begin, x_count);
+    } else if (p->xfast) {
       const long long ntiles = (long long)p->n * ((x_count + 31) / 32) * ((p->nz + 31) / 32);
       slab_pack_p2p_xfast_kernel<<<(int)std::min<long long>(ntiles, cap * 4), 256, 0, s>>>(
           (const float2*)yz, p->peer_dev, p->n, p->nz, p->nxl, p->nyl, p->nranks, p->rank, x_begin, x_count);

@@ -109,7 +109,7 @@ def check_particles(x, y, z, w, device):
             raise TypeError(f"{name} must be a torch tensor (got {type(t).__name__}); use paint()/paint_powspec() for NumPy input")
         if t.dtype != torch.float32:
             raise TypeError(f"{name} must be float32 (got {t.dtype})")
-        if not t.is_cuda or t.device != device:
+        if not t.is_cuda or (device.index is not None and t.device.index != device.index):
             raise ValueError(f"{name} lives on {t.device}, the pipeline on {device}")
         if t.dim() != 1:
             raise ValueError(f"{name} must be 1-d (got shape {tuple(t.shape)})")

@@ -154,9 +154,14 @@ class SlabPipeline:
         # 1-D transforms (2048^3: 93.6 ms of FFT against ~55 ms) and the 8-fold binning kernel.
         self.local = None
         if self.single and rank is None:
-            self.local = PaintPowspec(self.n, self.box, self.edges, order=self.order, compat=self.compat,
-                                      method=self.method, shot_noise=self.shot_noise, wrap=self.wrap,
-                                      device=self.device)
+            try:
+                self.local = PaintPowspec(self.n, self.box, self.edges, order=self.order, compat=self.compat,
+                                          method=self.method, shot_noise=self.shot_noise, wrap=self.wrap,
+                                          device=self.device)
+            except (_lib.JpsError, torch.OutOfMemoryError) as e:     # 3-D plan does not fit: 2-D + 1-D transforms below
+                self.local, self._local_error = None, repr(e)
+                torch.cuda.empty_cache()
+        if self.local is not None:
             self.transport, self.xfast, self.handle = "local", False, None
             self.mesh, self.k3d, self.pk, self.nm = self.local.mesh, self.local.k3d, self.local.pk, self.local.nm
             self.gl = self.gh = 0
@@ -298,6 +303,11 @@ class SlabPipeline:
         check(lib.jps_slab_fft_yz(self.handle, ptr(self.owned()), ptr(self.buf_a), stream_ptr()), "jps_slab_fft_yz")
         if not self.single:
             check(lib.jps_slab_pack(self.handle, ptr(self.buf_a), ptr(self.buf_b), stream_ptr()), "jps_slab_pack")
+
+    def stage_fft_yz_only(self):
+        """The batched 2-D R2C of the owned planes alone (bench.py: what the transfer has to hide behind)."""
+        out = self.buf_a if self.buf_b is None else self.buf_b
+        check(lib.jps_slab_fft_yz(self.handle, ptr(self.owned()), ptr(out), stream_ptr()), "jps_slab_fft_yz")
 
     def stage_fft_yz_p2p(self):
         """2-D FFT into the local buffer, then ONE kernel that writes every destination's block straight

@@ -56,18 +56,24 @@ def paint(mesh, x, y, z, w, xmin, ymin, zmin, box_size, n_bins, wrap=True, *, or
     return out
 
 
-def powspec(delta, box_size, k_edges, *, mas_order=2, workers=-1):
-    """rfftn (scipy, all cores) + serial float32 binning.  Returns (k3D, Pk3D f32[nb,3], Nmodes f32)."""
+def powspec(delta, box_size, k_edges, *, mas_order=2, workers=-1, times=None):
+    """rfftn (scipy, all cores) + serial float32 binning.  Returns (k3D, Pk3D f32[nb,3], Nmodes f32).
+    ``times`` (a dict) receives the wall time of the two parts: fft_s, bin_s."""
+    import time
     delta = np.ascontiguousarray(delta, dtype=F32)
     n = delta.shape[0]
+    t0 = time.perf_counter()
     dk = sfft.rfftn(delta, workers=workers).astype(np.complex64, copy=False)
     dk = np.ascontiguousarray(dk)
+    t1 = time.perf_counter()
     kedges = grid_edges(k_edges, box_size)
     nb = len(kedges) - 1
     s0, s2, s4, cnt = (np.zeros(nb, F32) for _ in range(4))
     rc = lib().jpso_pk_bin(_p(dk.view(F32)), n, _p(kedges), nb, int(mas_order), _p(s0), _p(s2), _p(s4), _p(cnt))
     if rc != 0:
         raise RuntimeError("C oracle binning failed")
+    if times is not None:
+        times["fft_s"], times["bin_s"] = t1 - t0, time.perf_counter() - t1
     vol = (F32(box_size) / F32(n * n)) ** 3
     with np.errstate(invalid="ignore", divide="ignore"):
         pk = np.stack([s0 / cnt * vol, s2 / cnt * F32(5.0) * vol, s4 / cnt * F32(9.0) * vol], axis=1)
