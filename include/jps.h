@@ -83,6 +83,11 @@ extern "C" {
 /* plan flags */
 #define JPS_PLAN_DEFAULT      0
 #define JPS_PLAN_TABLES_ONLY  1   /* bin tables + accumulators only: no 3-D FFT plans, no delta_k buffer */
+#define JPS_PLAN_FFT_PENCIL   2   /* forward transform as three contiguous batched 1-D cuFFT passes with two
+                                     transposing kernels in between (spectrum left as [kz][ky][kx]); for big
+                                     meshes (2048^3: the monolithic 3-D plan needs 93 ms, this ~60).  Such a
+                                     plan serves jps_powspec / jps_paint_powspec only; it holds a second
+                                     delta_k-sized buffer (n_shell_fields must be 0). */
 
 typedef struct jps_plan jps_plan_t;
 typedef struct jps_slab_plan jps_slab_plan_t;

@@ -17,6 +17,7 @@ COMPAT_REFERENCE, COMPAT_FIXED = 0, 1
 VARIANT_VEC, VARIANT_SCAN = 0, 1
 PAINT_AUTO, PAINT_ATOMIC, PAINT_SORTED = 0, 1, 2
 PK_HERMITIAN = 1
+PLAN_TABLES_ONLY, PLAN_FFT_PENCIL = 1, 2
 
 COMPAT = {"reference": COMPAT_REFERENCE, "fixed": COMPAT_FIXED}
 METHOD = {"auto": PAINT_AUTO, "atomic": PAINT_ATOMIC, "sorted": PAINT_SORTED}

@@ -285,7 +285,10 @@ class PaintPowspec:
     weights are read with stride 1, strided views are made contiguous."""
 
     def __init__(self, n_mesh, box_size, k_edges, *, order=2, compat="fixed", method="auto",
-                 n_part_max=0, shot_noise=0.0, wrap=True, device=None, plan=None):
+                 n_part_max=0, shot_noise=0.0, wrap=True, device=None, plan=None, fft="auto"):
+        """fft: "3d" = one monolithic cuFFT 3-D R2C plan; "pencil" = three contiguous batched 1-D passes with
+        transposing kernels in between (JPS_PLAN_FFT_PENCIL; a second delta_k-sized buffer); "auto" = pencil
+        from 1024^3 up, where the 3-D plan falls to a third of the HBM roofline (env JPS_FFT overrides)."""
         self.device = device or require_cuda()
         self.n = int(n_mesh)
         self.box = float(box_size)
@@ -293,7 +296,16 @@ class PaintPowspec:
         self.nb = self.edges.size - 1
         self.order, self.compat, self.method = int(order), compat, method
         self.wrap, self.shot_noise = bool(wrap), float(shot_noise)
-        self.plan = plan if plan is not None else Plan(self.n, 0, self.device)
+        import os
+        fft = os.environ.get("JPS_FFT", fft)
+        if fft not in ("auto", "3d", "pencil"):
+            raise ValueError("fft must be 'auto', '3d' or 'pencil'")
+        self.fft = ("pencil" if self.n >= 1024 else "3d") if fft == "auto" else fft
+        if plan is not None:
+            self.plan = plan
+            self.fft = "pencil" if (plan.flags & _lib.PLAN_FFT_PENCIL) else "3d"
+        else:
+            self.plan = Plan(self.n, 0, self.device, _lib.PLAN_FFT_PENCIL if self.fft == "pencil" else 0)
         d = self.device
         self.mesh = torch.empty((self.n,) * 3, dtype=torch.float32, device=d)
         self.k3d = torch.empty(self.nb, dtype=torch.float32, device=d)

@@ -91,6 +91,7 @@ enum KernelId {
   K_MOCK_FIELD,
   K_MOCK_POPULATE,
   K_INTERLACE,
+  K_TRANSPOSE,
   K_NUM
 };
 
@@ -158,6 +159,12 @@ struct jps_plan {
   bool c2r_ok = false;
   cufftHandle r2c_ip = 0;       // forward transform IN PLACE on a shell field (estimator gradients);
   bool r2c_ip_ok = false;       // only when the plan has shell fields
+  // JPS_PLAN_FFT_PENCIL: three contiguous batched 1-D plans + a second delta_k-sized buffer; the
+  // spectrum ends in `dk` as [kz][ky][kx] (x fastest)
+  bool pencil = false;
+  cufftHandle fz = 0, fy = 0, fx = 0;
+  bool fz_ok = false, fy_ok = false, fx_ok = false;
+  float2* dk2 = nullptr;
 
   // workspace partition (all device pointers inside the caller's workspace)
   char* ws = nullptr;
@@ -190,6 +197,11 @@ int ensure_bin_table(jps_plan* plan, const float* kedges_grid, int nb, int mode,
                      BinTable** out);
 int64_t edge_threshold(float e, bool strict, int64_t k2max);
 int forward_fft(jps_plan* plan, const float* mesh, cudaStream_t s);
+// slab.cu: fold +-kx / window / Legendre weights / k-bin sums of a spectrum stored x-fastest, into
+// tables->acc (zeroed first).  kz_major = 0: dk[yl][kz][x] (y-shard [y0, y0 + nyl) of a slab rank);
+// kz_major = 1: dk[kz][yl][x] (the pencil plan's layout, nyl = n, y0 = 0).  dc: device Re rho_hat(0).
+int bin_xfast_layout(jps_plan* tables, const float2* dk, int nyl, int y0, int kz_major, const BinTable& T,
+                     const float* dc, int normalise, int mas_order, cudaStream_t s);
 double ref_volume(float box_size, int n);
 float ref_kF(float box_size);
 

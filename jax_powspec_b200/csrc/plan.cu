@@ -21,7 +21,7 @@ static const char* kKernelNames[K_NUM] = {
     "paint_atomic", "bucket_count", "bucket_scan", "bucket_scatter", "bucket_fine", "paint_tile", "pk_fold_bin",
     "pk_count_modes", "pk_finalize", "cufft_r2c", "cufft_c2r", "memset", "shell_filter",
     "triple_reduce", "xi_bin", "misc", "text_index", "text_parse", "text_compact",
-    "mock_field", "mock_populate", "interlace_combine"};
+    "mock_field", "mock_populate", "interlace_combine", "fft_transpose"};
 
 // Distinct plans may be driven from distinct host threads (include/jps.h), so the process-wide
 // accounting is atomic counters + one mutex around the event lists.
@@ -100,12 +100,13 @@ struct TableLayout {
 };
 
 struct Layout {
-  size_t dk, fft_work, wlut, acc, scal, isum, shell, total;
+  size_t dk, dk2, fft_work, wlut, acc, scal, isum, shell, total;
   TableLayout t[kNumTables];
   int cap;
 };
 
-static Layout make_layout(int n, int pitch, size_t fft_work_bytes, int n_shell_fields, bool tables_only = false) {
+static Layout make_layout(int n, int pitch, size_t fft_work_bytes, int n_shell_fields, bool tables_only = false,
+                          bool pencil = false) {
   Layout L;
   const int mid = n / 2;
   const int64_t k2max = 3LL * mid * mid;
@@ -113,6 +114,7 @@ static Layout make_layout(int n, int pitch, size_t fft_work_bytes, int n_shell_f
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   L.dk = take(tables_only ? 0 : (size_t)n * n * pitch * sizeof(float2));
+  L.dk2 = take(pencil ? (size_t)n * n * pitch * sizeof(float2) : 0);
   L.fft_work = take(fft_work_bytes);
   for (int i = 0; i < kNumTables; ++i) {
     L.t[i].lut = take((size_t)(k2max + 1) * 4);
@@ -165,6 +167,25 @@ static int make_r2c_inplace(int n, int pitch, cufftHandle* h, size_t* work) {
   return JPS_OK;
 }
 
+// contiguous batched 1-D plans of the pencil decomposition
+static int make_pencil_z(int n, int pitch, cufftHandle* h, size_t* work) {          // R2C, n*n lines of n reals
+  JPS_CHECK_CUFFT(cufftCreate(h));
+  JPS_CHECK_CUFFT(cufftSetAutoAllocation(*h, 0));
+  long long dims[1] = {n};
+  long long inembed[1] = {n}, onembed[1] = {pitch};
+  JPS_CHECK_CUFFT(cufftMakePlanMany64(*h, 1, dims, inembed, 1, n, onembed, 1, pitch, CUFFT_R2C, (long long)n * n, work));
+  return JPS_OK;
+}
+
+static int make_pencil_c2c(int n, long long batch, cufftHandle* h, size_t* work) {   // C2C, `batch` lines of n
+  JPS_CHECK_CUFFT(cufftCreate(h));
+  JPS_CHECK_CUFFT(cufftSetAutoAllocation(*h, 0));
+  long long dims[1] = {n};
+  long long embed[1] = {n};
+  JPS_CHECK_CUFFT(cufftMakePlanMany64(*h, 1, dims, embed, 1, n, embed, 1, n, CUFFT_C2C, batch, work));
+  return JPS_OK;
+}
+
 static int pitch_for(int n) { return n / 2 + 1; }
 
 }  // namespace jps
@@ -209,6 +230,18 @@ extern "C" int jps_plan_workspace_bytes(int n_mesh, int n_shell_fields, int flag
   }
   cufftHandle h;
   size_t w1 = 0, w2 = 0;
+  if (flags & JPS_PLAN_FFT_PENCIL) {
+    JPS_REQUIRE(n_shell_fields == 0, "jps_plan_workspace_bytes: a JPS_PLAN_FFT_PENCIL plan has no shell fields");
+    size_t wz = 0, wy = 0;
+    int rcp = make_pencil_z(n_mesh, pitch, &h, &wz);
+    cufftDestroy(h);
+    if (rcp) return rcp;
+    rcp = make_pencil_c2c(n_mesh, (long long)n_mesh * pitch, &h, &wy);
+    cufftDestroy(h);
+    if (rcp) return rcp;
+    *bytes = make_layout(n_mesh, pitch, std::max(wz, wy), 0, false, true).total;
+    return JPS_OK;
+  }
   int rc = make_r2c(n_mesh, pitch, &h, &w1);
   cufftDestroy(h);
   if (rc) return rc;
@@ -243,7 +276,24 @@ extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* 
   if (ce != cudaSuccess) { delete p; set_error("jps_plan_create: cudaGetDevice failed: %s", cudaGetErrorString(ce)); return JPS_ERR_CUDA; }
   size_t w1 = 0, w2 = 0, w3 = 0;
   int rc = JPS_OK;
-  if (!tables_only) {
+  const bool pencil = (flags & JPS_PLAN_FFT_PENCIL) != 0;
+  if (pencil) {
+    if (tables_only || n_shell_fields != 0) {
+      delete p;
+      set_error("jps_plan_create: JPS_PLAN_FFT_PENCIL excludes JPS_PLAN_TABLES_ONLY and shell fields");
+      return JPS_ERR_INVALID;
+    }
+    p->pencil = true;
+    rc = make_pencil_z(n_mesh, p->pitch, &p->fz, &w1);
+    if (rc) { delete p; return rc; }
+    p->fz_ok = true;
+    rc = make_pencil_c2c(n_mesh, (long long)n_mesh * p->pitch, &p->fy, &w2);
+    if (rc) { jps_plan_destroy(p); return rc; }
+    p->fy_ok = true;
+    rc = make_pencil_c2c(n_mesh, (long long)n_mesh * p->pitch, &p->fx, &w3);
+    if (rc) { jps_plan_destroy(p); return rc; }
+    p->fx_ok = true;
+  } else if (!tables_only) {
     rc = make_r2c(n_mesh, p->pitch, &p->r2c, &w1);
     if (rc) { delete p; return rc; }
     p->r2c_ok = true;
@@ -256,7 +306,7 @@ extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* 
       p->r2c_ip_ok = true;
     }
   }
-  Layout L = make_layout(n_mesh, p->pitch, std::max(std::max(w1, w2), w3), n_shell_fields, tables_only);
+  Layout L = make_layout(n_mesh, p->pitch, std::max(std::max(w1, w2), w3), n_shell_fields, tables_only, pencil);
   if (workspace_bytes < L.total) {
     set_error("jps_plan_create: workspace has %zu bytes, %zu needed", workspace_bytes, L.total);
     jps_plan_destroy(p);
@@ -266,6 +316,7 @@ extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* 
   p->ws = ws;
   p->ws_bytes = workspace_bytes;
   p->dk = (float2*)(ws + L.dk);
+  p->dk2 = pencil ? (float2*)(ws + L.dk2) : nullptr;
   p->fft_work = ws + L.fft_work;
   p->fft_work_bytes = std::max(std::max(w1, w2), w3);
   for (int i = 0; i < kNumTables; ++i) {
@@ -285,7 +336,11 @@ extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* 
   p->shell = (float*)(ws + L.shell);
   p->acc_cap = L.cap;
   cufftResult r = CUFFT_SUCCESS;
-  if (!tables_only) {
+  if (pencil) {
+    r = cufftSetWorkArea(p->fz, p->fft_work);
+    if (r == CUFFT_SUCCESS) r = cufftSetWorkArea(p->fy, p->fft_work);
+    if (r == CUFFT_SUCCESS) r = cufftSetWorkArea(p->fx, p->fft_work);
+  } else if (!tables_only) {
     r = cufftSetWorkArea(p->r2c, p->fft_work);
     if (r == CUFFT_SUCCESS) r = cufftSetWorkArea(p->c2r, p->fft_work);
     if (r == CUFFT_SUCCESS && p->r2c_ip_ok) r = cufftSetWorkArea(p->r2c_ip, p->fft_work);
@@ -313,6 +368,9 @@ extern "C" int jps_plan_destroy(jps_plan_t* p) {
   if (p->r2c_ok) cufftDestroy(p->r2c);
   if (p->c2r_ok) cufftDestroy(p->c2r);
   if (p->r2c_ip_ok) cufftDestroy(p->r2c_ip);
+  if (p->fz_ok) cufftDestroy(p->fz);
+  if (p->fy_ok) cufftDestroy(p->fy);
+  if (p->fx_ok) cufftDestroy(p->fx);
   delete p;
   return JPS_OK;
 }

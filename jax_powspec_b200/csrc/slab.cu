@@ -19,9 +19,19 @@
 #include <cmath>
 
 constexpr int kMaxRanks = 64;
-constexpr int kSlabChunks = 4;
+// Pieces the owned planes are cut into for the FFT / transfer overlap: the 2-D transform of piece c+1 runs
+// while the peer stores of piece c drain, so only the FIRST piece's transform is exposed.  8 pieces of 32
+// planes at 2048^3 on 8 GPUs (JPS_SLAB_CHUNKS overrides; round 1 used 4).
+static int slab_chunks() {
+  static const int k = [] { const char* e = getenv("JPS_SLAB_CHUNKS"); const int v = e ? atoi(e) : 0; return v >= 1 ? v : 8; }();
+  return k;
+}
 
-static int chunk_planes_for(int nxl) { return (nxl % kSlabChunks == 0 && nxl / kSlabChunks >= 2) ? nxl / kSlabChunks : 0; }
+static int chunk_planes_for(int nxl) {
+  for (int k = slab_chunks(); k >= 2; k >>= 1)
+    if (nxl % k == 0 && nxl / k >= 2) return nxl / k;
+  return 0;
+}
 
 struct jps_slab_plan {
   int n = 0, nz = 0, nranks = 1, rank = 0, nxl = 0, nyl = 0;
@@ -90,6 +100,7 @@ struct SlabPkParams {
   double* acc;           // [nbc][4]
   const float* dc;       // device: Re rho_hat(k=0) (used when normalise)
   int normalise;
+  int kz_major;          // x-fast kernel only: 0 = dk[yl][kz][x], 1 = dk[kz][yl][x]
 };
 
 // One warp per (a = |kx|, local y): folds the rows ix = a and ix = n-a, lanes along kz.
@@ -212,7 +223,8 @@ __global__ void __launch_bounds__(256) pk_bin_xfast_kernel(SlabPkParams P) {
   const int n = P.n, nz = P.nz, mid = n / 2;
   const long long items = (long long)P.nyl * nz;
   for (long long it = (long long)blockIdx.x * nwarps + warp; it < items; it += (long long)gridDim.x * nwarps) {
-    const int yl = (int)(it / nz), kz = (int)(it % nz);
+    const int yl = P.kz_major ? (int)(it % P.nyl) : (int)(it / nz);
+    const int kz = P.kz_major ? (int)(it / P.nyl) : (int)(it % nz);
     const int iy = P.y0 + yl;
     const int ky = iy > mid ? iy - n : iy;
     const float2* r = P.dk + (size_t)it * n;
@@ -431,6 +443,64 @@ __global__ void slab_finalize_kernel(int nb, const float* __restrict__ edges, co
   k3d[j] = (0.5f * (edges[j + 1] + edges[j])) * kF;
 }
 
+// Launch of the y-sharded / x-fast binning kernels on one spectrum shard (accumulators zeroed first).
+static int bin_layout(jps_plan* tp, const float2* dk, int nyl, int y0, int xfast, int kz_major, const BinTable& T,
+                      const float* dc, int normalise, int mas_order, cudaStream_t s) {
+  {
+    ScopedLaunch L(K_MEMSET, s);
+    JPS_CHECK_CUDA(cudaMemsetAsync(tp->acc, 0, (size_t)std::max(T.nbc, 1) * 4 * 8, s));
+  }
+  if (T.nbc == 0) return JPS_OK;
+  SlabPkParams P;
+  P.dk = dk; P.n = tp->n; P.nz = tp->nz; P.nyl = nyl; P.y0 = y0;
+  P.lut = T.lut; P.wl = tp->wlut + (size_t)(mas_order - 2) * tp->n; P.nbc = T.nbc; P.acc = tp->acc;
+  P.dc = dc; P.normalise = normalise; P.kz_major = kz_major;
+  const int threads = 256, warps = 8;
+  const long long items = xfast ? (long long)nyl * tp->nz : (long long)(tp->n / 2 + 1) * nyl;
+  const long long want = (items + warps - 1) / warps;
+  static PerDeviceFlag attr_set;
+  if (!attr_set.get()) {
+    const int sw = (int)((size_t)warps * kMaxSmemBins * 3 * sizeof(float));
+    const int sb = (int)((size_t)kMaxBlockBins * 3 * sizeof(float));
+    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw));
+    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw));
+    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    attr_set.set();
+  }
+  using KernelFn = void (*)(SlabPkParams);
+  KernelFn fn;
+  size_t smem = 0;
+  long long cap_per_sm = 0;
+  if (T.nbc <= kMaxSmemBins) {
+    fn = xfast ? pk_bin_xfast_kernel<ACC_WARP> : pk_bin_ysharded_kernel<ACC_WARP>;
+    smem = (size_t)warps * T.nbc * 3 * sizeof(float);
+  } else if (T.nbc <= kMaxBlockBins) {
+    fn = xfast ? pk_bin_xfast_kernel<ACC_BLOCK> : pk_bin_ysharded_kernel<ACC_BLOCK>;
+    smem = (size_t)T.nbc * 3 * sizeof(float);
+  } else {
+    fn = xfast ? pk_bin_xfast_kernel<ACC_GLOBAL> : pk_bin_ysharded_kernel<ACC_GLOBAL>;
+    cap_per_sm = 8;
+  }
+  if (!cap_per_sm) {
+    int per_sm = 1;
+    JPS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
+    cap_per_sm = std::max(per_sm, 1);
+  }
+  const int blocks = (int)std::min<long long>(want, (long long)kNumSMs * cap_per_sm);
+  {
+    ScopedLaunch L(K_PK_FOLD_BIN, s);
+    fn<<<blocks, threads, smem, s>>>(P);
+  }
+  JPS_CHECK_LAUNCH();
+  return JPS_OK;
+}
+
+int bin_xfast_layout(jps_plan* tables, const float2* dk, int nyl, int y0, int kz_major, const BinTable& T,
+                     const float* dc, int normalise, int mas_order, cudaStream_t s) {
+  return bin_layout(tables, dk, nyl, y0, 1, kz_major, T, dc, normalise, mas_order, s);
+}
+
 static size_t tables_bytes(int n) {
   size_t b = 0;
   return jps_plan_workspace_bytes(n, 0, JPS_PLAN_TABLES_ONLY, &b) == JPS_OK ? b : 0;
@@ -611,7 +681,7 @@ extern "C" int jps_slab_pack_p2p_planes(jps_slab_plan_t* p, const void* yz, void
     // JPS_PACK_KERNEL=ldst forces the plain load/store transposing kernel (A/B runs)
     static const bool no_tma = [] { const char* e = getenv("JPS_PACK_KERNEL"); return e && !strcmp(e, "ldst"); }();
     static const int tma_ctas = [] { const char* e = getenv("JPS_PACK_TMA_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
-    if (p->xfast && !no_tma && x_count % 32 == 0 && p->nxl % 2 == 0 && p->n % 2 == 0) {
+    if (p->xfast && !no_tma && x_count % 32 == 0 && x_begin % 2 == 0 && p->nxl % 2 == 0 && p->n % 2 == 0) {
       const int tx = (x_count % 64 == 0) ? 64 : 32;
       const long long ntiles = (long long)p->n * (x_count / tx) * ((p->nz + 31) / 32);
       const int blocks = (int)std::min<long long>(ntiles, (long long)kNumSMs * (tma_ctas > 0 ? tma_ctas : 2));
@@ -693,54 +763,8 @@ extern "C" int jps_slab_powspec_partial(jps_slab_plan_t* p, const void* dk, cons
   BinTable* T = nullptr;
   int rc = ensure_bin_table(tp, kg.data(), nb, TABLE_PK_EDGES, s, &T);
   if (rc) return rc;
-  {
-    ScopedLaunch L(K_MEMSET, s);
-    JPS_CHECK_CUDA(cudaMemsetAsync(tp->acc, 0, (size_t)std::max(T->nbc, 1) * 4 * 8, s));
-  }
-  if (T->nbc > 0) {
-    SlabPkParams P;
-    P.dk = (const float2*)dk; P.n = p->n; P.nz = p->nz; P.nyl = p->nyl; P.y0 = p->rank * p->nyl;
-    P.lut = T->lut; P.wl = tp->wlut + (size_t)(mas_order - 2) * p->n; P.nbc = T->nbc; P.acc = tp->acc;
-    P.dc = dc; P.normalise = normalise;
-    const int threads = 256, warps = 8;
-    const long long items = p->xfast ? (long long)p->nyl * p->nz : (long long)(p->n / 2 + 1) * p->nyl;
-    const long long want = (items + warps - 1) / warps;
-    static PerDeviceFlag attr_set;
-    if (!attr_set.get()) {
-      const int sw = (int)((size_t)warps * kMaxSmemBins * 3 * sizeof(float));
-      const int sb = (int)((size_t)kMaxBlockBins * 3 * sizeof(float));
-      JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw));
-      JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-      JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw));
-      JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-      attr_set.set();
-    }
-    using KernelFn = void (*)(SlabPkParams);
-    KernelFn fn;
-    size_t smem = 0;
-    long long cap_per_sm = 0;
-    if (T->nbc <= kMaxSmemBins) {
-      fn = p->xfast ? pk_bin_xfast_kernel<ACC_WARP> : pk_bin_ysharded_kernel<ACC_WARP>;
-      smem = (size_t)warps * T->nbc * 3 * sizeof(float);
-    } else if (T->nbc <= kMaxBlockBins) {
-      fn = p->xfast ? pk_bin_xfast_kernel<ACC_BLOCK> : pk_bin_ysharded_kernel<ACC_BLOCK>;
-      smem = (size_t)T->nbc * 3 * sizeof(float);
-    } else {
-      fn = p->xfast ? pk_bin_xfast_kernel<ACC_GLOBAL> : pk_bin_ysharded_kernel<ACC_GLOBAL>;
-      cap_per_sm = 8;
-    }
-    if (!cap_per_sm) {
-      int per_sm = 1;
-      JPS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
-      cap_per_sm = std::max(per_sm, 1);
-    }
-    const int blocks = (int)std::min<long long>(want, (long long)kNumSMs * cap_per_sm);
-    {
-      ScopedLaunch L(K_PK_FOLD_BIN, s);
-      fn<<<blocks, threads, smem, s>>>(P);
-    }
-    JPS_CHECK_LAUNCH();
-  }
+  rc = bin_layout(tp, (const float2*)dk, p->nyl, p->rank * p->nyl, p->xfast ? 1 : 0, 0, *T, dc, normalise, mas_order, s);
+  if (rc) return rc;
   {
     ScopedLaunch L(K_PK_FINALIZE, s);
     slab_expand_kernel<<<(nb + 127) / 128, 128, 0, s>>>(nb, T->bin_to_compact, tp->acc, T->cnt, sums, counts);

@@ -29,19 +29,20 @@ def ptr(t) -> C.c_void_p:
 class Plan:
     """Owns the workspace tensor and the jps_plan_t* built on it."""
 
-    def __init__(self, n_mesh: int, n_shell_fields: int, device: torch.device):
+    def __init__(self, n_mesh: int, n_shell_fields: int, device: torch.device, flags: int = 0):
         self.n = int(n_mesh)
         self.n_shell_fields = int(n_shell_fields)
         self.device = device
+        self.flags = int(flags)
         nbytes = C.c_size_t(0)
         with torch.cuda.device(device):
-            check(lib.jps_plan_workspace_bytes(self.n, self.n_shell_fields, 0, C.byref(nbytes)),
+            check(lib.jps_plan_workspace_bytes(self.n, self.n_shell_fields, self.flags, C.byref(nbytes)),
                   "jps_plan_workspace_bytes")
             self.workspace = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=device)
             base = self.workspace.data_ptr()
             aligned = (base + 255) // 256 * 256
             handle = C.c_void_p(0)
-            check(lib.jps_plan_create(self.n, self.n_shell_fields, 0, C.c_void_p(aligned),
+            check(lib.jps_plan_create(self.n, self.n_shell_fields, self.flags, C.c_void_p(aligned),
                                       C.c_size_t(nbytes.value), C.byref(handle)), "jps_plan_create")
         self.handle = handle
         self.workspace_bytes = nbytes.value

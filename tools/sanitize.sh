@@ -9,6 +9,12 @@ mkdir -p gpurun_out
 SAN=/usr/local/cuda/bin/compute-sanitizer
 SEL='test_known_answers or test_translation_by_whole_cells or test_plane_wave_known_answer or test_golden_bispec or test_populate_device_in_device_out_and_empty or test_golden_gaussian_field or test_interlacing_leaves_a_band_limited_field_alone'
 for tool in memcheck racecheck; do
+  timeout 600 $SAN --tool $tool --error-exitcode 99 --print-limit 20 python tools/sanitize_paint.py \
+      > gpurun_out/sanitize_paint_$tool.log 2>&1
+  echo "$tool exit code $?" >> gpurun_out/sanitize_paint_$tool.log
+  tail -6 gpurun_out/sanitize_paint_$tool.log
+done
+for tool in memcheck racecheck; do
   timeout 400 $SAN --tool $tool --error-exitcode 99 --print-limit 20 \
       python -m pytest tests -m gpu -q -x -p no:cacheprovider -k "$SEL" \
       > gpurun_out/sanitize_$tool.log 2>&1
