@@ -677,6 +677,16 @@ def run_c4_arm(a, wl):
     h2d = 3 * nloc * 4 * world
     d2h = int(sum(np.asarray(o).nbytes for o in out)) * world
     e2e_pk_first = [float(v) for v in out[1][:3, 0]]
+    # the copies ALONE, all ranks at once: the host-side ceiling of this box for the e2e number
+    stage = torch.empty(nloc, dtype=torch.float32, device=dev)
+    sync()
+    e0.record()
+    for h in (xh, yh, zh):
+        stage.copy_(h, non_blocking=True)
+    e1.record()
+    sync()
+    ms_copy = max_over_ranks(e0.elapsed_time(e1))
+    del stage
     del host, xh, yh, zh
     pipe.close()
     del pipe
@@ -723,7 +733,10 @@ def run_c4_arm(a, wl):
         "clocks": clocks, "host_affinity": numa,
         "e2e": {"value": wl["n_part"] / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "h2d_gbs_per_gpu": h2d / world / ms_e2e / 1e6, "P0_first_bins": e2e_pk_first},
+                "h2d_gbs_per_gpu": h2d / world / ms_e2e / 1e6, "P0_first_bins": e2e_pk_first,
+                "h2d_copies_alone_ms": ms_copy, "h2d_copies_alone_gbs_per_gpu": h2d / world / ms_copy / 1e6,
+                "note": "h2d_copies_alone = the same pinned host -> device copies with nothing else running, all ranks at "
+                        "once: the host memory / PCIe ceiling of this box under the e2e step"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "whole_step": {"algorithmic_bytes": e2e_bytes, "frac_of_peak_all_gpus": e2e_bytes / ms / 1e6 / (peak * world)},
