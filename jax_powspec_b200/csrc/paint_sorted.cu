@@ -977,12 +977,62 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tmap, const
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the box has been read: smem may be released
 }
 
+// One particle straight into the global mesh (float atomics, the general per-particle arithmetic of
+// paint_atomic_kernel): used by the tile kernel for the rare particles it must not put into the fixed-point
+// tile (non-finite weights).
 template <int ORDER, bool REFCIC>
-__global__ void __launch_bounds__(1024) paint_tile_fx_kernel(const float4* __restrict__ sorted,
+__device__ __noinline__ void global_deposit(float rx, float ry, float rz, float rw, int n, int gx0, int gnx, int wrap,
+                                            int variant, float* __restrict__ mesh) {
+  const float4 r = make_float4(rx, ry, rz, rw);
+  struct { int x0, nx; } g = {gx0, gnx};
+  const size_t n2 = (size_t)n * n;
+  if (REFCIC) {
+    int x0, x1, y0, y1, z0, z1;
+    float mdx, ddx, mdy, ddy, mdz, ddz;
+    cic_reference_axis(r.x, n, wrap, variant, x0, x1, mdx, ddx);
+    cic_reference_axis(r.y, n, wrap, variant, y0, y1, mdy, ddy);
+    cic_reference_axis(r.z, n, wrap, variant, z0, z1, mdz, ddz);
+    x0 = local_plane(x0, g.x0, g.nx, n);
+    x1 = local_plane(x1, g.x0, g.nx, n);
+#define JPS_CORNER(ix, iy, iz, wx, wy, wz)                                           \
+  if (((ix) | (iy) | (iz)) >= 0)                                                      \
+    atomicAdd(mesh + (size_t)(ix) * n2 + (size_t)(iy) * n + (iz), (((wx) * (wy)) * (wz)) * r.w);
+    JPS_CORNER(x0, y0, z0, mdx, mdy, mdz)
+    JPS_CORNER(x1, y0, z0, ddx, mdy, mdz)
+    JPS_CORNER(x0, y1, z0, mdx, ddy, mdz)
+    JPS_CORNER(x0, y0, z1, mdx, mdy, ddz)
+    JPS_CORNER(x1, y1, z0, ddx, ddy, mdz)
+    JPS_CORNER(x1, y0, z1, ddx, mdy, ddz)
+    JPS_CORNER(x0, y1, z1, mdx, mdy, ddz)
+    JPS_CORNER(x1, y1, z1, ddx, ddy, ddz)
+#undef JPS_CORNER
+  } else {
+    int ix[ORDER], iy[ORDER], iz[ORDER];
+    float wx[ORDER], wy[ORDER], wz[ORDER];
+    bspline_axis<ORDER>(r.x, n, wrap, ix, wx);
+    bspline_axis<ORDER>(r.y, n, wrap, iy, wy);
+    bspline_axis<ORDER>(r.z, n, wrap, iz, wz);
+#pragma unroll
+    for (int a = 0; a < ORDER; ++a) {
+      const int lx = local_plane(ix[a], g.x0, g.nx, n);
+#pragma unroll
+      for (int b = 0; b < ORDER; ++b) {
+        if ((lx | iy[b]) < 0) continue;
+        float* row = mesh + (size_t)lx * n2 + (size_t)iy[b] * n;
+        const float wxy = wx[a] * wy[b];
+#pragma unroll
+        for (int c = 0; c < ORDER; ++c)
+          if (iz[c] >= 0) atomicAdd(row + iz[c], (wxy * wz[c]) * r.w);
+      }
+    }
+  }
+}
+
+template <int ORDER, bool REFCIC>
+__global__ void __launch_bounds__(512, 3) paint_tile_fx_kernel(const float4* __restrict__ sorted,
                                                             const unsigned* __restrict__ offsets,
                                                             TileGeom g, int wrap, int variant,
-                                                            int mesh_vec_ok,
-                                                            const unsigned* __restrict__ wmax_bits,
+                                                            int mesh_vec_ok, int has_w,
                                                             float* __restrict__ mesh,
                                                             const __grid_constant__ CUtensorMap tmap, int use_tma) {
   constexpr int L = TileDims<ORDER>::L, LP = TileDims<ORDER>::LP, NC = TileDims<ORDER>::CELLS;
@@ -997,9 +1047,28 @@ __global__ void __launch_bounds__(1024) paint_tile_fx_kernel(const float4* __res
   const int n = g.n;
   static_assert((2 * NC) % 4 == 0, "tile words are zeroed 16 bytes at a time");
   for (int i = threadIdx.x; i < (2 * NC) / 4; i += blockDim.x) reinterpret_cast<uint4*>(fx_smem)[i] = make_uint4(0u, 0u, 0u, 0u);
-  // power-of-two scale: 2^e >= max|w|  ->  |contribution| * 2^(31-e) <= 2^31 fits one 32-bit word
-  float wmax = __uint_as_float(*wmax_bits);
-  if (!(wmax > 0.0f) || !(wmax < 3.0e38f)) wmax = 1.0f;
+  // Power-of-two scale of THIS tile: 2^e >= max|w| over the tile's own particles, so that
+  // |contribution| * 2^(31-e) <= 2^31 fits one 32-bit word and the quantum is 2^-31 of the tile's largest
+  // weight -- one outlier weight costs precision in its own 16^3 cells only, not in the whole mesh.  With unit
+  // weights (no w array) the scale is 2^31 and the extra pass over the tile's records is skipped.  Particles
+  // with a non-finite weight never enter the fixed-point tile: they are deposited straight into the mesh with
+  // float atomics, so inf / NaN propagate as they do in the reference's float32 scatter.
+  __shared__ float s_wmax[32];
+  float wmax = 1.0f;
+  if (has_w) {
+    float m = 0.0f;
+    for (unsigned i = beg + threadIdx.x; i < end; i += blockDim.x) {
+      const float a = fabsf(sorted[i].w);
+      if (a < 3.0e38f) m = fmaxf(m, a);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) s_wmax[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = 0.0f;
+    for (int q = 0; q < (int)((blockDim.x + 31) >> 5); ++q) m = fmaxf(m, s_wmax[q]);
+    wmax = m > 0.0f ? m : 1.0f;
+  }
   int e;
   frexpf(wmax, &e);
   e = max(-90, min(90, e));
@@ -1009,7 +1078,8 @@ __global__ void __launch_bounds__(1024) paint_tile_fx_kernel(const float4* __res
   for (unsigned i = beg + threadIdx.x; i < end; i += blockDim.x) {
     const float4 r = sorted[i];
     const float ws = fabsf(r.w) * scale;
-    if (r.w >= 0.0f) fx_deposit<ORDER, REFCIC, false>(r, ws, lo, hi, g, wrap, variant, ox, oy, oz);
+    if (has_w && !(fabsf(r.w) < 3.0e38f)) global_deposit<ORDER, REFCIC>(r.x, r.y, r.z, r.w, n, g.x0, g.nx, wrap, variant, mesh);
+    else if (r.w >= 0.0f) fx_deposit<ORDER, REFCIC, false>(r, ws, lo, hi, g, wrap, variant, ox, oy, oz);
     else fx_deposit<ORDER, REFCIC, true>(r, ws, lo, hi, g, wrap, variant, ox, oy, oz);
   }
   __syncthreads();
@@ -1346,14 +1416,14 @@ static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayo
       // CTA size (measured, C2 / a C4 rank): 256 threads 1.94 ms, 384 1.56, 512 1.61, 768 1.89 for TSC;
       // PCS on sparse tiles 9.2 (256), 6.67 (384), 6.41 (512) ms; CIC flat between 320 and 512.
       static const int tpb_env = [] { const char* e = getenv("JPS_TILE_THREADS"); return e ? atoi(e) : 0; }();
-      const int tpb = tpb_env > 0 ? tpb_env : (ORDER == 3 ? 384 : 512);
+      const int tpb = tpb_env > 0 ? std::min(tpb_env, 512) : (ORDER == 3 ? 384 : 512);
       // JPS_TILE_FLUSH=red forces the per-thread red flush everywhere (A/B runs, tests)
       static const bool no_tma = [] { const char* e = getenv("JPS_TILE_FLUSH"); return e && !strcmp(e, "red"); }();
       CUtensorMap tmap;
       memset(&tmap, 0, sizeof(tmap));
       const int use_tma = (!no_tma && make_mesh_tensor_map(&tmap, p.mesh, g.n, g.nx, TileDims<ORDER>::L, TileDims<ORDER>::LP)) ? 1 : 0;
       paint_tile_fx_kernel<ORDER, REFCIC><<<g.ntiles, tpb, smem, s>>>(sorted, offsets, g, p.wrap, p.variant,
-                                                                    mesh_vec_ok, wmax_bits, p.mesh, tmap, use_tma);
+                                                                    mesh_vec_ok, p.w ? 1 : 0, p.mesh, tmap, use_tma);
     }
   }
   JPS_CHECK_LAUNCH();

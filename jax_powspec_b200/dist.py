@@ -126,10 +126,13 @@ def covariance_batch(seeds: Sequence[int], measure: Callable[[int], torch.Tensor
     mine = shard_indices(len(seeds))
     rows = [measure(seeds[i]).detach().to(torch.float32).reshape(1, -1) for i in mine]
     ncol = None
+    local = None
     if rows:
         local = torch.cat(rows, dim=0)
         ncol = local.shape[1]
     r, w = world()
+    if w == 1 and local is None:                # no seeds at all: nothing to measure, nothing to gather
+        return np.zeros((0, 0, 3), np.float32), np.zeros(0), np.zeros((0, 0))
     if w > 1:                                  # ranks with no work still need the row width
         dev = rows[0].device if rows else (torch.device("cuda", torch.cuda.current_device())
                                           if dist.get_backend() == "nccl" else torch.device("cpu"))
@@ -201,6 +204,11 @@ def bispec_pairs_sharded(delta, box_size, k1, k2, theta, **kw):
     if res is None:
         return None
     k_all, pk, B, Q = res
-    if not isinstance(delta, torch.Tensor):           # same container kind as the input, like bispec_pairs
+    # same container kind as the input, like bispec_pairs: NumPy in -> NumPy out; host tensor in -> host tensors
+    # (also under NCCL, which gathers on the device); CUDA tensor in -> CUDA tensors.  theta follows.
+    if not isinstance(delta, torch.Tensor):
         k_all, pk, B, Q = (t.cpu().numpy() for t in (k_all, pk, B, Q))
-    return k_all, pk, th, B, Q
+        return k_all, pk, th, B, Q
+    if not delta.is_cuda:
+        k_all, pk, B, Q = (t.cpu() for t in (k_all, pk, B, Q))
+    return k_all, pk, torch.from_numpy(th).to(k_all.device), B, Q

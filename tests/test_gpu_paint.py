@@ -227,3 +227,45 @@ def test_fixed_point_deposit_weight_ranges(jps, order, compat, wkind):
     tol = 3e-7 * per_cell + 1e-7 * wmax
     bad = np.abs(got - want) > tol
     assert not bad.any(), f"{bad.sum()} cells off, worst {np.max(np.abs(got - want) / (tol + 1e-300)):.2f}x tol"
+
+
+@pytest.mark.parametrize("order", [2, 3, 4])
+def test_one_outlier_weight_costs_precision_in_its_own_tile_only(jps, order):
+    """The fixed-point scale is per TILE (2^e >= the tile's own max|w|): a particle 1e9 times heavier than the
+    rest must not degrade cells of other tiles (with a mesh-global scale every unit-weight contribution would
+    be quantised at 2^-31 * 1e9 = 0.5)."""
+    n, box, npart = 64, 1000.0, 100_000
+    p = clustered_particles(21, npart, box)
+    w = np.ones(npart, F32)
+    p[0] = [10.0, 10.0, 10.0]                       # cell (0,0,0): tile 0
+    w[0] = 1e9
+    want = om.paint(np.zeros((n, n, n)), p[:, 0], p[:, 1], p[:, 2], w, 0., 0., 0., box, n, True,
+                    order=order, compat="fixed", precision="f64")
+    got = jps.paint(np.zeros((n, n, n), F32), p[:, 0], p[:, 1], p[:, 2], w, 0., 0., 0., box, n, True,
+                    order=order, compat="fixed", method="sorted").astype(np.float64)
+    far = np.ones((n, n, n), bool)
+    far[:20, :20, :20] = False                      # tile 0 + halo: only float32 accuracy relative to 1e9 there
+    far[-4:, :, :] = far[:, -4:, :] = far[:, :, -4:] = False      # stencils of the tile wrap to the high planes
+    err = np.abs(got - want)[far] / np.maximum(want[far], 1.0)
+    assert err.max() <= 1e-6, f"cells far from the outlier are off by {err.max():.2e}"
+    near = ~far
+    assert np.abs(got - want)[near].max() <= 3e-7 * 1e9
+
+
+@pytest.mark.parametrize("bad", [np.inf, -np.inf, np.nan])
+def test_non_finite_weight_propagates_like_a_float_scatter(jps, bad):
+    """inf / NaN weights never enter the fixed-point tile: the particle is deposited with float atomics, so its
+    stencil cells become non-finite (as in the reference's float32 scatter) and every other cell is exact."""
+    n, box, npart = 64, 1000.0, 50_000
+    p = clustered_particles(22, npart, box)
+    w = np.ones(npart, F32)
+    p[7] = [500.0, 500.0, 500.0]
+    w[7] = bad
+    got = jps.paint(np.zeros((n, n, n), F32), p[:, 0], p[:, 1], p[:, 2], w, 0., 0., 0., box, n, True,
+                    order=3, compat="fixed", method="sorted")
+    ref = jps.paint(np.zeros((n, n, n), F32), p[:, 0], p[:, 1], p[:, 2], w, 0., 0., 0., box, n, True,
+                    order=3, compat="fixed", method="atomic")
+    assert np.array_equal(np.isfinite(got), np.isfinite(ref))
+    assert 1 <= (~np.isfinite(got)).sum() <= 27
+    ok = np.isfinite(ref)
+    np.testing.assert_allclose(got[ok], ref[ok], rtol=0, atol=4e-6 * max(ref[ok].max(), 1.0))
