@@ -146,6 +146,24 @@ JPS_API int jps_paint_slab(int n_mesh, int x0, int nx_alloc,
                    int order, int wrap, int compat, int variant, int method,
                    float* mesh, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The two halves of jps_paint_slab(method = JPS_PAINT_SORTED) as separate calls, for pipelines that overlap the
+ * deposit with the transform of the planes already finished (jax_powspec_b200/slab.py): phase
+ * JPS_PAINT_PHASE_BUCKET partitions the catalogue by 16^3-cell tile into `workspace`; JPS_PAINT_PHASE_DEPOSIT
+ * deposits the tiles of tile rows [tx_begin, tx_end) along x (16 planes each, jps_paint_tile_rows(nx_alloc) rows
+ * in all; a tile row also touches the next order-1 planes) from a workspace bucketed by an earlier BUCKET call
+ * with the SAME arguments.  JPS_PAINT_PHASE_ALL is jps_paint_slab.  (No reference counterpart.) */
+#define JPS_PAINT_PHASE_ALL     0
+#define JPS_PAINT_PHASE_BUCKET  1
+#define JPS_PAINT_PHASE_DEPOSIT 2
+JPS_API int jps_paint_tile_rows(int nx_alloc);
+JPS_API int jps_paint_slab_phase(int n_mesh, int x0, int nx_alloc,
+                         const float* x, const float* y, const float* z, const float* w,
+                         int64_t stride, int64_t n_part,
+                         float xmin, float ymin, float zmin, float box_size,
+                         int order, int wrap, int compat, int variant, int method,
+                         float* mesh, void* workspace, size_t workspace_bytes,
+                         int phase, int tx_begin, int tx_end, void* stream);
+
 /* ------------------------------------------------------------------ P(k) ------------- */
 /* Power-spectrum multipoles of a mesh in user bins.
  *   mesh       : device float32 [n,n,n]; not modified.

@@ -18,6 +18,7 @@ VARIANT_VEC, VARIANT_SCAN = 0, 1
 PAINT_AUTO, PAINT_ATOMIC, PAINT_SORTED = 0, 1, 2
 PK_HERMITIAN = 1
 PLAN_TABLES_ONLY, PLAN_FFT_PENCIL = 1, 2
+PAINT_PHASE_ALL, PAINT_PHASE_BUCKET, PAINT_PHASE_DEPOSIT = 0, 1, 2
 
 COMPAT = {"reference": COMPAT_REFERENCE, "fixed": COMPAT_FIXED}
 METHOD = {"auto": PAINT_AUTO, "atomic": PAINT_ATOMIC, "sorted": PAINT_SORTED}
@@ -54,6 +55,9 @@ SIGNATURES = {
                        _vp, _vp, _sz, _vp]),
     "jps_paint_slab": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _f, _f, _i, _i, _i, _i, _i,
                             _vp, _vp, _sz, _vp]),
+    "jps_paint_tile_rows": (_i, [_i]),
+    "jps_paint_slab_phase": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _f, _f, _i, _i, _i, _i, _i,
+                                  _vp, _vp, _sz, _i, _i, _i, _vp]),
     "jps_powspec": (_i, [_vp, _vp, _i, _f, _fp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "jps_powspec_ex": (_i, [_vp, _vp, _vp, _i, _f, _fp, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "jps_fundamental_nbins": (_i, [_i]),

@@ -125,6 +125,7 @@ enum TableMode {
 };
 
 constexpr int kNumTables = 4;
+constexpr int kMaxSegments = 4096;    // 32 KB of shared memory for (seg_bp, seg_val)
 
 struct BinTable {               // cached k^2 -> bin lookup for one set of edges (one slot)
   std::vector<float> key;       // mode tag + edges in grid units (float32) that produced it
@@ -141,6 +142,14 @@ struct BinTable {               // cached k^2 -> bin lookup for one set of edges
   unsigned long long* cnt = nullptr;   // [acc_cap] exact mode / cell counts   } geometry only,
   double* ksum = nullptr;              // [acc_cap] sum of |k| (grid units)     } computed once
   unsigned long long* lastidx = nullptr;  // [acc_cap] largest C-order flat index (Q18) } per table
+  // The lut as a short list of SEGMENTS of constant value (k^2 in [seg_bp[i], seg_bp[i+1]) -> seg_val[i]) with a
+  // per-integer-|k| entry point coarse[floor(sqrt(k^2))]: small enough for shared memory (kernels whose lanes
+  // run along one axis of a 2048^3 spectrum otherwise pull one 32-byte L2 sector of the 12 MB lut per mode).
+  int32_t* seg_bp = nullptr;           // [kMaxSegments]
+  int32_t* seg_val = nullptr;          // [kMaxSegments]
+  int32_t* coarse = nullptr;           // [isqrt(k2max) + 2]
+  int nseg = 0;                        // 0: too many segments / too long scans -> use the lut
+  int ncoarse = 0;
 };
 
 }  // namespace jps

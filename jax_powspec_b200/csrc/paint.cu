@@ -86,7 +86,7 @@ static int launch_atomic(const PaintParams& p, int order, int compat, cudaStream
 }
 
 int paint_sorted(const PaintParams& p, int order, int compat, void* ws, size_t ws_bytes,
-                 cudaStream_t s);                       // paint_sorted.cu
+                 cudaStream_t s, int phase, int tx_begin, int tx_end);   // paint_sorted.cu
 size_t paint_sorted_workspace(int n, int64_t n_part, int order);
 
 }  // namespace jps
@@ -117,6 +117,21 @@ extern "C" int jps_paint_slab(int n_mesh, int x0, int nx_alloc, const float* x, 
                               float xmin, float ymin, float zmin, float box_size, int order, int wrap,
                               int compat, int variant, int method, float* mesh, void* workspace,
                               size_t workspace_bytes, void* stream) {
+  return jps_paint_slab_phase(n_mesh, x0, nx_alloc, x, y, z, w, stride, n_part, xmin, ymin, zmin, box_size, order, wrap,
+                              compat, variant, method, mesh, workspace, workspace_bytes, JPS_PAINT_PHASE_ALL, 0, 0, stream);
+}
+
+extern "C" int jps_paint_tile_rows(int nx_alloc) { return (nx_alloc + 15) / 16; }
+
+extern "C" int jps_paint_slab_phase(int n_mesh, int x0, int nx_alloc, const float* x, const float* y,
+                                    const float* z, const float* w, int64_t stride, int64_t n_part,
+                                    float xmin, float ymin, float zmin, float box_size, int order, int wrap,
+                                    int compat, int variant, int method, float* mesh, void* workspace,
+                                    size_t workspace_bytes, int phase, int tx_begin, int tx_end, void* stream) {
+  JPS_REQUIRE(phase == JPS_PAINT_PHASE_ALL || phase == JPS_PAINT_PHASE_BUCKET || phase == JPS_PAINT_PHASE_DEPOSIT,
+              "jps_paint_slab_phase: unknown phase %d", phase);
+  JPS_REQUIRE(phase == JPS_PAINT_PHASE_ALL || method == JPS_PAINT_SORTED,
+              "jps_paint_slab_phase: the bucket / deposit phases exist for method = JPS_PAINT_SORTED only");
   JPS_REQUIRE(nx_alloc >= 1 && nx_alloc <= n_mesh, "jps_paint_slab: nx_alloc=%d out of range [1,%d]", nx_alloc, n_mesh);
   JPS_REQUIRE(n_mesh >= 2 && n_mesh <= 4096, "jps_paint: n_mesh=%d out of range [2,4096]", n_mesh);
   JPS_REQUIRE(n_part >= 0, "jps_paint: n_part < 0");
@@ -151,5 +166,5 @@ extern "C" int jps_paint_slab(int n_mesh, int x0, int nx_alloc, const float* x, 
   }
   if (method == JPS_PAINT_ATOMIC) return launch_atomic(p, order, compat, s);
   JPS_REQUIRE(method == JPS_PAINT_SORTED, "jps_paint: unknown method %d", method);
-  return paint_sorted(p, order, compat, workspace, workspace_bytes, s);
+  return paint_sorted(p, order, compat, workspace, workspace_bytes, s, phase, tx_begin, tx_end);
 }

@@ -1034,12 +1034,13 @@ __global__ void __launch_bounds__(512, 3) paint_tile_fx_kernel(const float4* __r
                                                             TileGeom g, int wrap, int variant,
                                                             int mesh_vec_ok, int has_w,
                                                             float* __restrict__ mesh,
-                                                            const __grid_constant__ CUtensorMap tmap, int use_tma) {
+                                                            const __grid_constant__ CUtensorMap tmap, int use_tma,
+                                                            int tile_offset) {
   constexpr int L = TileDims<ORDER>::L, LP = TileDims<ORDER>::LP, NC = TileDims<ORDER>::CELLS;
   extern __shared__ __align__(128) unsigned fx_smem[];
   unsigned* lo = fx_smem;
   unsigned* hi = fx_smem + NC;
-  const int t = blockIdx.x;
+  const int t = blockIdx.x + tile_offset;
   const unsigned beg = offsets[t * g.rep], end = offsets[(t + 1) * g.rep];
   if (beg == end) return;
   const int tz = t % g.nt, ty = (t / g.nt) % g.nt, tx = t / (g.nt * g.nt);
@@ -1394,7 +1395,11 @@ static bool make_mesh_tensor_map(CUtensorMap* tm, float* mesh, int n, int nx, in
 
 // deposit a bucketed piece into the mesh on stream `s`
 template <int ORDER, bool REFCIC>
-static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayout& L, char* ws, cudaStream_t s) {
+static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayout& L, char* ws, cudaStream_t s,
+                       int tx_begin, int tx_end) {
+  const int tile_offset = tx_begin * g.nt * g.nt;
+  const int tile_count = (tx_end - tx_begin) * g.nt * g.nt;
+  if (tile_count <= 0) return JPS_OK;
   const unsigned* offsets = (const unsigned*)(ws + L.offsets);
   const float4* sorted = (const float4*)(ws + L.sorted);
   const unsigned* wmax_bits = (const unsigned*)(ws + L.wmax);
@@ -1403,6 +1408,7 @@ static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayo
     const int mesh_vec_ok = (((uintptr_t)p.mesh) & 15) == 0 ? 1 : 0;
     static const bool plain = [] { const char* e = getenv("JPS_TILE_KERNEL"); return e && !strcmp(e, "plain"); }();
     if (plain) {
+      JPS_REQUIRE(tile_count == g.ntiles, "JPS_TILE_KERNEL=plain cannot deposit a range of tile rows");
       paint_tile_kernel<ORDER, REFCIC><<<g.ntiles, 256, 0, s>>>(sorted, offsets, g, p.wrap, p.variant,
                                                               mesh_vec_ok, p.mesh);
     } else {
@@ -1422,12 +1428,13 @@ static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayo
       CUtensorMap tmap;
       memset(&tmap, 0, sizeof(tmap));
       const int use_tma = (!no_tma && make_mesh_tensor_map(&tmap, p.mesh, g.n, g.nx, TileDims<ORDER>::L, TileDims<ORDER>::LP)) ? 1 : 0;
-      paint_tile_fx_kernel<ORDER, REFCIC><<<g.ntiles, tpb, smem, s>>>(sorted, offsets, g, p.wrap, p.variant,
-                                                                    mesh_vec_ok, p.w ? 1 : 0, p.mesh, tmap, use_tma);
+      paint_tile_fx_kernel<ORDER, REFCIC><<<tile_count, tpb, smem, s>>>(sorted, offsets, g, p.wrap, p.variant,
+                                                                      mesh_vec_ok, p.w ? 1 : 0, p.mesh, tmap, use_tma,
+                                                                      tile_offset);
     }
   }
   JPS_CHECK_LAUNCH();
-  if (REFCIC) {
+  if (REFCIC && tx_begin == 0) {                  // the outlier bucket goes with the first range
     ScopedLaunch T(K_PAINT_ATOMIC, s);
     paint_outliers_kernel<<<kNumSMs, 256, 0, s>>>(sorted, offsets, g.ntiles * g.rep, g.n, g.x0, g.nx, p.wrap,
                                                   p.variant, p.mesh);
@@ -1440,17 +1447,25 @@ static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayo
 // an auxiliary stream while piece c is deposited.  The step got SLOWER, 6.9 -> 8.5 ms on C2: each
 // piece re-zeroes and re-flushes every tile, so the deposit grows from 2.7 to 4 x 1.1 ms, and the
 // two kernels do not overlap well enough to pay that back.)
+// phase 0: bucket + deposit everything; 1: bucket only; 2: deposit tile rows [tx_begin, tx_end) of a workspace
+// bucketed by an earlier phase-1 call with the same arguments
 template <int ORDER, bool REFCIC>
-static int run_sorted(const PaintParams& p, const TileGeom& g, char* ws, size_t ws_bytes, cudaStream_t s) {
+static int run_sorted(const PaintParams& p, const TileGeom& g, char* ws, size_t ws_bytes, cudaStream_t s, int phase,
+                      int tx_begin, int tx_end) {
   (void)ws_bytes;
   const SortedLayout L = sorted_layout(p.n, p.nx, p.n_part);
-  int rc = g.two_level ? run_bucket_two_level<ORDER, REFCIC>(p, g, L, ws, s) : run_bucket<ORDER, REFCIC>(p, g, L, ws, s);
-  if (rc) return rc;
-  return run_deposit<ORDER, REFCIC>(p, g, L, ws, s);
+  if (phase != 2) {
+    int rc = g.two_level ? run_bucket_two_level<ORDER, REFCIC>(p, g, L, ws, s) : run_bucket<ORDER, REFCIC>(p, g, L, ws, s);
+    if (rc) return rc;
+  }
+  if (phase == 1) return JPS_OK;
+  if (phase == 0) { tx_begin = 0; tx_end = g.ntx; }
+  JPS_REQUIRE(tx_begin >= 0 && tx_end <= g.ntx && tx_begin <= tx_end, "jps_paint: tile rows [%d, %d) outside [0, %d)", tx_begin, tx_end, g.ntx);
+  return run_deposit<ORDER, REFCIC>(p, g, L, ws, s, tx_begin, tx_end);
 }
 
 int paint_sorted(const PaintParams& p, int order, int compat, void* ws, size_t ws_bytes,
-                 cudaStream_t s) {
+                 cudaStream_t s, int phase, int tx_begin, int tx_end) {
   if (p.n_part == 0) return JPS_OK;
   JPS_REQUIRE(p.n_part < ((int64_t)1 << 32) - 1, "jps_paint: the sorted painter takes < 2^32 particles per call");
   const SortedLayout L = sorted_layout(p.n, p.nx, p.n_part);
@@ -1479,10 +1494,10 @@ int paint_sorted(const PaintParams& p, int order, int compat, void* ws, size_t w
   g.two_level = (forced != 1 && fits_two) ? 1 : 0;
   g.rep = g.two_level ? 1 : replicas_for(g.ntiles);
   char* w = (char*)ws;
-  if (order == 2 && compat == JPS_COMPAT_REFERENCE) return run_sorted<2, true>(p, g, w, ws_bytes, s);
-  if (order == 2) return run_sorted<2, false>(p, g, w, ws_bytes, s);
-  if (order == 3) return run_sorted<3, false>(p, g, w, ws_bytes, s);
-  return run_sorted<4, false>(p, g, w, ws_bytes, s);
+  if (order == 2 && compat == JPS_COMPAT_REFERENCE) return run_sorted<2, true>(p, g, w, ws_bytes, s, phase, tx_begin, tx_end);
+  if (order == 2) return run_sorted<2, false>(p, g, w, ws_bytes, s, phase, tx_begin, tx_end);
+  if (order == 3) return run_sorted<3, false>(p, g, w, ws_bytes, s, phase, tx_begin, tx_end);
+  return run_sorted<4, false>(p, g, w, ws_bytes, s, phase, tx_begin, tx_end);
 }
 
 }  // namespace jps

@@ -96,7 +96,7 @@ void host_window_axis(int n, int p, float* out) {
 }
 
 struct TableLayout {
-  size_t lut, compact_to_bin, bin_to_compact, edges, cnt, ksum, lastidx;
+  size_t lut, compact_to_bin, bin_to_compact, edges, cnt, ksum, lastidx, seg_bp, seg_val, coarse;
 };
 
 struct Layout {
@@ -124,6 +124,9 @@ static Layout make_layout(int n, int pitch, size_t fft_work_bytes, int n_shell_f
     L.t[i].cnt = take((size_t)L.cap * 8);
     L.t[i].ksum = take((size_t)L.cap * 8);
     L.t[i].lastidx = take((size_t)L.cap * 8);
+    L.t[i].seg_bp = take((size_t)kMaxSegments * 4);
+    L.t[i].seg_val = take((size_t)kMaxSegments * 4);
+    L.t[i].coarse = take((size_t)((int64_t)sqrt((double)k2max) + 4) * 4);
   }
   L.wlut = take((size_t)3 * n * 4);
   L.acc = take((size_t)L.cap * 4 * 8);
@@ -328,6 +331,9 @@ extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* 
     T.cnt = (unsigned long long*)(ws + L.t[i].cnt);
     T.ksum = (double*)(ws + L.t[i].ksum);
     T.lastidx = (unsigned long long*)(ws + L.t[i].lastidx);
+    T.seg_bp = (int32_t*)(ws + L.t[i].seg_bp);
+    T.seg_val = (int32_t*)(ws + L.t[i].seg_val);
+    T.coarse = (int32_t*)(ws + L.t[i].coarse);
   }
   p->wlut = (float*)(ws + L.wlut);
   p->acc = (double*)(ws + L.acc);

@@ -343,6 +343,30 @@ int ensure_bin_table(jps_plan* plan, const float* kedges_grid, int nb, int mode,
     pk_count_kernel<<<kNumSMs * 8, 256, 0, s>>>(C);
   }
   JPS_CHECK_LAUNCH();
+  // segment form of the lut (see BinTable): breakpoints where the value changes + entry point per integer |k|
+  {
+    std::vector<int32_t> bp, val;
+    for (int64_t m = 0; m <= k2max; ++m)
+      if (m == 0 || lut[(size_t)m] != lut[(size_t)m - 1]) { bp.push_back((int32_t)m); val.push_back(lut[(size_t)m]); }
+    const int ncoarse = (int)sqrt((double)k2max) + 2;
+    std::vector<int32_t> coarse((size_t)ncoarse, 0);
+    int seg = 0, max_scan = 0;
+    for (int r = 0; r < ncoarse; ++r) {
+      const int64_t lo = (int64_t)r * r, hi = (int64_t)(r + 1) * (r + 1);
+      while (seg + 1 < (int)bp.size() && bp[(size_t)seg + 1] <= lo) ++seg;
+      coarse[(size_t)r] = seg;
+      int scan = 0;
+      for (int t = seg; t + 1 < (int)bp.size() && bp[(size_t)t + 1] < hi; ++t) ++scan;
+      max_scan = std::max(max_scan, scan);
+    }
+    T.nseg = 0; T.ncoarse = ncoarse;
+    if ((int)bp.size() <= kMaxSegments && max_scan <= 8) {
+      T.nseg = (int)bp.size();
+      JPS_CHECK_CUDA(cudaMemcpyAsync(T.seg_bp, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice, s));
+      JPS_CHECK_CUDA(cudaMemcpyAsync(T.seg_val, val.data(), val.size() * 4, cudaMemcpyHostToDevice, s));
+      JPS_CHECK_CUDA(cudaMemcpyAsync(T.coarse, coarse.data(), coarse.size() * 4, cudaMemcpyHostToDevice, s));
+    }
+  }
   T.key = key; T.mode = mode; T.nb = nb; T.nbc = nbc; T.valid = true; T.stamp = ++plan->stamp;
   *out = &T;
   return JPS_OK;

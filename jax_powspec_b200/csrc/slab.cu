@@ -101,7 +101,19 @@ struct SlabPkParams {
   const float* dc;       // device: Re rho_hat(k=0) (used when normalise)
   int normalise;
   int kz_major;          // x-fast kernel only: 0 = dk[yl][kz][x], 1 = dk[kz][yl][x]
+  // x-fast kernel only: the lut in segment form, staged in shared memory (nseg == 0: read the lut from L2)
+  const int32_t* seg_bp; const int32_t* seg_val; const int32_t* coarse;
+  int nseg, ncoarse;
 };
+
+// k^2 -> compact bin through the shared-memory segment list: entry point from floor(sqrt(k^2)) (exact in float32
+// for k^2 < 2^22), then a short forward scan (bounded by the table builder, <= 8 steps).
+__device__ __forceinline__ int seg_lookup(const int* __restrict__ bp, const int* __restrict__ val,
+                                          const int* __restrict__ coarse, int nseg, int k2) {
+  int sidx = coarse[(int)sqrtf((float)k2)];
+  while (sidx + 1 < nseg && k2 >= bp[sidx + 1]) ++sidx;
+  return val[sidx];
+}
 
 // One warp per (a = |kx|, local y): folds the rows ix = a and ix = n-a, lanes along kz.
 template <int MODE>
@@ -221,6 +233,16 @@ __global__ void __launch_bounds__(256) pk_bin_xfast_kernel(SlabPkParams P) {
     scale2 = (float)(s * s);
   }
   const int n = P.n, nz = P.nz, mid = n / 2;
+  // segment tables behind the accumulators (dynamic shared memory sized by the launcher)
+  const int nacc_all = (MODE == ACC_WARP ? nwarps : (MODE == ACC_BLOCK ? 1 : 0)) * nacc;
+  int* s_bp = reinterpret_cast<int*>(sacc + nacc_all);
+  int* s_val = s_bp + P.nseg;
+  int* s_coarse = s_val + P.nseg;
+  if (P.nseg) {
+    for (int i = threadIdx.x; i < P.nseg; i += blockDim.x) { s_bp[i] = P.seg_bp[i]; s_val[i] = P.seg_val[i]; }
+    for (int i = threadIdx.x; i < P.ncoarse; i += blockDim.x) s_coarse[i] = P.coarse[i];
+    __syncthreads();
+  }
   const long long items = (long long)P.nyl * nz;
   for (long long it = (long long)blockIdx.x * nwarps + warp; it < items; it += (long long)gridDim.x * nwarps) {
     const int yl = P.kz_major ? (int)(it % P.nyl) : (int)(it / nz);
@@ -251,7 +273,7 @@ __global__ void __launch_bounds__(256) pk_bin_xfast_kernel(SlabPkParams P) {
         int cb = -2;
         if (a <= mid) {
           const int k2 = k2yz + a * a;
-          cb = __ldg(P.lut + k2);
+          cb = P.nseg ? seg_lookup(s_bp, s_val, s_coarse, P.nseg, k2) : __ldg(P.lut + k2);
           const float c = (P.wl[a] * wy) * wz;
           float re = d0[u].x * c, im = d0[u].y * c;
           float sum = re * re + im * im;
@@ -455,6 +477,11 @@ static int bin_layout(jps_plan* tp, const float2* dk, int nyl, int y0, int xfast
   P.dk = dk; P.n = tp->n; P.nz = tp->nz; P.nyl = nyl; P.y0 = y0;
   P.lut = T.lut; P.wl = tp->wlut + (size_t)(mas_order - 2) * tp->n; P.nbc = T.nbc; P.acc = tp->acc;
   P.dc = dc; P.normalise = normalise; P.kz_major = kz_major;
+  static const bool no_seg = [] { const char* e = getenv("JPS_BIN_LUT"); return e && !strcmp(e, "global"); }();
+  const bool seg = xfast && T.nseg > 0 && !no_seg;
+  P.seg_bp = T.seg_bp; P.seg_val = T.seg_val; P.coarse = T.coarse;
+  P.nseg = seg ? T.nseg : 0; P.ncoarse = seg ? T.ncoarse : 0;
+  const size_t seg_bytes = seg ? (size_t)(2 * T.nseg + T.ncoarse) * sizeof(int) : 0;
   const int threads = 256, warps = 8;
   const long long items = xfast ? (long long)nyl * tp->nz : (long long)(tp->n / 2 + 1) * nyl;
   const long long want = (items + warps - 1) / warps;
@@ -462,10 +489,12 @@ static int bin_layout(jps_plan* tp, const float2* dk, int nyl, int y0, int xfast
   if (!attr_set.get()) {
     const int sw = (int)((size_t)warps * kMaxSmemBins * 3 * sizeof(float));
     const int sb = (int)((size_t)kMaxBlockBins * 3 * sizeof(float));
+    const int sseg = (int)((size_t)(2 * kMaxSegments + 8192) * sizeof(int));       // segment tables (x-fast kernels)
     JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw));
     JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw));
-    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw + sseg));
+    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb + sseg));
+    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, sseg));
     attr_set.set();
   }
   using KernelFn = void (*)(SlabPkParams);
@@ -474,12 +503,13 @@ static int bin_layout(jps_plan* tp, const float2* dk, int nyl, int y0, int xfast
   long long cap_per_sm = 0;
   if (T.nbc <= kMaxSmemBins) {
     fn = xfast ? pk_bin_xfast_kernel<ACC_WARP> : pk_bin_ysharded_kernel<ACC_WARP>;
-    smem = (size_t)warps * T.nbc * 3 * sizeof(float);
+    smem = (size_t)warps * T.nbc * 3 * sizeof(float) + seg_bytes;
   } else if (T.nbc <= kMaxBlockBins) {
     fn = xfast ? pk_bin_xfast_kernel<ACC_BLOCK> : pk_bin_ysharded_kernel<ACC_BLOCK>;
-    smem = (size_t)T.nbc * 3 * sizeof(float);
+    smem = (size_t)T.nbc * 3 * sizeof(float) + seg_bytes;
   } else {
     fn = xfast ? pk_bin_xfast_kernel<ACC_GLOBAL> : pk_bin_ysharded_kernel<ACC_GLOBAL>;
+    smem = seg_bytes;
     cap_per_sm = 8;
   }
   if (!cap_per_sm) {

@@ -123,7 +123,7 @@ class SlabPipeline:
 
     def __init__(self, n_mesh, box_size, k_edges, *, order=2, compat="fixed", method="auto", wrap=True,
                  shot_noise=0.0, rank=None, world=None, device=None, transport="auto", overlap=True,
-                 layout="auto"):
+                 layout="auto", pipeline=True):
         """transport: how the transpose crosses GPUs -- "p2p": one fused pack + peer-store kernel
         over NVLink peer memory (receive buffers mapped into every rank with CUDA IPC); "nccl":
         pack kernel + ``all_to_all_single``; "auto": p2p when the mapping succeeds, else nccl.
@@ -131,7 +131,9 @@ class SlabPipeline:
         while the 2-D FFT of chunk c+1 runs.
         layout: "xfast" = the peer-store kernel transposes on the way so that the shard arrives as
         [y_local][kz][x] and the 1-D FFT along x is contiguous (p2p only); "xslow" = [x][y_local][kz]
-        with a strided FFT; "auto" = xfast with p2p, xslow otherwise."""
+        with a strided FFT; "auto" = xfast with p2p, xslow otherwise.
+        pipeline: run deposit, halo exchange, 2-D FFT and peer transfer as one pipeline over pieces of planes
+        (p2p + overlap only; see _pipelined_paint_fft)."""
         r, w = _world()
         self.rank = r if rank is None else rank
         self.world = w if world is None else world
@@ -206,6 +208,9 @@ class SlabPipeline:
         self.overlap = bool(overlap)
         self.chunk_planes = int(lib.jps_slab_chunk_planes(self.handle))
         self._side, self._events = None, None
+        self._halo_stream, self._halo_ev = None, None
+        self._dep_stream = None
+        self.pipeline = bool(pipeline)
         self._local_peers = False
         self._force_chunks = False                      # tests: take the chunked path on small meshes
         if layout not in ("auto", "xfast", "xslow"):
@@ -279,20 +284,24 @@ class SlabPipeline:
 
     # ---- stages (each enqueues on the current stream; exchanges are separate so that a test can
     #      drive several virtual ranks on one device)
+    def _paint_call(self, x, y, z, w, xmin, ymin, zmin, phase=_lib.PAINT_PHASE_ALL, tx_begin=0, tx_end=0, method=None):
+        x, y, z, w, stride = check_particles(x, y, z, w, self.device)
+        npart = x.numel()
+        meth = _lib.METHOD[self.method if method is None else method]
+        if paint_workspace_bytes(self.n, npart, self.order, meth) > self.pws_bytes:
+            self.pws, self.pws_bytes = new_paint_workspace(self.n, npart, self.order, meth, self.device)
+        check(lib.jps_paint_slab_phase(self.n, self.x0, self.nxa, ptr(x), ptr(y), ptr(z), ptr(w), stride, npart,
+                                       float(xmin), float(ymin), float(zmin), self.box, self.order, int(self.wrap),
+                                       _lib.COMPAT[self.compat], _lib.VARIANT_VEC, meth, ptr(self.mesh), ptr(self.pws),
+                                       self.pws_bytes, int(phase), int(tx_begin), int(tx_end), stream_ptr()),
+              "jps_paint_slab")
+
     def stage_paint(self, x, y, z, w=None, xmin=0.0, ymin=0.0, zmin=0.0, zero=True):
         """Deposit this rank's particles into its planes (+ ghosts).  zero=False accumulates on top of the
         planes as they are (a catalogue streamed in pieces, SlabHostPipeline)."""
-        x, y, z, w, stride = check_particles(x, y, z, w, self.device)
-        npart = x.numel()
-        meth = _lib.METHOD[self.method]
-        if paint_workspace_bytes(self.n, npart, self.order, meth) > self.pws_bytes:
-            self.pws, self.pws_bytes = new_paint_workspace(self.n, npart, self.order, meth, self.device)
         if zero:
             self.mesh.zero_()
-        check(lib.jps_paint_slab(self.n, self.x0, self.nxa, ptr(x), ptr(y), ptr(z), ptr(w), stride, npart,
-                                 float(xmin), float(ymin), float(zmin), self.box, self.order, int(self.wrap),
-                                 _lib.COMPAT[self.compat], _lib.VARIANT_VEC, meth, ptr(self.mesh), ptr(self.pws),
-                                 self.pws_bytes, stream_ptr()), "jps_paint_slab")
+        self._paint_call(x, y, z, w, xmin, ymin, zmin)
 
     def owned(self):
         return self.mesh[self.gl: self.gl + self.nxl]
@@ -309,22 +318,36 @@ class SlabPipeline:
         out = self.buf_a if self.buf_b is None else self.buf_b
         check(lib.jps_slab_fft_yz(self.handle, ptr(self.owned()), ptr(out), stream_ptr()), "jps_slab_fft_yz")
 
-    def stage_fft_yz_p2p(self):
+    def _chunked(self):
+        """Planes per piece of the chunked FFT / transfer overlap, or 0.  Chunking pays when a piece is tens
+        of MB or more (2048^3 on 2-8 GPUs); on a 512^3 mesh the extra launches and stream hops cost more than
+        they hide."""
+        if self.transport != "p2p":
+            return 0
+        big = self._force_chunks or self.buf_b.numel() * 8 >= (1 << 30)
+        cp = self.chunk_planes if (self.overlap and big) else 0
+        return cp if (cp and cp < self.nxl) else 0
+
+    def stage_fft_yz_p2p(self, halo_done=None):
         """2-D FFT into the local buffer, then ONE kernel that writes every destination's block straight
         into that rank's receive buffer over NVLink.  Ordering: the peers finished reading their
         receive buffers before the previous step's allreduce completed (stream order), and the tiny
-        allreduce below makes every rank's stores visible before anyone starts the 1-D FFT."""
-        # chunking pays when a chunk is tens of MB or more (2048^3 on 2-8 GPUs: 37.1 -> 24.7 ms for this
-        # stage on 2 GPUs); on a 512^3 mesh the extra launches and stream hops cost more than they hide
-        big = self._force_chunks or self.buf_b.numel() * 8 >= (1 << 30)
-        cp = self.chunk_planes if (self.overlap and big) else 0
-        if cp and cp < self.nxl:
-            # chunked: the transfer of chunk c (side stream) runs under the 2-D FFT of chunk c+1
+        allreduce below makes every rank's stores visible before anyone starts the 1-D FFT.
+        halo_done: event after which the first and the last piece of planes are final (the ring halo exchange
+        running on its own stream only touches the first two and the last owned plane); the pieces in between
+        are transformed and sent first, so the exchange hides behind them."""
+        cp = self._chunked()
+        if cp:
+            # chunked: the transfer of chunk c (side stream) runs under the 2-D FFT of the next chunk
             main = torch.cuda.current_stream(self.device)
+            nchunk = self.nxl // cp
             if self._side is None:
                 self._side = torch.cuda.Stream(self.device)
-                self._events = [torch.cuda.Event() for _ in range(self.nxl // cp + 1)]
-            for c in range(self.nxl // cp):
+                self._events = [torch.cuda.Event() for _ in range(nchunk + 1)]
+            order = list(range(1, nchunk - 1)) + [0] + ([nchunk - 1] if nchunk > 1 else [])
+            for c in order:
+                if halo_done is not None and c == 0:
+                    main.wait_event(halo_done)
                 check(lib.jps_slab_fft_yz_planes(self.handle, ptr(self.owned()), ptr(self.buf_b), c * cp, cp,
                                                  stream_ptr()), "jps_slab_fft_yz_planes")
                 self._events[c].record(main)
@@ -363,18 +386,97 @@ class SlabPipeline:
         """x, y, z[, w]: this rank's particles (x inside its slab; use route_particles otherwise)."""
         if self.local is not None:
             return self.local(x, y, z, w, xmin, ymin, zmin)
+        if self.pipeline and self._can_pipeline(x.numel()):
+            self._pipelined_paint_fft(x, y, z, w, xmin, ymin, zmin)
+            return self._after_transpose()
         self.stage_paint(x, y, z, w, xmin, ymin, zmin)
         return self.finish()
 
-    def finish(self):
-        """Everything after the deposit: halo exchange, distributed FFT, binning, allreduce."""
-        if self.local is not None:
-            return self.local.finish()
-        if not self.single:
+    def _can_pipeline(self, npart):
+        """The deposit / transform / transfer pipeline needs the chunked p2p path, the bucketed painter and
+        at least three pieces of planes."""
+        cp = self._chunked()
+        if not cp or self.nxl // cp < 3 or self._local_peers or self.method == "atomic":
+            return False
+        return npart >= (1 << 18)                 # what jps_paint's "auto" would bucket anyway
+
+    def _rows_touching(self, p_lo, p_hi):
+        """Tile rows (16 allocated planes each + order-1 halo planes above) that write any plane in [p_lo, p_hi]."""
+        rows = int(lib.jps_paint_tile_rows(self.nxa))
+        first = max(0, (p_lo - (self.order - 1)) // 16)
+        last = min(rows - 1, p_hi // 16)
+        return range(first, last + 1)
+
+    def _pipelined_paint_fft(self, x, y, z, w, xmin, ymin, zmin):
+        """Deposit, ring halo exchange, 2-D FFT and peer transfer as ONE pipeline over pieces of planes.
+        The bucketed tiles are ordered along x, so the deposit is issued tile row by tile row on its own stream;
+        a piece of planes is transformed (main stream) as soon as the tile rows that write it are done, and sent
+        (transfer stream) as soon as it is transformed.  The halo exchange (its own stream) starts after the few
+        tile rows that write the ghost planes and the boundary planes, which are deposited FIRST; the first and
+        the last piece wait for it and go last.  The deposit (shared-memory bound), cuFFT (HBM bound) and the
+        NVLink stores then overlap instead of running back to back."""
+        main = torch.cuda.current_stream(self.device)
+        cp = self._chunked()
+        nchunk = self.nxl // cp
+        if self._dep_stream is None:
+            self._dep_stream = torch.cuda.Stream(self.device)
+            self._halo_stream = self._halo_stream or torch.cuda.Stream(self.device)
+            self._side = self._side or torch.cuda.Stream(self.device)
+        ev = lambda: torch.cuda.Event()
+        self.mesh.zero_()
+        self._paint_call(x, y, z, w, xmin, ymin, zmin, phase=_lib.PAINT_PHASE_BUCKET, method="sorted")
+        e_bucket = ev(); e_bucket.record(main)
+        self._dep_stream.wait_event(e_bucket)
+        done = set()
+
+        def deposit(rows):
+            """Deposit the not-yet-deposited tile rows of `rows` (dep stream); returns an event after them."""
+            todo = sorted(r for r in rows if r not in done)
+            with torch.cuda.stream(self._dep_stream):
+                i = 0
+                while i < len(todo):
+                    j = i
+                    while j + 1 < len(todo) and todo[j + 1] == todo[j] + 1:
+                        j += 1
+                    self._paint_call(x, y, z, w, xmin, ymin, zmin, phase=_lib.PAINT_PHASE_DEPOSIT,
+                                     tx_begin=todo[i], tx_end=todo[j] + 1, method="sorted")
+                    i = j + 1
+                e = ev(); e.record(self._dep_stream)
+            done.update(todo)
+            return e
+
+        # 1. everything the halo exchange reads or adds into: ghost planes and the boundary owned planes
+        halo_rows = set(self._rows_touching(0, self.gl + GHOST_HI - 1)) | \
+            set(self._rows_touching(self.gl + self.nxl - GHOST_LO, self.nxa - 1))
+        e_h = deposit(halo_rows)
+        self._halo_stream.wait_event(e_h)
+        with torch.cuda.stream(self._halo_stream):
             halo_exchange_add(self.mesh, self.nxl)
-        self.stage_fft_yz_pack()
-        if not self.single and self.transport == "nccl":
-            transpose_all_to_all(self.buf_b, self.buf_a)
+            halo_done = ev(); halo_done.record(self._halo_stream)
+        # 2. middle pieces first, then the two that need the neighbours' ghost planes
+        order = list(range(1, nchunk - 1)) + [0, nchunk - 1]
+        last_pack = None
+        for c in order:
+            e_d = deposit(self._rows_touching(self.gl + c * cp, self.gl + (c + 1) * cp - 1))
+            main.wait_event(e_d)
+            if c in (0, nchunk - 1):
+                main.wait_event(halo_done)
+            check(lib.jps_slab_fft_yz_planes(self.handle, ptr(self.owned()), ptr(self.buf_b), c * cp, cp, stream_ptr()),
+                  "jps_slab_fft_yz_planes")
+            e_f = ev(); e_f.record(main)
+            self._side.wait_event(e_f)
+            with torch.cuda.stream(self._side):
+                check(lib.jps_slab_pack_p2p_planes(self.handle, ptr(self.buf_b), self.peer_ptrs, c * cp, cp,
+                                                   stream_ptr()), "jps_slab_pack_p2p_planes")
+                last_pack = ev(); last_pack.record(self._side)
+        rows = int(lib.jps_paint_tile_rows(self.nxa))
+        e_rest = deposit(range(rows))                 # nothing left by construction; keeps the invariant explicit
+        main.wait_event(e_rest)
+        main.wait_event(last_pack)
+        main.wait_event(halo_done)
+        dist.all_reduce(self._sync_flag)              # every rank's stores are visible before anyone reads its shard
+
+    def _after_transpose(self):
         self.stage_fft_x()
         if self.rank == 0:
             self.dc.copy_(self.local_dc())
@@ -384,6 +486,30 @@ class SlabPipeline:
         if self.world > 1:
             dist.all_reduce(self.sums)
         return self.stage_finalize()
+
+    def finish(self):
+        """Everything after the deposit: halo exchange, distributed FFT, binning, allreduce."""
+        if self.local is not None:
+            return self.local.finish()
+        if not self.single and self._chunked() and self.nxl // self._chunked() >= 3 and not self._local_peers:
+            # ring halo exchange on its own stream, hidden behind the transform + transfer of the middle pieces
+            main = torch.cuda.current_stream(self.device)
+            if self._halo_stream is None:
+                self._halo_stream = torch.cuda.Stream(self.device)
+                self._halo_ev = (torch.cuda.Event(), torch.cuda.Event())
+            self._halo_ev[0].record(main)
+            self._halo_stream.wait_event(self._halo_ev[0])
+            with torch.cuda.stream(self._halo_stream):
+                halo_exchange_add(self.mesh, self.nxl)
+                self._halo_ev[1].record(self._halo_stream)
+            self.stage_fft_yz_p2p(halo_done=self._halo_ev[1])
+        else:
+            if not self.single:
+                halo_exchange_add(self.mesh, self.nxl)
+            self.stage_fft_yz_pack()
+        if not self.single and self.transport == "nccl":
+            transpose_all_to_all(self.buf_b, self.buf_a)
+        return self._after_transpose()
 
     # ---- NVLink reference rate of the transpose (bench.py reports the fused stage against it)
     def probe_transpose(self, xfast: bool, repeats: int = 3) -> float:

@@ -45,14 +45,17 @@ for order, weighted in ((4, False), (3, True), (2, False)):
         wf = torch.from_numpy(w_all).to(dev) if weighted else None
         ref = jps.PaintPowspec(n, box, ke, order=order, compat="fixed", device=dev)
         k1, pk1, nm1 = (t.clone() for t in ref(*full, wf))
-    for transport, layout, overlap in (("p2p", "xfast", True), ("p2p", "xfast", False), ("p2p", "xslow", True), ("nccl", "xslow", True)):
-        pipe = SlabPipeline(n, box, ke, order=order, compat="fixed", transport=transport, layout=layout, overlap=overlap)
+    for transport, layout, overlap, pipelined in (("p2p", "xfast", True, True), ("p2p", "xfast", True, False),
+                                                  ("p2p", "xfast", False, False), ("p2p", "xslow", True, True),
+                                                  ("nccl", "xslow", True, False)):
+        pipe = SlabPipeline(n, box, ke, order=order, compat="fixed", transport=transport, layout=layout, overlap=overlap,
+                            pipeline=pipelined)
         pipe._force_chunks = overlap
         for _ in range(2):                                      # twice: buffers reused across steps
             k3d, pk, nm = pipe(x, y, z, w)
         case = {"order": order, "weighted": weighted, "transport": pipe.transport, "layout": "xfast" if pipe.xfast else "xslow",
-                "overlap": overlap}
-        if transport == "p2p" and layout == "xfast" and overlap and order == 4:
+                "overlap": overlap, "pipelined": bool(pipelined and pipe._can_pipeline(x.numel()))}
+        if transport == "p2p" and layout == "xfast" and overlap and pipelined and order == 4:
             # the host-buffer pipeline (what bench.py's e2e times) must give the same numbers
             host = SlabHostPipeline(pipe, x.numel(), weighted=weighted, n_chunks=3)
             hk, hpk, hnm = host(x.cpu().numpy(), y.cpu().numpy(), z.cpu().numpy(), None if w is None else w.cpu().numpy())

@@ -29,18 +29,22 @@ def test_slab_pipeline_over_real_ranks(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "helpers", "multi_rank_check.py"), "256", "2e6"]
-    r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    env = dict(os.environ)
+    if world == 2:
+        env["JPS_SLAB_CHUNKS"] = "4"      # 128 owned planes -> 4 pieces of 32: the TMA bulk-store peer kernel takes them
+    r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-4000:]
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("MULTI_RANK_RESULT ")]
     assert line, r.stdout[-4000:]
     res = json.loads(line[-1][len("MULTI_RANK_RESULT "):])
-    assert res["world"] == world and len(res["cases"]) == 12
+    assert res["world"] == world and len(res["cases"]) == 15
     for c in res["cases"]:
         assert c["counts_equal"] and c["k_equal"], c
         assert c["max_rel_P0"] <= 1e-5, c
         if "host_pipeline_max_rel" in c:
             assert c["host_pipeline_max_rel"] <= 1e-5, c
     assert {c["transport"] for c in res["cases"]} == {"p2p", "nccl"}, "the peer-memory transport must have been exercised"
+    assert any(c["pipelined"] for c in res["cases"]), "the deposit / FFT / transfer pipeline must have been exercised"
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
     with open(os.path.join(out, f"multi_rank_parity_w{world}.json"), "w") as f:
