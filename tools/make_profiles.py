@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--raw", action="append", required=True)
     ap.add_argument("--launches")
     ap.add_argument("--tag", default="r1")
+    ap.add_argument("--suffix", default="c2", help="workload suffix of the output files (c2, c4_rank, ...)")
     ap.add_argument("--title", default="bench.py C2 (Np=1e8 lognormal, TSC, N=512)")
     a = ap.parse_args()
     kernels = OrderedDict()
@@ -62,7 +63,8 @@ def main():
         for k, d in read_raw(p).items():
             kernels[short(k)] = (k, d, os.path.basename(p))
     prof = os.path.join(ROOT, "profiles")
-    with open(os.path.join(prof, f"{a.tag}_ncu_full_summary.md"), "w") as f:
+    summary = f"{a.tag}_ncu_full_summary.md" if a.suffix == "c2" else f"{a.tag}_ncu_full_summary_{a.suffix}.md"
+    with open(os.path.join(prof, summary), "w") as f:
         f.write(f"# ncu --set full --clock-control none --import-source on, {a.title}\n\n"
                 "One launch per kernel inside the `jps_timed` NVTX range.  Exported with "
                 "`ncu -i <rep> --page raw --csv` and condensed by tools/make_profiles.py.  Durations under ncu are\n"
@@ -78,10 +80,10 @@ def main():
             rd, wr = d.get("dram__bytes_read.sum"), d.get("dram__bytes_write.sum")
             if rd and wr:
                 traffic[s] = float(rd[0]) * UNIT_SCALE.get(rd[1], 1.0) + float(wr[0]) * UNIT_SCALE.get(wr[1], 1.0)
-    with open(os.path.join(prof, f"{a.tag}_ncu_dram_traffic_c2.json"), "w") as f:
+    with open(os.path.join(prof, f"{a.tag}_ncu_dram_traffic_{a.suffix}.json"), "w") as f:
         json.dump(traffic, f, indent=1)
     if a.launches:
-        shutil.copy(a.launches, os.path.join(prof, f"{a.tag}_ncu_launches_c2.csv"))
+        shutil.copy(a.launches, os.path.join(prof, f"{a.tag}_ncu_launches_{a.suffix}.csv"))
         tot = OrderedDict()
         nsteps = 0
         for r in csv.reader(l for l in open(a.launches) if l.startswith('"')):
@@ -95,8 +97,8 @@ def main():
                 nsteps += 1
         nsteps = max(nsteps, 1)
         s = sum(tot.values())
-        with open(os.path.join(prof, f"{a.tag}_ncu_launch_shares_c2.txt"), "w") as f:
-            f.write(f"ncu launch list (profiles/{a.tag}_ncu_launches_c2.csv), {nsteps} steps of bench.py C2; "
+        with open(os.path.join(prof, f"{a.tag}_ncu_launch_shares_{a.suffix}.txt"), "w") as f:
+            f.write(f"ncu launch list (profiles/{a.tag}_ncu_launches_{a.suffix}.csv), {nsteps} steps of {a.title}; "
                     "share of the summed kernel time\n")
             for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
                 f.write(f"{k[:48]:<48s} {v / nsteps:7.3f} ms/step  {100 * v / s:5.1f}%\n")
