@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256) pk_bin_xfast_kernel(SlabPkParams P) {
     const float wy = P.wl[iy], wz = P.wl[kz];
     const int k2yz = ky * ky + kz * kz;
     const float kz2 = (float)(kz * kz);
-    constexpr int UNR = 4;
+    constexpr int UNR = 8;                         // 2 x 8 loads of 8 bytes in flight per lane (few warps per SM)
     for (int ab = 0; ab <= mid; ab += 32 * UNR) {
       float2 d0[UNR], d1[UNR];
 #pragma unroll
@@ -465,6 +465,8 @@ __global__ void slab_finalize_kernel(int nb, const float* __restrict__ edges, co
   k3d[j] = (0.5f * (edges[j + 1] + edges[j])) * kF;
 }
 
+constexpr int kXfastWarpSmem = 112 * 1024;      // most shared memory the x-fast kernel takes for warp-private sums + tables
+
 // Launch of the y-sharded / x-fast binning kernels on one spectrum shard (accumulators zeroed first).
 static int bin_layout(jps_plan* tp, const float2* dk, int nyl, int y0, int xfast, int kz_major, const BinTable& T,
                       const float* dc, int normalise, int mas_order, cudaStream_t s) {
@@ -482,17 +484,30 @@ static int bin_layout(jps_plan* tp, const float2* dk, int nyl, int y0, int xfast
   P.seg_bp = T.seg_bp; P.seg_val = T.seg_val; P.coarse = T.coarse;
   P.nseg = seg ? T.nseg : 0; P.ncoarse = seg ? T.ncoarse : 0;
   const size_t seg_bytes = seg ? (size_t)(2 * T.nseg + T.ncoarse) * sizeof(int) : 0;
-  const int threads = 256, warps = 8;
+  // Accumulation mode.  The x-fast kernel folds only TWO rows before binning (the fold kernel folds eight), and
+  // along kx the bin changes almost every lane once |kx| dominates |k|: ~0.5 segment heads per mode.  With one
+  // accumulator set per CTA that is ~3e9 shared-memory float CAS atomics on a 2048^3 spectrum, contended by the 8
+  // warps of a CTA working on neighbouring rows (measured: 13.4 ms = 2.6 TB/s).  So the x-fast kernel takes
+  // WARP-PRIVATE accumulators (plain +=, no atomics) whenever they fit, with fewer warps per CTA for more bins.
+  int warps = 8;
+  bool warp_private = T.nbc <= kMaxSmemBins;
+  if (xfast) {
+    const size_t budget = 72 * 1024;             // 3 CTAs per SM
+    while (warps > 2 && (size_t)warps * T.nbc * 3 * sizeof(float) + seg_bytes > budget) warps >>= 1;
+    warp_private = (size_t)warps * T.nbc * 3 * sizeof(float) + seg_bytes <= (size_t)kXfastWarpSmem;
+    if (!warp_private) warps = 8;
+  }
+  const int threads = warps * 32;
   const long long items = xfast ? (long long)nyl * tp->nz : (long long)(tp->n / 2 + 1) * nyl;
   const long long want = (items + warps - 1) / warps;
   static PerDeviceFlag attr_set;
   if (!attr_set.get()) {
-    const int sw = (int)((size_t)warps * kMaxSmemBins * 3 * sizeof(float));
+    const int sw = (int)((size_t)8 * kMaxSmemBins * 3 * sizeof(float));
     const int sb = (int)((size_t)kMaxBlockBins * 3 * sizeof(float));
     const int sseg = (int)((size_t)(2 * kMaxSegments + 8192) * sizeof(int));       // segment tables (x-fast kernels)
     JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw));
     JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw + sseg));
+    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kXfastWarpSmem));
     JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb + sseg));
     JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, sseg));
     attr_set.set();
@@ -501,7 +516,7 @@ static int bin_layout(jps_plan* tp, const float2* dk, int nyl, int y0, int xfast
   KernelFn fn;
   size_t smem = 0;
   long long cap_per_sm = 0;
-  if (T.nbc <= kMaxSmemBins) {
+  if (warp_private) {
     fn = xfast ? pk_bin_xfast_kernel<ACC_WARP> : pk_bin_ysharded_kernel<ACC_WARP>;
     smem = (size_t)warps * T.nbc * 3 * sizeof(float) + seg_bytes;
   } else if (T.nbc <= kMaxBlockBins) {
