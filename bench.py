@@ -701,11 +701,15 @@ def run_c4_arm(a, wl):
         return 0
 
     kernels, roofline = kernel_table(prof, a.steps, ms, nloc, n ** 3 // world, n * n * nz // world, wl, world)
-    if "cufft_r2c" in kernels:
+    fft_parts = [k for k in ("cufft_r2c", "cufft_c2c_y", "cufft_c2c_x", "fft_transpose") if k in kernels]
+    fft = None
+    if fft_parts:
         b = 24 * n ** 3 // world
-        t = kernels["cufft_r2c"]["ms_per_launch"] * kernels["cufft_r2c"]["launches_per_step"]
-        kernels["cufft_r2c"].update(algorithmic_bytes_per_step=b, achieved_gbs=b / t / 1e6, frac_of_peak=b / t / 1e6 / measured_peak()[0],
-                                    note="3 passes x (read + write) of this rank's share; all cuFFT launches of a step together")
+        t = sum(kernels[k]["ms_per_launch"] * kernels[k]["launches_per_step"] for k in fft_parts)
+        fft = {"parts": fft_parts, "ms_per_step_rank0": t, "algorithmic_bytes_per_step": b, "achieved_gbs": b / t / 1e6,
+               "frac_of_peak": b / t / 1e6 / measured_peak()[0],
+               "note": "forward R2C transform of this rank's share against the 3-pass model (3 axes x read + write = 24 B per "
+                       "cell); cuFFT launches (library) + our transposing kernels of the pencil plan"}
     paint_ms = sum(kernels[k]["ms_per_launch"] * kernels[k]["launches_per_step"]
                    for k in ("bucket_count", "bucket_scan", "bucket_scatter", "bucket_fine", "paint_tile", "paint_atomic") if k in kernels)
     peak, _ = measured_peak()
@@ -741,6 +745,7 @@ def run_c4_arm(a, wl):
         "roofline": roofline,
         "whole_step": {"algorithmic_bytes": e2e_bytes, "frac_of_peak_all_gpus": e2e_bytes / ms / 1e6 / (peak * world)},
         "painting": painting,
+        "fft": fft,
         "kernels": kernels,
         "stages_ms_max_over_ranks": stages or None,
         "transpose": transpose,

@@ -119,7 +119,7 @@ def check(rc: int, what: str = "") -> None:
 
 
 # kernels that are library calls (cuFFT, cudaMemset), not hand-written ones
-LIBRARY_KERNELS = ("cufft_r2c", "cufft_c2r", "memset")
+LIBRARY_KERNELS = ("cufft_r2c", "cufft_c2r", "cufft_c2c_y", "cufft_c2c_x", "memset")
 
 
 def profile_enable(on: bool) -> None:

@@ -92,6 +92,8 @@ enum KernelId {
   K_MOCK_POPULATE,
   K_INTERLACE,
   K_TRANSPOSE,
+  K_FFT_C2C_Y,      // pencil plan: contiguous 1-D passes along y and x (cuFFT, library)
+  K_FFT_C2C_X,
   K_NUM
 };
 
@@ -174,6 +176,7 @@ struct jps_plan {
   cufftHandle fz = 0, fy = 0, fx = 0;
   bool fz_ok = false, fy_ok = false, fx_ok = false;
   float2* dk2 = nullptr;
+  int pitch_z = 0;              // row pitch (complex elements) of the z-pass output [x][y][pitch_z]: n/2+1 padded to 32 bytes
 
   // workspace partition (all device pointers inside the caller's workspace)
   char* ws = nullptr;

@@ -3,6 +3,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 
 namespace jps {
@@ -21,7 +22,7 @@ static const char* kKernelNames[K_NUM] = {
     "paint_atomic", "bucket_count", "bucket_scan", "bucket_scatter", "bucket_fine", "paint_tile", "pk_fold_bin",
     "pk_count_modes", "pk_finalize", "cufft_r2c", "cufft_c2r", "memset", "shell_filter",
     "triple_reduce", "xi_bin", "misc", "text_index", "text_parse", "text_compact",
-    "mock_field", "mock_populate", "interlace_combine", "fft_transpose"};
+    "mock_field", "mock_populate", "interlace_combine", "fft_transpose", "cufft_c2c_y", "cufft_c2c_x"};
 
 // Distinct plans may be driven from distinct host threads (include/jps.h), so the process-wide
 // accounting is atomic counters + one mutex around the event lists.
@@ -95,6 +96,15 @@ void host_window_axis(int n, int p, float* out) {
   }
 }
 
+// Row pitch of the pencil plan's z-pass output: n/2+1 is odd for even n, which leaves every second row of the
+// R2C output 8-byte aligned only; padding to a multiple of 4 complex elements (32 bytes) keeps cuFFT's stores and
+// the transpose's loads sector aligned (JPS_PENCIL_PAD=0 restores the dense pitch for A/B runs).
+static int pencil_pitch_z(int n) {
+  static const bool pad = [] { const char* e = getenv("JPS_PENCIL_PAD"); return !(e && atoi(e) == 0); }();
+  const int nz = n / 2 + 1;
+  return pad ? (nz + 3) / 4 * 4 : nz;
+}
+
 struct TableLayout {
   size_t lut, compact_to_bin, bin_to_compact, edges, cnt, ksum, lastidx, seg_bp, seg_val, coarse;
 };
@@ -113,7 +123,7 @@ static Layout make_layout(int n, int pitch, size_t fft_work_bytes, int n_shell_f
   L.cap = (int)std::min<int64_t>(k2max + 2, 262144);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-  L.dk = take(tables_only ? 0 : (size_t)n * n * pitch * sizeof(float2));
+  L.dk = take(tables_only ? 0 : (size_t)n * n * (pencil ? pencil_pitch_z(n) : pitch) * sizeof(float2));
   L.dk2 = take(pencil ? (size_t)n * n * pitch * sizeof(float2) : 0);
   L.fft_work = take(fft_work_bytes);
   for (int i = 0; i < kNumTables; ++i) {
@@ -191,6 +201,7 @@ static int make_pencil_c2c(int n, long long batch, cufftHandle* h, size_t* work)
 
 static int pitch_for(int n) { return n / 2 + 1; }
 
+
 }  // namespace jps
 
 using namespace jps;
@@ -236,7 +247,7 @@ extern "C" int jps_plan_workspace_bytes(int n_mesh, int n_shell_fields, int flag
   if (flags & JPS_PLAN_FFT_PENCIL) {
     JPS_REQUIRE(n_shell_fields == 0, "jps_plan_workspace_bytes: a JPS_PLAN_FFT_PENCIL plan has no shell fields");
     size_t wz = 0, wy = 0;
-    int rcp = make_pencil_z(n_mesh, pitch, &h, &wz);
+    int rcp = make_pencil_z(n_mesh, pencil_pitch_z(n_mesh), &h, &wz);
     cufftDestroy(h);
     if (rcp) return rcp;
     rcp = make_pencil_c2c(n_mesh, (long long)n_mesh * pitch, &h, &wy);
@@ -287,7 +298,8 @@ extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* 
       return JPS_ERR_INVALID;
     }
     p->pencil = true;
-    rc = make_pencil_z(n_mesh, p->pitch, &p->fz, &w1);
+    p->pitch_z = pencil_pitch_z(n_mesh);
+    rc = make_pencil_z(n_mesh, p->pitch_z, &p->fz, &w1);
     if (rc) { delete p; return rc; }
     p->fz_ok = true;
     rc = make_pencil_c2c(n_mesh, (long long)n_mesh * p->pitch, &p->fy, &w2);

@@ -376,11 +376,11 @@ int ensure_bin_table(jps_plan* plan, const float* kedges_grid, int nb, int mode,
 // Batched 2-D transpose of complex64: in[b][r][c] -> out[b][c][r].  64 x 64 tiles through shared memory,
 // 256 threads, 16 elements per thread: loads and stores are both 256-byte runs per warp row.
 __global__ void __launch_bounds__(256) transpose_c64_kernel(const float2* __restrict__ in, float2* __restrict__ out,
-                                                            long long rows, long long cols) {
+                                                            long long rows, long long cols, long long in_pitch) {
   __shared__ float2 tile[64][65];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;              // 8 rows of 32 lanes
   const long long c0 = (long long)blockIdx.x * 64, r0 = (long long)blockIdx.y * 64;
-  const float2* src = in + (size_t)blockIdx.z * rows * cols;
+  const float2* src = in + (size_t)blockIdx.z * rows * in_pitch;
   float2* dst = out + (size_t)blockIdx.z * rows * cols;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(256) transpose_c64_kernel(const float2* __rest
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const long long c = c0 + tx + 32 * h;
-      if (r < rows && c < cols) tile[ty + 8 * i][tx + 32 * h] = __ldg(src + r * cols + c);
+      if (r < rows && c < cols) tile[ty + 8 * i][tx + 32 * h] = __ldg(src + r * in_pitch + c);
     }
   }
   __syncthreads();
@@ -403,11 +403,13 @@ __global__ void __launch_bounds__(256) transpose_c64_kernel(const float2* __rest
   }
 }
 
-static int transpose_c64(const float2* in, float2* out, long long batch, long long rows, long long cols, cudaStream_t s) {
+// in[b][r][0..cols) with row pitch in_pitch (>= cols) -> out[b][c][r], dense
+static int transpose_c64(const float2* in, float2* out, long long batch, long long rows, long long cols, long long in_pitch,
+                         cudaStream_t s) {
   const long long gx = (cols + 63) / 64, gy = (rows + 63) / 64;
   JPS_REQUIRE(gy <= 65535 && batch <= 65535 && gx <= 2147483647LL, "transpose: grid too large");
   ScopedLaunch L(K_TRANSPOSE, s);
-  transpose_c64_kernel<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)batch), 256, 0, s>>>(in, out, rows, cols);
+  transpose_c64_kernel<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)batch), 256, 0, s>>>(in, out, rows, cols, in_pitch);
   JPS_CHECK_LAUNCH();
   return JPS_OK;
 }
@@ -425,16 +427,16 @@ static int forward_fft_pencil(jps_plan* plan, const float* mesh, cudaStream_t s)
     ScopedLaunch L(K_FFT_R2C, s);
     JPS_CHECK_CUFFT(cufftExecR2C(plan->fz, (cufftReal*)mesh, (cufftComplex*)plan->dk));               // [x][y][kz]
   }
-  int rc = transpose_c64(plan->dk, plan->dk2, n, n, nz, s);                                            // [x][kz][y]
+  int rc = transpose_c64(plan->dk, plan->dk2, n, n, nz, plan->pitch_z, s);                             // [x][kz][y]
   if (rc) return rc;
   {
-    ScopedLaunch L(K_FFT_R2C, s);
+    ScopedLaunch L(K_FFT_C2C_Y, s);
     JPS_CHECK_CUFFT(cufftExecC2C(plan->fy, (cufftComplex*)plan->dk2, (cufftComplex*)plan->dk2, CUFFT_FORWARD));
   }
-  rc = transpose_c64(plan->dk2, plan->dk, 1, n, nz * n, s);                                            // [kz][y][x]
+  rc = transpose_c64(plan->dk2, plan->dk, 1, n, nz * n, nz * n, s);                                    // [kz][y][x]
   if (rc) return rc;
   {
-    ScopedLaunch L(K_FFT_R2C, s);
+    ScopedLaunch L(K_FFT_C2C_X, s);
     JPS_CHECK_CUFFT(cufftExecC2C(plan->fx, (cufftComplex*)plan->dk, (cufftComplex*)plan->dk, CUFFT_FORWARD));
   }
   return JPS_OK;
