@@ -176,7 +176,7 @@ struct jps_plan {
   cufftHandle fz = 0, fy = 0, fx = 0;
   bool fz_ok = false, fy_ok = false, fx_ok = false;
   float2* dk2 = nullptr;
-  int pitch_z = 0;              // row pitch (complex elements) of the z-pass output [x][y][pitch_z]: n/2+1 padded to 32 bytes
+  float2* ztw = nullptr;        // [n/4 + 1] twiddles e^{-2 pi i k / n} of the real-to-complex untangle step
 
   // workspace partition (all device pointers inside the caller's workspace)
   char* ws = nullptr;
@@ -211,7 +211,8 @@ int64_t edge_threshold(float e, bool strict, int64_t k2max);
 int forward_fft(jps_plan* plan, const float* mesh, cudaStream_t s);
 // slab.cu: fold +-kx / window / Legendre weights / k-bin sums of a spectrum stored x-fastest, into
 // tables->acc (zeroed first).  kz_major = 0: dk[yl][kz][x] (y-shard [y0, y0 + nyl) of a slab rank);
-// kz_major = 1: dk[kz][yl][x] (the pencil plan's layout, nyl = n, y0 = 0).  dc: device Re rho_hat(0).
+// kz_major = 1: dk[kz][yl][x] (the pencil plan's layout, nyl = n, y0 = 0: the +-ky partner row is local and is
+// folded too).  dc: device Re rho_hat(0).
 int bin_xfast_layout(jps_plan* tables, const float2* dk, int nyl, int y0, int kz_major, const BinTable& T,
                      const float* dc, int normalise, int mas_order, cudaStream_t s);
 double ref_volume(float box_size, int n);

@@ -96,21 +96,13 @@ void host_window_axis(int n, int p, float* out) {
   }
 }
 
-// Row pitch of the pencil plan's z-pass output: n/2+1 is odd for even n, which leaves every second row of the
-// R2C output 8-byte aligned only; padding to a multiple of 4 complex elements (32 bytes) keeps cuFFT's stores and
-// the transpose's loads sector aligned (JPS_PENCIL_PAD=0 restores the dense pitch for A/B runs).
-static int pencil_pitch_z(int n) {
-  static const bool pad = [] { const char* e = getenv("JPS_PENCIL_PAD"); return !(e && atoi(e) == 0); }();
-  const int nz = n / 2 + 1;
-  return pad ? (nz + 3) / 4 * 4 : nz;
-}
 
 struct TableLayout {
   size_t lut, compact_to_bin, bin_to_compact, edges, cnt, ksum, lastidx, seg_bp, seg_val, coarse;
 };
 
 struct Layout {
-  size_t dk, dk2, fft_work, wlut, acc, scal, isum, shell, total;
+  size_t dk, dk2, ztw, fft_work, wlut, acc, scal, isum, shell, total;
   TableLayout t[kNumTables];
   int cap;
 };
@@ -123,8 +115,9 @@ static Layout make_layout(int n, int pitch, size_t fft_work_bytes, int n_shell_f
   L.cap = (int)std::min<int64_t>(k2max + 2, 262144);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-  L.dk = take(tables_only ? 0 : (size_t)n * n * (pencil ? pencil_pitch_z(n) : pitch) * sizeof(float2));
+  L.dk = take(tables_only ? 0 : (size_t)n * n * pitch * sizeof(float2));
   L.dk2 = take(pencil ? (size_t)n * n * pitch * sizeof(float2) : 0);
+  L.ztw = take(pencil ? (size_t)(n / 4 + 2) * sizeof(float2) : 0);
   L.fft_work = take(fft_work_bytes);
   for (int i = 0; i < kNumTables; ++i) {
     L.t[i].lut = take((size_t)(k2max + 1) * 4);
@@ -181,14 +174,6 @@ static int make_r2c_inplace(int n, int pitch, cufftHandle* h, size_t* work) {
 }
 
 // contiguous batched 1-D plans of the pencil decomposition
-static int make_pencil_z(int n, int pitch, cufftHandle* h, size_t* work) {          // R2C, n*n lines of n reals
-  JPS_CHECK_CUFFT(cufftCreate(h));
-  JPS_CHECK_CUFFT(cufftSetAutoAllocation(*h, 0));
-  long long dims[1] = {n};
-  long long inembed[1] = {n}, onembed[1] = {pitch};
-  JPS_CHECK_CUFFT(cufftMakePlanMany64(*h, 1, dims, inembed, 1, n, onembed, 1, pitch, CUFFT_R2C, (long long)n * n, work));
-  return JPS_OK;
-}
 
 static int make_pencil_c2c(int n, long long batch, cufftHandle* h, size_t* work) {   // C2C, `batch` lines of n
   JPS_CHECK_CUFFT(cufftCreate(h));
@@ -247,7 +232,8 @@ extern "C" int jps_plan_workspace_bytes(int n_mesh, int n_shell_fields, int flag
   if (flags & JPS_PLAN_FFT_PENCIL) {
     JPS_REQUIRE(n_shell_fields == 0, "jps_plan_workspace_bytes: a JPS_PLAN_FFT_PENCIL plan has no shell fields");
     size_t wz = 0, wy = 0;
-    int rcp = make_pencil_z(n_mesh, pencil_pitch_z(n_mesh), &h, &wz);
+    JPS_REQUIRE(n_mesh % 2 == 0, "jps_plan_workspace_bytes: JPS_PLAN_FFT_PENCIL needs an even mesh size");
+    int rcp = make_pencil_c2c(n_mesh / 2, (long long)n_mesh * n_mesh, &h, &wz);
     cufftDestroy(h);
     if (rcp) return rcp;
     rcp = make_pencil_c2c(n_mesh, (long long)n_mesh * pitch, &h, &wy);
@@ -297,9 +283,11 @@ extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* 
       set_error("jps_plan_create: JPS_PLAN_FFT_PENCIL excludes JPS_PLAN_TABLES_ONLY and shell fields");
       return JPS_ERR_INVALID;
     }
+    if (n_mesh % 2) { delete p; set_error("jps_plan_create: JPS_PLAN_FFT_PENCIL needs an even mesh size"); return JPS_ERR_INVALID; }
     p->pencil = true;
-    p->pitch_z = pencil_pitch_z(n_mesh);
-    rc = make_pencil_z(n_mesh, p->pitch_z, &p->fz, &w1);
+    // z-pass: the n reals of a line are read as n/2 complex numbers (even, odd samples): C2C of length n/2, then the
+    // untangle step of the real transform is done by OUR transposing kernel on the way (r2c_untangle_transpose)
+    rc = make_pencil_c2c(n_mesh / 2, (long long)n_mesh * n_mesh, &p->fz, &w1);
     if (rc) { delete p; return rc; }
     p->fz_ok = true;
     rc = make_pencil_c2c(n_mesh, (long long)n_mesh * p->pitch, &p->fy, &w2);
@@ -332,6 +320,7 @@ extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* 
   p->ws_bytes = workspace_bytes;
   p->dk = (float2*)(ws + L.dk);
   p->dk2 = pencil ? (float2*)(ws + L.dk2) : nullptr;
+  p->ztw = pencil ? (float2*)(ws + L.ztw) : nullptr;
   p->fft_work = ws + L.fft_work;
   p->fft_work_bytes = std::max(std::max(w1, w2), w3);
   for (int i = 0; i < kNumTables; ++i) {
@@ -367,6 +356,19 @@ extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* 
     set_error("jps_plan_create: cufftSetWorkArea failed (%d)", (int)r);
     jps_plan_destroy(p);
     return JPS_ERR_CUFFT;
+  }
+  if (pencil) {                                    // e^{-2 pi i k / n}, k = 0 .. n/4, evaluated in double
+    std::vector<float2> tw((size_t)n_mesh / 4 + 1);
+    for (int k = 0; k <= n_mesh / 4; ++k) {
+      const double ang = -2.0 * M_PI * (double)k / (double)n_mesh;
+      tw[(size_t)k] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    ce = cudaMemcpy(p->ztw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) {
+      set_error("jps_plan_create: twiddle table upload failed: %s", cudaGetErrorString(ce));
+      jps_plan_destroy(p);
+      return JPS_ERR_CUDA;
+    }
   }
   // window tables for p = 2, 3, 4 (tiny; synchronous copy at plan creation)
   std::vector<float> w((size_t)3 * n_mesh);

@@ -414,26 +414,80 @@ static int transpose_c64(const float2* in, float2* out, long long batch, long lo
   return JPS_OK;
 }
 
-// mesh[x][y][z] -> dk[kz][ky][kx]: 1-D R2C along z, transpose (y fastest), 1-D C2C along y, transpose
-// (x fastest), 1-D C2C along x.  Every cuFFT pass is a contiguous batched transform (one read + one write
-// of the array at ~6 TB/s, measured on the slab path's x-pass), where the monolithic 3-D plan and the
+// Real-to-complex "untangle" step fused with the first transpose.  The z-pass reads the n reals of a line as
+// M = n/2 complex numbers z[m] = x[2m] + i x[2m+1] and transforms them with a C2C of length M (Z).  The spectrum of
+// the real line follows from pairs (Z[k], Z[M-k]):
+//     E = (Z[k] + conj Z[M-k]) / 2,  O = -i (Z[k] - conj Z[M-k]) / 2,  T = e^{-2 pi i k / n} O
+//     X[k] = E + T,   X[M-k] = conj(E - T)            (k = 0 .. M/2;  Z[M] = Z[0];  X[M] comes from k = 0)
+// cuFFT does this in a separate pass over the array (its R2C of 2048 reals = C2C-1024 + `postprocess_kernel`,
+// 17 ms of a 26.7 ms z-pass at 2048^3); here it rides on the transpose that is needed anyway: a CTA loads a
+// 64 (y) x 32 (k) tile and the mirrored tile (coalesced along k, forwards and backwards), and writes rows k and
+// M-k of the transposed array out[x][kz][y] (coalesced along y).  One read and one write of the array instead of three.
+__global__ void __launch_bounds__(256) r2c_untangle_transpose_kernel(const float2* __restrict__ Z, float2* __restrict__ out,
+                                                                     const float2* __restrict__ tw, int n) {
+  __shared__ float2 ta[64][33], tb[64][33];
+  const int M = n / 2;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;              // 8 rows of 32 lanes
+  const int k0 = blockIdx.x * 32, y0 = blockIdx.y * 64;
+  const float2* src = Z + (size_t)blockIdx.z * n * M;                  // plane x: [y][M]
+  float2* dst = out + (size_t)blockIdx.z * (size_t)(M + 1) * n;        // plane x: [kz][y]
+  const int k = k0 + tx;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int y = y0 + ty + 8 * i;
+    if (y < n && k <= M / 2) {
+      ta[ty + 8 * i][tx] = __ldg(src + (size_t)y * M + k);
+      tb[ty + 8 * i][tx] = __ldg(src + (size_t)y * M + (k == 0 ? 0 : M - k));
+    }
+  }
+  __syncthreads();
+  // thread (t = k index within the tile, lanes along y)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = ty + 8 * i;
+    const int kk = k0 + t;
+    if (kk > M / 2) continue;
+    const float2 w = __ldg(tw + kk);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int yl = tx + 32 * h, y = y0 + yl;
+      if (y >= n) continue;
+      const float2 a = ta[yl][t], b = tb[yl][t];
+      const float ex = 0.5f * (a.x + b.x), ey = 0.5f * (a.y - b.y);          // E = (a + conj b) / 2
+      const float ox = 0.5f * (a.y + b.y), oy = -0.5f * (a.x - b.x);         // O = -i (a - conj b) / 2
+      const float tr = w.x * ox - w.y * oy, ti = w.x * oy + w.y * ox;        // T = w O
+      dst[(size_t)kk * n + y] = make_float2(ex + tr, ey + ti);
+      if (M - kk != kk) dst[(size_t)(M - kk) * n + y] = make_float2(ex - tr, -(ey - ti));
+    }
+  }
+}
+
+// mesh[x][y][z] -> dk[kz][ky][kx]: C2C of length n/2 along z on the real lines read as complex pairs, untangle +
+// transpose (y fastest), 1-D C2C along y, transpose (x fastest), 1-D C2C along x.  Every cuFFT pass is a contiguous
+// batched C2C (one read + one write of the array at ~6.5 TB/s, measured), where the monolithic 3-D plan and the
 // strided 1-D plans need the equivalent of 7-8 passes at 2048^3.
 static int forward_fft_pencil(jps_plan* plan, const float* mesh, cudaStream_t s) {
   const long long n = plan->n, nz = plan->nz;
+  JPS_REQUIRE(((uintptr_t)mesh & 7) == 0, "jps_powspec: the mesh must be 8-byte aligned for a JPS_PLAN_FFT_PENCIL plan");
   JPS_CHECK_CUFFT(cufftSetStream(plan->fz, s));
   JPS_CHECK_CUFFT(cufftSetStream(plan->fy, s));
   JPS_CHECK_CUFFT(cufftSetStream(plan->fx, s));
   {
-    ScopedLaunch L(K_FFT_R2C, s);
-    JPS_CHECK_CUFFT(cufftExecR2C(plan->fz, (cufftReal*)mesh, (cufftComplex*)plan->dk));               // [x][y][kz]
+    ScopedLaunch L(K_FFT_R2C, s);                                                   // Z[x][y][n/2]
+    JPS_CHECK_CUFFT(cufftExecC2C(plan->fz, (cufftComplex*)const_cast<float*>(mesh), (cufftComplex*)plan->dk, CUFFT_FORWARD));
   }
-  int rc = transpose_c64(plan->dk, plan->dk2, n, n, nz, plan->pitch_z, s);                             // [x][kz][y]
-  if (rc) return rc;
+  {
+    const int M = plan->n / 2;
+    ScopedLaunch L(K_TRANSPOSE, s);
+    r2c_untangle_transpose_kernel<<<dim3((unsigned)((M / 2 + 1 + 31) / 32), (unsigned)((n + 63) / 64), (unsigned)n), 256, 0, s>>>(
+        plan->dk, plan->dk2, plan->ztw, plan->n);                                   // [x][kz][y]
+  }
+  JPS_CHECK_LAUNCH();
   {
     ScopedLaunch L(K_FFT_C2C_Y, s);
     JPS_CHECK_CUFFT(cufftExecC2C(plan->fy, (cufftComplex*)plan->dk2, (cufftComplex*)plan->dk2, CUFFT_FORWARD));
   }
-  rc = transpose_c64(plan->dk2, plan->dk, 1, n, nz * n, nz * n, s);                                    // [kz][y][x]
+  int rc = transpose_c64(plan->dk2, plan->dk, 1, n, nz * n, nz * n, s);             // [kz][y][x]
   if (rc) return rc;
   {
     ScopedLaunch L(K_FFT_C2C_X, s);

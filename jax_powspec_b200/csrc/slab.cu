@@ -243,19 +243,25 @@ __global__ void __launch_bounds__(256) pk_bin_xfast_kernel(SlabPkParams P) {
     for (int i = threadIdx.x; i < P.ncoarse; i += blockDim.x) s_coarse[i] = P.coarse[i];
     __syncthreads();
   }
-  const long long items = (long long)P.nyl * nz;
+  // kz_major (the pencil plan's [kz][y][x]): the whole ky axis is local, so the rows y = b and y = n - b are folded
+  // together (4 modes per lane and step share |k|, mu, window, weights and bin); a slab shard folds +-kx only.
+  const bool fold_y = P.kz_major != 0;
+  const long long items = fold_y ? (long long)nz * (mid + 1) : (long long)P.nyl * nz;
   for (long long it = (long long)blockIdx.x * nwarps + warp; it < items; it += (long long)gridDim.x * nwarps) {
-    const int yl = P.kz_major ? (int)(it % P.nyl) : (int)(it / nz);
-    const int kz = P.kz_major ? (int)(it / P.nyl) : (int)(it % nz);
+    int yl, kz;
+    if (fold_y) { kz = (int)(it / (mid + 1)); yl = (int)(it % (mid + 1)); }
+    else { yl = (int)(it / nz); kz = (int)(it % nz); }
     const int iy = P.y0 + yl;
     const int ky = iy > mid ? iy - n : iy;
-    const float2* r = P.dk + (size_t)it * n;
+    const bool two_y = fold_y && yl > 0 && 2 * yl != n;
+    const float2* r = P.dk + (fold_y ? ((size_t)kz * n + yl) * n : (size_t)it * n);
+    const float2* r2 = two_y ? P.dk + ((size_t)kz * n + (n - yl)) * n : r;
     const float wy = P.wl[iy], wz = P.wl[kz];
     const int k2yz = ky * ky + kz * kz;
     const float kz2 = (float)(kz * kz);
-    constexpr int UNR = 8;                         // 2 x 8 loads of 8 bytes in flight per lane (few warps per SM)
+    constexpr int UNR = 4;
     for (int ab = 0; ab <= mid; ab += 32 * UNR) {
-      float2 d0[UNR], d1[UNR];
+      float2 d0[UNR], d1[UNR], d2[UNR], d3[UNR];
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         const int a = ab + 32 * u + lane;
@@ -263,6 +269,8 @@ __global__ void __launch_bounds__(256) pk_bin_xfast_kernel(SlabPkParams P) {
         const bool two = in && a > 0 && 2 * a != n;
         d0[u] = in ? __ldg(r + a) : make_float2(0.0f, 0.0f);
         d1[u] = two ? __ldg(r + (n - a)) : make_float2(0.0f, 0.0f);
+        d2[u] = (in && two_y) ? __ldg(r2 + a) : make_float2(0.0f, 0.0f);
+        d3[u] = (two && two_y) ? __ldg(r2 + (n - a)) : make_float2(0.0f, 0.0f);
       }
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
@@ -278,6 +286,10 @@ __global__ void __launch_bounds__(256) pk_bin_xfast_kernel(SlabPkParams P) {
           float re = d0[u].x * c, im = d0[u].y * c;
           float sum = re * re + im * im;
           re = d1[u].x * c; im = d1[u].y * c;
+          sum += re * re + im * im;
+          re = d2[u].x * c; im = d2[u].y * c;
+          sum += re * re + im * im;
+          re = d3[u].x * c; im = d3[u].y * c;
           sum += re * re + im * im;
           sum *= scale2;
           float mu2 = 0.0f;
@@ -465,8 +477,6 @@ __global__ void slab_finalize_kernel(int nb, const float* __restrict__ edges, co
   k3d[j] = (0.5f * (edges[j + 1] + edges[j])) * kF;
 }
 
-constexpr int kXfastWarpSmem = 112 * 1024;      // most shared memory the x-fast kernel takes for warp-private sums + tables
-
 // Launch of the y-sharded / x-fast binning kernels on one spectrum shard (accumulators zeroed first).
 static int bin_layout(jps_plan* tp, const float2* dk, int nyl, int y0, int xfast, int kz_major, const BinTable& T,
                       const float* dc, int normalise, int mas_order, cudaStream_t s) {
@@ -484,21 +494,14 @@ static int bin_layout(jps_plan* tp, const float2* dk, int nyl, int y0, int xfast
   P.seg_bp = T.seg_bp; P.seg_val = T.seg_val; P.coarse = T.coarse;
   P.nseg = seg ? T.nseg : 0; P.ncoarse = seg ? T.ncoarse : 0;
   const size_t seg_bytes = seg ? (size_t)(2 * T.nseg + T.ncoarse) * sizeof(int) : 0;
-  // Accumulation mode.  The x-fast kernel folds only TWO rows before binning (the fold kernel folds eight), and
-  // along kx the bin changes almost every lane once |kx| dominates |k|: ~0.5 segment heads per mode.  With one
-  // accumulator set per CTA that is ~3e9 shared-memory float CAS atomics on a 2048^3 spectrum, contended by the 8
-  // warps of a CTA working on neighbouring rows (measured: 13.4 ms = 2.6 TB/s).  So the x-fast kernel takes
-  // WARP-PRIVATE accumulators (plain +=, no atomics) whenever they fit, with fewer warps per CTA for more bins.
-  int warps = 8;
-  bool warp_private = T.nbc <= kMaxSmemBins;
-  if (xfast) {
-    const size_t budget = 72 * 1024;             // 3 CTAs per SM
-    while (warps > 2 && (size_t)warps * T.nbc * 3 * sizeof(float) + seg_bytes > budget) warps >>= 1;
-    warp_private = (size_t)warps * T.nbc * 3 * sizeof(float) + seg_bytes <= (size_t)kXfastWarpSmem;
-    if (!warp_private) warps = 8;
-  }
+  // (Measured and dropped: warp-private accumulators for ~1000 bins with 4 warps per CTA -- 24.6 ms against 13.4 ms
+  // on a 2048^3 spectrum.  The kernel is bound by instructions per byte (segment lookup, segmented reduction and
+  // Legendre weights serve only the modes folded before them), not by its shared atomics: fold more instead.)
+  const int warps = 8;
+  const bool warp_private = T.nbc <= kMaxSmemBins;
   const int threads = warps * 32;
-  const long long items = xfast ? (long long)nyl * tp->nz : (long long)(tp->n / 2 + 1) * nyl;
+  const long long items = (xfast && kz_major) ? (long long)tp->nz * (tp->n / 2 + 1)
+                          : xfast ? (long long)nyl * tp->nz : (long long)(tp->n / 2 + 1) * nyl;
   const long long want = (items + warps - 1) / warps;
   static PerDeviceFlag attr_set;
   if (!attr_set.get()) {
@@ -507,7 +510,7 @@ static int bin_layout(jps_plan* tp, const float2* dk, int nyl, int y0, int xfast
     const int sseg = (int)((size_t)(2 * kMaxSegments + 8192) * sizeof(int));       // segment tables (x-fast kernels)
     JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw));
     JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kXfastWarpSmem));
+    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw + sseg));
     JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb + sseg));
     JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, sseg));
     attr_set.set();

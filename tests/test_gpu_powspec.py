@@ -233,4 +233,4 @@ def test_pencil_fft_plan_equals_3d_plan_and_oracle(jps, n, order):
     _check_pk(pkb, nmb, pk64, counts, tol=2e-5)
     # shot noise and a second call on the same plan (buffers reused)
     kb2, pkb2, _ = (t.cpu().numpy() for t in b(x, y, z))
-    np.testing.assert_allclose(pkb2, pkb, rtol=1e-6)
+    assert rel_to_monopole(pkb2.astype(np.float64), pkb.astype(np.float64)).max() < 2e-6     # atomic order of the painter only
