@@ -423,14 +423,21 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(PaintParams p, Tile
 constexpr int COARSE_CHUNK = JPS_COARSE_CHUNK;     // 64 KB of staged records per CTA
 constexpr int COARSE_THREADS = JPS_COARSE_THREADS;
 constexpr int COARSE_QPT = COARSE_CHUNK / (4 * COARSE_THREADS);   // quads (4 particles) per thread
-constexpr int kMaxGroups = 2048;
+constexpr int kMaxGroups = 4096;         // capacity (12-bit group ids in the coarse pass); the partition uses max_groups() of them
+
+// Groups of the coarse partition.  More groups = fewer tiles per group for the fine pass (which is latency bound on
+// its scattered write frontiers) but shorter runs per (CTA, group) in the coarse pass.  JPS_MAX_GROUPS overrides (A/B).
+static int max_groups() {
+  static const int g = [] { const char* e = getenv("JPS_MAX_GROUPS"); const int v = e ? atoi(e) : 0; return (v >= 64 && v <= kMaxGroups) ? v : 2048; }();
+  return g;
+}
 
 // exclusive scan of a[0..n) in shared memory, in place, by all threads of the CTA (n <= 4 * blockDim);
-// returns the total.  `scratch` holds >= 33 words.
+// returns the total.  `scratch` holds >= 33 words.  n <= 8 * blockDim.
 __device__ __forceinline__ unsigned block_scan_inplace(unsigned* a, int n, unsigned* scratch) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x + 31) >> 5;
   const int ipt = (n + blockDim.x - 1) / blockDim.x;
-  unsigned v[4];
+  unsigned v[8];
   unsigned tsum = 0;
   for (int j = 0; j < ipt; ++j) {
     const int i = tid * ipt + j;
@@ -1276,7 +1283,7 @@ static int run_bucket_two_level(const PaintParams& p, const TileGeom& g, const S
   unsigned* gcursor = (unsigned*)(ws + L.gcursor);
   const int nbuckets = g.ntiles + 1;               // + the outlier bucket
   int gshift = 0;
-  while (((nbuckets + (1 << gshift) - 1) >> gshift) > kMaxGroups) ++gshift;
+  while (((nbuckets + (1 << gshift) - 1) >> gshift) > max_groups()) ++gshift;
   const int ngroups = (nbuckets + (1 << gshift) - 1) >> gshift;
   // Tile offsets BEFORE the partition (the fine pass then reads its records once): from the per-SM
   // shared-memory histogram when the tile table fits it, from global reds into the (L2-resident) table

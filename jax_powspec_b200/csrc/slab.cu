@@ -489,7 +489,10 @@ static int bin_layout(jps_plan* tp, const float2* dk, int nyl, int y0, int xfast
   P.dk = dk; P.n = tp->n; P.nz = tp->nz; P.nyl = nyl; P.y0 = y0;
   P.lut = T.lut; P.wl = tp->wlut + (size_t)(mas_order - 2) * tp->n; P.nbc = T.nbc; P.acc = tp->acc;
   P.dc = dc; P.normalise = normalise; P.kz_major = kz_major;
-  static const bool no_seg = [] { const char* e = getenv("JPS_BIN_LUT"); return e && !strcmp(e, "global"); }();
+  // JPS_BIN_LUT=segments stages the k^2 -> bin table in shared memory in segment form.  Measured on the 2048^3 shards
+  // of 2 B200s: 7.6 ms against 6.1 ms with the plain L2-resident lut -- the sqrt + scan costs more instructions than the
+  // sector traffic it saves (the kernel is bound by instructions per byte), so the lut stays the default.
+  static const bool no_seg = [] { const char* e = getenv("JPS_BIN_LUT"); return !(e && !strcmp(e, "segments")); }();
   const bool seg = xfast && T.nseg > 0 && !no_seg;
   P.seg_bp = T.seg_bp; P.seg_val = T.seg_val; P.coarse = T.coarse;
   P.nseg = seg ? T.nseg : 0; P.ncoarse = seg ? T.ncoarse : 0;
@@ -726,8 +729,11 @@ extern "C" int jps_slab_pack_p2p_planes(jps_slab_plan_t* p, const void* yz, void
     // quarter of the SMs' worth of CTAs keeps the links busy without starving cuFFT
     static const int per_sm_env = [] { const char* e = getenv("JPS_PACK_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
     const long long cap = (x_count == p->nxl) ? (long long)kNumSMs * 8 : (long long)kNumSMs * (per_sm_env > 0 ? per_sm_env : 2);
-    // JPS_PACK_KERNEL=ldst forces the plain load/store transposing kernel (A/B runs)
-    static const bool no_tma = [] { const char* e = getenv("JPS_PACK_KERNEL"); return e && !strcmp(e, "ldst"); }();
+    // JPS_PACK_KERNEL=tma selects the TMA bulk-store variant.  Measured on 2 B200s (2048^3, 8.6 GB leaving each
+    // rank, kernel alone): straight contiguous peer copy 12.4 ms = 692 GB/s; the plain load/store transposing kernel
+    // 12.6 ms = 0.99 of it; the TMA variant 14.0 ms = 0.89 (one warp serialises 32 UBLKCP issues per 16 KB tile while
+    // the other seven wait at the barrier).  The link is already saturated by the plain kernel, so it stays the default.
+    static const bool no_tma = [] { const char* e = getenv("JPS_PACK_KERNEL"); return !(e && !strcmp(e, "tma")); }();
     static const int tma_ctas = [] { const char* e = getenv("JPS_PACK_TMA_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
     if (p->xfast && !no_tma && x_count % 32 == 0 && x_begin % 2 == 0 && p->nxl % 2 == 0 && p->n % 2 == 0) {
       const int tx = (x_count % 64 == 0) ? 64 : 32;

@@ -343,6 +343,7 @@ class SlabPipeline:
             nchunk = self.nxl // cp
             if self._side is None:
                 self._side = torch.cuda.Stream(self.device)
+            if self._events is None or len(self._events) != nchunk + 1:
                 self._events = [torch.cuda.Event() for _ in range(nchunk + 1)]
             order = list(range(1, nchunk - 1)) + [0] + ([nchunk - 1] if nchunk > 1 else [])
             for c in order:
@@ -496,6 +497,7 @@ class SlabPipeline:
             main = torch.cuda.current_stream(self.device)
             if self._halo_stream is None:
                 self._halo_stream = torch.cuda.Stream(self.device)
+            if self._halo_ev is None:
                 self._halo_ev = (torch.cuda.Event(), torch.cuda.Event())
             self._halo_ev[0].record(main)
             self._halo_stream.wait_event(self._halo_ev[0])
