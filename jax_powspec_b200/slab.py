@@ -551,7 +551,8 @@ class SlabHostPipeline:
             return
         self.inner = None
         d = pipe.device
-        self.cap, self.n_chunks = int(n_part_max), max(1, int(n_chunks))
+        import os
+        self.cap, self.n_chunks = int(n_part_max), max(1, int(os.environ.get("JPS_HOST_CHUNKS", n_chunks)))
         self.dev = [torch.empty(self.cap, dtype=torch.float32, device=d) for _ in range(4 if weighted else 3)]
         self.k3d = torch.empty(pipe.nb, dtype=torch.float32).pin_memory()
         self.pk = torch.empty((pipe.nb, 3), dtype=torch.float32).pin_memory()
