@@ -8,7 +8,7 @@ Default workload at every N: BASELINE.json configs[3] ("C4", the north-star conf
 over the N GPUs in x-slabs (strong scaling): every rank paints its slab's particles, ghost planes
 go round a ring, the R2C FFT is 2-D local + fused transposing peer-store over NVLink + 1-D local,
 the binned sums are all-reduced.  At N=1 the whole 2048^3 mesh lives on the one GPU (147 GB) and the
-step is the single-GPU pipeline with one 3-D FFT plan.  A "step" is one full pass
+step is the single-GPU pipeline with the pencil FFT plan (three contiguous 1-D passes).  A "step" is one full pass
 particles -> mesh -> delta_k -> multipoles.
 
   value  : whole-job Gparticles/s (1e9 / step time, max over ranks) with the catalogue resident in HBM
@@ -219,7 +219,7 @@ def workload_text(wl, world):
     if wl["name"] == "C4":
         return (f"C4: {wl['n_part']:.3g} uniform particles (every rank generates its x-slab's share), {MAS[wl['order']]} on "
                 f"{wl['n_mesh']}^3, box {wl['box']:g} Mpc/h, slab-sharded paint + distributed R2C FFT + P0/P2/P4 in kF-wide "
-                f"bins up to k_Nyquist" + (" (one rank: whole mesh on one GPU, one 3-D FFT plan)" if world == 1 else ""))
+                f"bins up to k_Nyquist" + (" (one rank: whole mesh on one GPU, pencil FFT plan)" if world == 1 else ""))
     return (f"C2: lognormal mock, {wl['n_part']:.3g} particles in redshift space (LOS z), {MAS[wl['order']]} on "
             f"{wl['n_mesh']}^3, box {wl['box']:g} Mpc/h, P0/P2/P4 in kF-wide bins up to k_Nyquist")
 

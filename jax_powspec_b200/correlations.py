@@ -355,6 +355,24 @@ class PaintPowspec:
         return self.k3d, self.pk, self.nm
 
 
+def host_chunks(n_chunks, n_part, n_cells):
+    """Pieces a host catalogue is streamed in.  Every piece pays the deposit's per-MESH cost again (zero,
+    convert and flush every tile: ~1.2 ps per cell) while it hides a copy that shrinks with the piece, so big
+    sparse meshes want few pieces and small dense ones many: measured on one B200, 1e9 particles on 2048^3:
+    2 / 4 / 8 / 16 pieces -> 336 / 322 / 368 / 580 ms end to end; 1e8 particles on 512^3: 8 pieces, PCIe bound.
+    Rule: copy time of the whole catalogue (55 GB/s) over five times the per-mesh cost, clamped to [2, 8];
+    an explicit n_chunks or JPS_HOST_CHUNKS overrides."""
+    import os
+    env = os.environ.get("JPS_HOST_CHUNKS")
+    if env:
+        return max(1, int(env))
+    if n_chunks is not None:
+        return max(1, int(n_chunks))
+    copy_s = 12.0 * n_part / 55e9
+    fixed_s = 1.2e-12 * n_cells
+    return int(min(8, max(2, copy_s / (5.0 * fixed_s))))
+
+
 class HostPipeline:
     """End-to-end call for catalogues that live in HOST memory (what a user of the reference has
     after np.loadtxt, tests/correlations.py:29-31): host->device copy of x, y, z[, w], paint,
@@ -365,12 +383,11 @@ class HostPipeline:
     step costs max(H2D, compute) instead of their sum.  Device staging buffers and pinned result
     buffers are allocated once."""
 
-    def __init__(self, pipe: PaintPowspec, n_part_max: int, weighted: bool = False, n_chunks: int = 8):
+    def __init__(self, pipe: PaintPowspec, n_part_max: int, weighted: bool = False, n_chunks=None):
         self.pipe = pipe
         d = pipe.device
         self.cap = int(n_part_max)
-        import os
-        self.n_chunks = max(1, int(os.environ.get("JPS_HOST_CHUNKS", n_chunks)))
+        self.n_chunks = host_chunks(n_chunks, self.cap, pipe.n ** 3)
         self.dev = [torch.empty(self.cap, dtype=torch.float32, device=d) for _ in range(4 if weighted else 3)]
         self.k3d = torch.empty(pipe.nb, dtype=torch.float32).pin_memory()
         self.pk = torch.empty((pipe.nb, 3), dtype=torch.float32).pin_memory()

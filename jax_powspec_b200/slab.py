@@ -25,7 +25,7 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import check, lib
-from .correlations import HostPipeline, PaintPowspec, _edge_ptr, _host_edges
+from .correlations import HostPipeline, PaintPowspec, _edge_ptr, _host_edges, host_chunks
 from .mas import new_paint_workspace, paint_workspace_bytes
 from .plan import check_particles, ptr, stream_ptr
 
@@ -546,15 +546,15 @@ class SlabHostPipeline:
     then halo exchange, distributed FFT, binning, allreduce, and the device->host read of
     (k3D, Pk3D, Nmodes3D).  This is what bench.py's ``e2e`` times on the sharded path."""
 
-    def __init__(self, pipe: SlabPipeline, n_part_max: int, weighted: bool = False, n_chunks: int = 8):
+    def __init__(self, pipe: SlabPipeline, n_part_max: int, weighted: bool = False, n_chunks=None):
         self.pipe = pipe
         if pipe.local is not None:                       # one rank: the single-GPU host pipeline
             self.inner = HostPipeline(pipe.local, n_part_max, weighted=weighted, n_chunks=n_chunks)
             return
         self.inner = None
         d = pipe.device
-        import os
-        self.cap, self.n_chunks = int(n_part_max), max(1, int(os.environ.get("JPS_HOST_CHUNKS", n_chunks)))
+        self.cap = int(n_part_max)
+        self.n_chunks = host_chunks(n_chunks, self.cap, pipe.nxa * pipe.n * pipe.n)
         self.dev = [torch.empty(self.cap, dtype=torch.float32, device=d) for _ in range(4 if weighted else 3)]
         self.k3d = torch.empty(pipe.nb, dtype=torch.float32).pin_memory()
         self.pk = torch.empty((pipe.nb, 3), dtype=torch.float32).pin_memory()
