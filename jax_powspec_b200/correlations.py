@@ -327,6 +327,8 @@ class PaintPowspec:
         npart = x.numel()
         if paint_workspace_bytes(self.n, npart, self.order, _lib.METHOD[self.method]) > self.ws_bytes:
             self.reserve(npart)
+        if self.n >= 512 and npart >= (1 << 18) and self.method != "atomic":
+            return self._call_overlapped(x, y, z, w, stride, npart, xmin, ymin, zmin)
         check(lib.jps_paint_powspec(self.plan.handle, ptr(x), ptr(y), ptr(z), ptr(w), stride, npart,
                                     float(xmin), float(ymin), float(zmin), self.box, self.order,
                                     int(self.wrap), _lib.COMPAT[self.compat], _lib.METHOD[self.method],
@@ -334,6 +336,28 @@ class PaintPowspec:
                                     ptr(self.ws), self.ws_bytes, ptr(self.k3d), ptr(self.pk), ptr(self.nm),
                                     ptr(self.sums), ptr(self.counts), stream_ptr()), "jps_paint_powspec")
         return self.k3d, self.pk, self.nm
+
+    def _call_overlapped(self, x, y, z, w, stride, npart, xmin, ymin, zmin):
+        """Big meshes: the mesh is zeroed on a side stream WHILE the bucketing passes run (they never touch the
+        mesh and leave most of the HBM bandwidth idle): 2048^3 = 34 GB = 4.6 ms of memset off the critical path.
+        Same C-ABI work as jps_paint_powspec, split at the phase boundary (jps_paint_slab_phase)."""
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_zero_stream", None) is None:
+            self._zero_stream = torch.cuda.Stream(self.device)
+            self._zero_ev = (torch.cuda.Event(), torch.cuda.Event())
+        self._zero_ev[0].record(main)                     # the previous step's transform has consumed the mesh
+        self._zero_stream.wait_event(self._zero_ev[0])
+        with torch.cuda.stream(self._zero_stream):
+            self.mesh.zero_()
+            self._zero_ev[1].record(self._zero_stream)
+        args = (self.n, 0, self.n, ptr(x), ptr(y), ptr(z), ptr(w), stride, npart, float(xmin), float(ymin), float(zmin),
+                self.box, self.order, int(self.wrap), _lib.COMPAT[self.compat], _lib.VARIANT_VEC, _lib.PAINT_SORTED,
+                ptr(self.mesh), ptr(self.ws), self.ws_bytes)
+        check(lib.jps_paint_slab_phase(*args, _lib.PAINT_PHASE_BUCKET, 0, 0, stream_ptr()), "jps_paint (bucket)")
+        main.wait_event(self._zero_ev[1])
+        check(lib.jps_paint_slab_phase(*args, _lib.PAINT_PHASE_DEPOSIT, 0, lib.jps_paint_tile_rows(self.n), stream_ptr()),
+              "jps_paint (deposit)")
+        return self.finish()
 
     # ---- the same pipeline in pieces (HostPipeline streams the catalogue through these)
     def paint_chunk(self, x, y, z, w=None, xmin=0.0, ymin=0.0, zmin=0.0):

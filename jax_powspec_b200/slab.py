@@ -212,6 +212,7 @@ class SlabPipeline:
         self._side, self._events = None, None
         self._halo_stream, self._halo_ev = None, None
         self._dep_stream = None
+        self._zero_stream, self._zero_ev = None, None
         self.pipeline = bool(pipeline)
         self._local_peers = False
         self._force_chunks = False                      # tests: take the chunked path on small meshes
@@ -301,6 +302,22 @@ class SlabPipeline:
     def stage_paint(self, x, y, z, w=None, xmin=0.0, ymin=0.0, zmin=0.0, zero=True):
         """Deposit this rank's particles into its planes (+ ghosts).  zero=False accumulates on top of the
         planes as they are (a catalogue streamed in pieces, SlabHostPipeline)."""
+        if zero and self.n >= 512 and x.numel() >= (1 << 18) and self.method != "atomic":
+            # zero the planes on a side stream while the bucketing passes (which never touch the mesh) run
+            main = torch.cuda.current_stream(self.device)
+            if self._zero_stream is None:
+                self._zero_stream = torch.cuda.Stream(self.device)
+                self._zero_ev = (torch.cuda.Event(), torch.cuda.Event())
+            self._zero_ev[0].record(main)
+            self._zero_stream.wait_event(self._zero_ev[0])
+            with torch.cuda.stream(self._zero_stream):
+                self.mesh.zero_()
+                self._zero_ev[1].record(self._zero_stream)
+            self._paint_call(x, y, z, w, xmin, ymin, zmin, phase=_lib.PAINT_PHASE_BUCKET, method="sorted")
+            main.wait_event(self._zero_ev[1])
+            self._paint_call(x, y, z, w, xmin, ymin, zmin, phase=_lib.PAINT_PHASE_DEPOSIT, tx_begin=0,
+                             tx_end=int(lib.jps_paint_tile_rows(self.nxa)), method="sorted")
+            return
         if zero:
             self.mesh.zero_()
         self._paint_call(x, y, z, w, xmin, ymin, zmin)
