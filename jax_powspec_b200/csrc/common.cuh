@@ -209,6 +209,11 @@ int ensure_bin_table(jps_plan* plan, const float* kedges_grid, int nb, int mode,
                      BinTable** out);
 int64_t edge_threshold(float e, bool strict, int64_t k2max);
 int forward_fft(jps_plan* plan, const float* mesh, cudaStream_t s);
+// powspec.cu: the real-to-complex untangle step fused with a transpose (see r2c_untangle_transpose_kernel):
+// Z[b][y][n/2] (C2C of the real lines read as complex pairs) -> out[b][kz][y], b = 0 .. batch-1
+int launch_r2c_untangle_transpose(const float2* Z, float2* out, const float2* tw, int n, int batch, cudaStream_t s);
+void host_r2c_twiddles(int n, std::vector<float2>& tw);      // e^{-2 pi i k / n}, k = 0 .. n/4, evaluated in double
+
 // slab.cu: fold +-kx / window / Legendre weights / k-bin sums of a spectrum stored x-fastest, into
 // tables->acc (zeroed first).  kz_major = 0: dk[yl][kz][x] (y-shard [y0, y0 + nyl) of a slab rank);
 // kz_major = 1: dk[kz][yl][x] (the pencil plan's layout, nyl = n, y0 = 0: the +-ky partner row is local and is

@@ -358,11 +358,8 @@ extern "C" int jps_plan_create(int n_mesh, int n_shell_fields, int flags, void* 
     return JPS_ERR_CUFFT;
   }
   if (pencil) {                                    // e^{-2 pi i k / n}, k = 0 .. n/4, evaluated in double
-    std::vector<float2> tw((size_t)n_mesh / 4 + 1);
-    for (int k = 0; k <= n_mesh / 4; ++k) {
-      const double ang = -2.0 * M_PI * (double)k / (double)n_mesh;
-      tw[(size_t)k] = make_float2((float)cos(ang), (float)sin(ang));
-    }
+    std::vector<float2> tw;
+    host_r2c_twiddles(n_mesh, tw);
     ce = cudaMemcpy(p->ztw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) {
       set_error("jps_plan_create: twiddle table upload failed: %s", cudaGetErrorString(ce));

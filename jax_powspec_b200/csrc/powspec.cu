@@ -462,6 +462,24 @@ __global__ void __launch_bounds__(256) r2c_untangle_transpose_kernel(const float
   }
 }
 
+int launch_r2c_untangle_transpose(const float2* Z, float2* out, const float2* tw, int n, int batch, cudaStream_t s) {
+  const int M = n / 2;
+  JPS_REQUIRE(n % 2 == 0 && batch >= 1 && batch <= 65535, "r2c untangle: bad sizes");
+  ScopedLaunch L(K_TRANSPOSE, s);
+  r2c_untangle_transpose_kernel<<<dim3((unsigned)((M / 2 + 1 + 31) / 32), (unsigned)((n + 63) / 64), (unsigned)batch), 256, 0, s>>>(
+      Z, out, tw, n);
+  JPS_CHECK_LAUNCH();
+  return JPS_OK;
+}
+
+void host_r2c_twiddles(int n, std::vector<float2>& tw) {
+  tw.resize((size_t)n / 4 + 1);
+  for (int k = 0; k <= n / 4; ++k) {
+    const double ang = -2.0 * M_PI * (double)k / (double)n;
+    tw[(size_t)k] = make_float2((float)cos(ang), (float)sin(ang));
+  }
+}
+
 // mesh[x][y][z] -> dk[kz][ky][kx]: C2C of length n/2 along z on the real lines read as complex pairs, untangle +
 // transpose (y fastest), 1-D C2C along y, transpose (x fastest), 1-D C2C along x.  Every cuFFT pass is a contiguous
 // batched C2C (one read + one write of the array at ~6.5 TB/s, measured), where the monolithic 3-D plan and the
@@ -476,13 +494,8 @@ static int forward_fft_pencil(jps_plan* plan, const float* mesh, cudaStream_t s)
     ScopedLaunch L(K_FFT_R2C, s);                                                   // Z[x][y][n/2]
     JPS_CHECK_CUFFT(cufftExecC2C(plan->fz, (cufftComplex*)const_cast<float*>(mesh), (cufftComplex*)plan->dk, CUFFT_FORWARD));
   }
-  {
-    const int M = plan->n / 2;
-    ScopedLaunch L(K_TRANSPOSE, s);
-    r2c_untangle_transpose_kernel<<<dim3((unsigned)((M / 2 + 1 + 31) / 32), (unsigned)((n + 63) / 64), (unsigned)n), 256, 0, s>>>(
-        plan->dk, plan->dk2, plan->ztw, plan->n);                                   // [x][kz][y]
-  }
-  JPS_CHECK_LAUNCH();
+  int rc0 = launch_r2c_untangle_transpose(plan->dk, plan->dk2, plan->ztw, plan->n, plan->n, s);         // [x][kz][y]
+  if (rc0) return rc0;
   {
     ScopedLaunch L(K_FFT_C2C_Y, s);
     JPS_CHECK_CUFFT(cufftExecC2C(plan->fy, (cufftComplex*)plan->dk2, (cufftComplex*)plan->dk2, CUFFT_FORWARD));

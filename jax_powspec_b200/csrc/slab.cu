@@ -52,6 +52,15 @@ struct jps_slab_plan {
   bool xc_ok = false;
   void* work = nullptr;
   size_t work_bytes = 0;
+  // "Pencil" form of the 2-D transform of the owned planes (x-fast layout, even n): C2C of length n/2 along z on the
+  // real lines read as complex pairs -> untangle + transpose (y fastest) -> contiguous C2C along y.  Three streaming
+  // passes at 5-6.5 TB/s instead of cuFFT's 2-D R2C plan (24.3 ms for 1024 planes of 2048^2 on 2 GPUs = 2.3x the 2-pass
+  // model).  The transformed planes are then [xl][kz][y] and the peer-store kernel transposes (xl <-> y) on the way.
+  bool pencil_ok = false;
+  cufftHandle pz = 0, py = 0, pz_chunk = 0, py_chunk = 0;
+  bool pz_ok = false, py_ok = false, pzc_ok = false, pyc_ok = false;
+  float2* zbuf = nullptr;         // [nxl][n][n/2] complex: output of the z-pass
+  float2* ztw = nullptr;          // untangle twiddles
   jps_plan* tables = nullptr;     // bin tables + accumulators (no 3-D FFT inside)
 };
 
@@ -89,6 +98,20 @@ static int make_fft_x_contig(int n, int nyl, cufftHandle* h, size_t* work) {
   long long embed[1] = {n};
   JPS_CHECK_CUFFT(cufftMakePlanMany64(*h, 1, dims, embed, 1, n, embed, 1, n, CUFFT_C2C, (long long)nyl * nz, work));
   return JPS_OK;
+}
+
+static int make_c2c_contig(int len, long long batch, cufftHandle* h, size_t* work) {
+  JPS_CHECK_CUFFT(cufftCreate(h));
+  JPS_CHECK_CUFFT(cufftSetAutoAllocation(*h, 0));
+  long long dims[1] = {len};
+  long long embed[1] = {len};
+  JPS_CHECK_CUFFT(cufftMakePlanMany64(*h, 1, dims, embed, 1, len, embed, 1, len, CUFFT_C2C, batch, work));
+  return JPS_OK;
+}
+
+static bool slab_pencil_wanted(int n, int nranks) {
+  static const bool off = [] { const char* e = getenv("JPS_SLAB_FFT"); return e && !strcmp(e, "cufft2d"); }();
+  return !off && nranks > 1 && n % 2 == 0;
 }
 
 struct SlabPkParams {
@@ -213,7 +236,7 @@ __global__ void __launch_bounds__(256) pk_bin_ysharded_kernel(SlabPkParams P) {
 // a = |kx| (|k| is monotone in a, so the warp-segmented reduction applies unchanged); the partner
 // row element n - a is the same row read backwards.  The window product keeps the reference's
 // order (c(kx) c(ky)) c(kz).
-template <int MODE>
+template <int MODE, bool FOLD_Y>
 __global__ void __launch_bounds__(256) pk_bin_xfast_kernel(SlabPkParams P) {
   extern __shared__ float sacc[];
   constexpr bool SMEM = (MODE != ACC_GLOBAL);
@@ -245,7 +268,7 @@ __global__ void __launch_bounds__(256) pk_bin_xfast_kernel(SlabPkParams P) {
   }
   // kz_major (the pencil plan's [kz][y][x]): the whole ky axis is local, so the rows y = b and y = n - b are folded
   // together (4 modes per lane and step share |k|, mu, window, weights and bin); a slab shard folds +-kx only.
-  const bool fold_y = P.kz_major != 0;
+  constexpr bool fold_y = FOLD_Y;               // compile time: a slab shard must not carry the second row's registers
   const long long items = fold_y ? (long long)nz * (mid + 1) : (long long)P.nyl * nz;
   for (long long it = (long long)blockIdx.x * nwarps + warp; it < items; it += (long long)gridDim.x * nwarps) {
     int yl, kz;
@@ -269,8 +292,10 @@ __global__ void __launch_bounds__(256) pk_bin_xfast_kernel(SlabPkParams P) {
         const bool two = in && a > 0 && 2 * a != n;
         d0[u] = in ? __ldg(r + a) : make_float2(0.0f, 0.0f);
         d1[u] = two ? __ldg(r + (n - a)) : make_float2(0.0f, 0.0f);
-        d2[u] = (in && two_y) ? __ldg(r2 + a) : make_float2(0.0f, 0.0f);
-        d3[u] = (two && two_y) ? __ldg(r2 + (n - a)) : make_float2(0.0f, 0.0f);
+        if (FOLD_Y) {
+          d2[u] = (in && two_y) ? __ldg(r2 + a) : make_float2(0.0f, 0.0f);
+          d3[u] = (two && two_y) ? __ldg(r2 + (n - a)) : make_float2(0.0f, 0.0f);
+        }
       }
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
@@ -287,10 +312,12 @@ __global__ void __launch_bounds__(256) pk_bin_xfast_kernel(SlabPkParams P) {
           float sum = re * re + im * im;
           re = d1[u].x * c; im = d1[u].y * c;
           sum += re * re + im * im;
-          re = d2[u].x * c; im = d2[u].y * c;
-          sum += re * re + im * im;
-          re = d3[u].x * c; im = d3[u].y * c;
-          sum += re * re + im * im;
+          if (FOLD_Y) {
+            re = d2[u].x * c; im = d2[u].y * c;
+            sum += re * re + im * im;
+            re = d3[u].x * c; im = d3[u].y * c;
+            sum += re * re + im * im;
+          }
           sum *= scale2;
           float mu2 = 0.0f;
           if (k2 > 0) mu2 = kz2 / (float)k2;
@@ -422,6 +449,43 @@ __global__ void __launch_bounds__(256) slab_pack_p2p_xfast_tma_kernel(const floa
   if (warp == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all writes performed before the grid retires
 }
 
+// Transposing peer-store for planes transformed in pencil form, yz[xl][kz][y] (y fastest): 32 (xl) x 32 (y) tiles at
+// fixed kz go through shared memory, loads coalesced along y, (remote) stores coalesced along x:
+//   dst_q[((yl * nz) + kz) * n + rank * nxl + xl] = yz[(xl * nz + kz) * n + q * nyl + yl]
+__global__ void __launch_bounds__(256) slab_pack_p2p_xfast_ykz_kernel(const float2* __restrict__ yz,
+                                                                      void* const* __restrict__ peers, int n, int nz,
+                                                                      int nxl, int nyl, int nranks, int rank,
+                                                                      int x_begin, int x_count) {
+  __shared__ float2 tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 8 rows of 32 lanes
+  const int ntx = (x_count + 31) / 32, nty = (n + 31) / 32;
+  const long long ntiles = (long long)nz * ntx * nty;
+  // consecutive CTAs take y tiles a whole peer apart, so that all links are busy at once
+  const int per_peer = (nty % nranks == 0) ? nty / nranks : 0;
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    int by = (int)(t % nty);
+    const long long rest = t / nty;
+    const int bx = (int)(rest % ntx), kz = (int)(rest / ntx);
+    if (per_peer) by = (by % nranks) * per_peer + by / nranks;
+    const int xl0 = x_begin + bx * 32, y0 = by * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int xl = xl0 + ty + 8 * i, y = y0 + tx;
+      if (xl < x_begin + x_count && y < n) tile[ty + 8 * i][tx] = __ldg(yz + ((size_t)xl * nz + kz) * n + y);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int y = y0 + ty + 8 * i, xl = xl0 + tx;
+      if (y < n && xl < x_begin + x_count) {
+        const int q = y / nyl, yl = y - q * nyl;
+        reinterpret_cast<float2*>(peers[q])[((size_t)yl * nz + kz) * n + (size_t)rank * nxl + xl] = tile[tx][ty + 8 * i];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // Fused pack + all-to-all over NVLink peer memory: block q of this rank's yz-transformed planes is
 // written DIRECTLY into rank q's receive buffer (peer pointers obtained through CUDA IPC on the host
 // side), at the slot of this rank -- no packed send buffer, no NCCL copy kernels.  One launch moves
@@ -513,9 +577,12 @@ static int bin_layout(jps_plan* tp, const float2* dk, int nyl, int y0, int xfast
     const int sseg = (int)((size_t)(2 * kMaxSegments + 8192) * sizeof(int));       // segment tables (x-fast kernels)
     JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw));
     JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_ysharded_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw + sseg));
-    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb + sseg));
-    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, sseg));
+    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_WARP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw + sseg));
+    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_BLOCK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb + sseg));
+    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_GLOBAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sseg));
+    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_WARP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw + sseg));
+    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_BLOCK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb + sseg));
+    JPS_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_xfast_kernel<ACC_GLOBAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sseg));
     attr_set.set();
   }
   using KernelFn = void (*)(SlabPkParams);
@@ -523,13 +590,13 @@ static int bin_layout(jps_plan* tp, const float2* dk, int nyl, int y0, int xfast
   size_t smem = 0;
   long long cap_per_sm = 0;
   if (warp_private) {
-    fn = xfast ? pk_bin_xfast_kernel<ACC_WARP> : pk_bin_ysharded_kernel<ACC_WARP>;
+    fn = xfast ? (kz_major ? pk_bin_xfast_kernel<ACC_WARP, true> : pk_bin_xfast_kernel<ACC_WARP, false>) : pk_bin_ysharded_kernel<ACC_WARP>;
     smem = (size_t)warps * T.nbc * 3 * sizeof(float) + seg_bytes;
   } else if (T.nbc <= kMaxBlockBins) {
-    fn = xfast ? pk_bin_xfast_kernel<ACC_BLOCK> : pk_bin_ysharded_kernel<ACC_BLOCK>;
+    fn = xfast ? (kz_major ? pk_bin_xfast_kernel<ACC_BLOCK, true> : pk_bin_xfast_kernel<ACC_BLOCK, false>) : pk_bin_ysharded_kernel<ACC_BLOCK>;
     smem = (size_t)T.nbc * 3 * sizeof(float) + seg_bytes;
   } else {
-    fn = xfast ? pk_bin_xfast_kernel<ACC_GLOBAL> : pk_bin_ysharded_kernel<ACC_GLOBAL>;
+    fn = xfast ? (kz_major ? pk_bin_xfast_kernel<ACC_GLOBAL, true> : pk_bin_xfast_kernel<ACC_GLOBAL, false>) : pk_bin_ysharded_kernel<ACC_GLOBAL>;
     smem = seg_bytes;
     cap_per_sm = 8;
   }
@@ -584,7 +651,20 @@ extern "C" int jps_slab_plan_workspace_bytes(int n_mesh, int nranks, size_t* byt
   if (rc) return rc;
   const size_t tb = tables_bytes(n_mesh);
   JPS_REQUIRE(tb > 0, "jps_slab_plan_workspace_bytes: table sizing failed");
-  *bytes = align_up(std::max(std::max(w1, w2), std::max(w3, w4)), 256) + align_up(tb, 256) + 1024 + 512;
+  size_t wp = 0, pencil_bytes = 0;
+  if (slab_pencil_wanted(n_mesh, nranks)) {
+    const int nxl = n_mesh / nranks, nzz = n_mesh / 2 + 1;
+    size_t a = 0, b = 0;
+    rc = make_c2c_contig(n_mesh / 2, (long long)nxl * n_mesh, &h, &a);
+    cufftDestroy(h);
+    if (rc) return rc;
+    rc = make_c2c_contig(n_mesh, (long long)nxl * nzz, &h, &b);
+    cufftDestroy(h);
+    if (rc) return rc;
+    wp = std::max(a, b);
+    pencil_bytes = align_up((size_t)nxl * n_mesh * (n_mesh / 2) * sizeof(float2), 256) + align_up((size_t)(n_mesh / 4 + 2) * sizeof(float2), 256);
+  }
+  *bytes = align_up(std::max(std::max(std::max(w1, w2), std::max(w3, w4)), wp), 256) + align_up(tb, 256) + 1024 + 512 + pencil_bytes;
   return JPS_OK;
 }
 
@@ -594,6 +674,10 @@ extern "C" int jps_slab_plan_destroy(jps_slab_plan_t* p) {
   if (p->x_ok) cufftDestroy(p->fft_x);
   if (p->yzc_ok) cufftDestroy(p->fft_yz_chunk);
   if (p->xc_ok) cufftDestroy(p->fft_x_contig);
+  if (p->pz_ok) cufftDestroy(p->pz);
+  if (p->py_ok) cufftDestroy(p->py);
+  if (p->pzc_ok) cufftDestroy(p->pz_chunk);
+  if (p->pyc_ok) cufftDestroy(p->py_chunk);
   if (p->tables) jps_plan_destroy(p->tables);
   delete p;
   return JPS_OK;
@@ -628,10 +712,30 @@ extern "C" int jps_slab_plan_create(int n_mesh, int nranks, int rank, void* work
   rc = make_fft_x_contig(n_mesh, p->nyl, &p->fft_x_contig, &w4);
   if (rc) { jps_slab_plan_destroy(p); return rc; }
   p->xc_ok = true;
-  const size_t wb = align_up(std::max(std::max(w1, w2), std::max(w3, w4)), 256) + 1024;       // + the peer pointer table
+  size_t wp = 0, pencil_bytes = 0;
+  const bool want_pencil = slab_pencil_wanted(n_mesh, nranks);
+  if (want_pencil) {
+    size_t a = 0;
+    rc = make_c2c_contig(n_mesh / 2, (long long)p->nxl * n_mesh, &p->pz, &a);
+    if (rc) { jps_slab_plan_destroy(p); return rc; }
+    p->pz_ok = true; wp = std::max(wp, a);
+    rc = make_c2c_contig(n_mesh, (long long)p->nxl * p->nz, &p->py, &a);
+    if (rc) { jps_slab_plan_destroy(p); return rc; }
+    p->py_ok = true; wp = std::max(wp, a);
+    if (p->chunk_planes) {
+      rc = make_c2c_contig(n_mesh / 2, (long long)p->chunk_planes * n_mesh, &p->pz_chunk, &a);
+      if (rc) { jps_slab_plan_destroy(p); return rc; }
+      p->pzc_ok = true; wp = std::max(wp, a);
+      rc = make_c2c_contig(n_mesh, (long long)p->chunk_planes * p->nz, &p->py_chunk, &a);
+      if (rc) { jps_slab_plan_destroy(p); return rc; }
+      p->pyc_ok = true; wp = std::max(wp, a);
+    }
+    pencil_bytes = align_up((size_t)p->nxl * n_mesh * (n_mesh / 2) * sizeof(float2), 256) + align_up((size_t)(n_mesh / 4 + 2) * sizeof(float2), 256);
+  }
+  const size_t wb = align_up(std::max(std::max(std::max(w1, w2), std::max(w3, w4)), wp), 256) + 1024;       // + the peer pointer table
   const size_t tb = tables_bytes(n_mesh);
-  if (workspace_bytes < wb + align_up(tb, 256)) {
-    set_error("jps_slab_plan_create: workspace has %zu bytes, %zu needed", workspace_bytes, wb + align_up(tb, 256));
+  if (workspace_bytes < wb + align_up(tb, 256) + pencil_bytes) {
+    set_error("jps_slab_plan_create: workspace has %zu bytes, %zu needed", workspace_bytes, wb + align_up(tb, 256) + pencil_bytes);
     jps_slab_plan_destroy(p);
     return JPS_ERR_WORKSPACE;
   }
@@ -644,19 +748,31 @@ extern "C" int jps_slab_plan_create(int n_mesh, int nranks, int rank, void* work
     jps_slab_plan_destroy(p);
     return JPS_ERR_CUFFT;
   }
-  rc = jps_plan_create(n_mesh, 0, JPS_PLAN_TABLES_ONLY, (char*)workspace + wb, workspace_bytes - wb, &p->tables);
+  rc = jps_plan_create(n_mesh, 0, JPS_PLAN_TABLES_ONLY, (char*)workspace + wb, align_up(tb, 256), &p->tables);
   if (rc) { jps_slab_plan_destroy(p); return rc; }
+  if (want_pencil) {
+    char* base = (char*)workspace + wb + align_up(tb, 256);
+    p->zbuf = (float2*)base;
+    p->ztw = (float2*)(base + align_up((size_t)p->nxl * n_mesh * (n_mesh / 2) * sizeof(float2), 256));
+    std::vector<float2> tw;
+    host_r2c_twiddles(n_mesh, tw);
+    if (cudaMemcpy(p->ztw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cufftSetWorkArea(p->pz, p->work) != CUFFT_SUCCESS || cufftSetWorkArea(p->py, p->work) != CUFFT_SUCCESS ||
+        (p->pzc_ok && cufftSetWorkArea(p->pz_chunk, p->work) != CUFFT_SUCCESS) ||
+        (p->pyc_ok && cufftSetWorkArea(p->py_chunk, p->work) != CUFFT_SUCCESS)) {
+      set_error("jps_slab_plan_create: pencil transform setup failed");
+      jps_slab_plan_destroy(p);
+      return JPS_ERR_CUFFT;
+    }
+    p->pencil_ok = true;
+  }
   *out = p;
   return JPS_OK;
 }
 
 extern "C" int jps_slab_fft_yz(jps_slab_plan_t* p, const float* slab, void* out, void* stream) {
   JPS_REQUIRE(p && slab && out, "jps_slab_fft_yz: NULL argument");
-  cudaStream_t s = (cudaStream_t)stream;
-  JPS_CHECK_CUFFT(cufftSetStream(p->fft_yz, s));
-  ScopedLaunch L(K_FFT_R2C, s);
-  JPS_CHECK_CUFFT(cufftExecR2C(p->fft_yz, (cufftReal*)slab, (cufftComplex*)out));
-  return JPS_OK;
+  return jps_slab_fft_yz_planes(p, slab, out, 0, p->nxl, stream);
 }
 
 extern "C" int jps_slab_pack(jps_slab_plan_t* p, const void* in, void* out, void* stream) {
@@ -735,7 +851,11 @@ extern "C" int jps_slab_pack_p2p_planes(jps_slab_plan_t* p, const void* yz, void
     // the other seven wait at the barrier).  The link is already saturated by the plain kernel, so it stays the default.
     static const bool no_tma = [] { const char* e = getenv("JPS_PACK_KERNEL"); return !(e && !strcmp(e, "tma")); }();
     static const int tma_ctas = [] { const char* e = getenv("JPS_PACK_TMA_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
-    if (p->xfast && !no_tma && x_count % 32 == 0 && x_begin % 2 == 0 && p->nxl % 2 == 0 && p->n % 2 == 0) {
+    if (p->xfast && p->pencil_ok) {
+      const long long ntiles = (long long)p->nz * ((x_count + 31) / 32) * ((p->n + 31) / 32);
+      slab_pack_p2p_xfast_ykz_kernel<<<(int)std::min<long long>(ntiles, cap * 4), 256, 0, s>>>(
+          (const float2*)yz, p->peer_dev, p->n, p->nz, p->nxl, p->nyl, p->nranks, p->rank, x_begin, x_count);
+    } else if (p->xfast && !no_tma && x_count % 32 == 0 && x_begin % 2 == 0 && p->nxl % 2 == 0 && p->n % 2 == 0) {
       const int tx = (x_count % 64 == 0) ? 64 : 32;
       const long long ntiles = (long long)p->n * (x_count / tx) * ((p->nz + 31) / 32);
       const int blocks = (int)std::min<long long>(ntiles, (long long)kNumSMs * (tma_ctas > 0 ? tma_ctas : 2));
@@ -780,13 +900,35 @@ extern "C" int jps_slab_fft_yz_planes(jps_slab_plan_t* p, const float* slab, voi
   JPS_REQUIRE(p && slab && out, "jps_slab_fft_yz_planes: NULL argument");
   JPS_REQUIRE(x_begin >= 0 && x_begin + x_count <= p->nxl, "jps_slab_fft_yz_planes: plane range outside the slab");
   cudaStream_t s = (cudaStream_t)stream;
-  cufftHandle h;
-  if (x_count == p->nxl) h = p->fft_yz;
-  else if (p->yzc_ok && x_count == p->chunk_planes) h = p->fft_yz_chunk;
-  else { set_error("jps_slab_fft_yz_planes: x_count=%d is neither the slab (%d) nor the chunk size (%d)", x_count, p->nxl, p->chunk_planes); return JPS_ERR_INVALID; }
+  const bool whole = (x_count == p->nxl), chunk = (p->chunk_planes && x_count == p->chunk_planes);
+  if (!whole && !chunk) {
+    set_error("jps_slab_fft_yz_planes: x_count=%d is neither the slab (%d) nor the chunk size (%d)", x_count, p->nxl, p->chunk_planes);
+    return JPS_ERR_INVALID;
+  }
+  const size_t n = (size_t)p->n;
+  if (p->pencil_ok && p->xfast) {
+    // out[xl][kz][y]: C2C of length n/2 along z (real lines read as complex pairs), untangle + transpose, C2C along y
+    const cufftHandle hz = whole ? p->pz : p->pz_chunk, hy = whole ? p->py : p->py_chunk;
+    const size_t M = n / 2;
+    float2* zb = p->zbuf + (size_t)x_begin * n * M;
+    float2* ob = (float2*)out + (size_t)x_begin * n * p->nz;
+    JPS_REQUIRE((((uintptr_t)slab) & 7) == 0, "jps_slab_fft_yz_planes: the planes must be 8-byte aligned");
+    JPS_CHECK_CUFFT(cufftSetStream(hz, s));
+    JPS_CHECK_CUFFT(cufftSetStream(hy, s));
+    {
+      ScopedLaunch L(K_FFT_R2C, s);
+      JPS_CHECK_CUFFT(cufftExecC2C(hz, (cufftComplex*)const_cast<float*>(slab + (size_t)x_begin * n * n), (cufftComplex*)zb, CUFFT_FORWARD));
+    }
+    int rc = launch_r2c_untangle_transpose(zb, ob, p->ztw, p->n, x_count, s);
+    if (rc) return rc;
+    ScopedLaunch L(K_FFT_C2C_Y, s);
+    JPS_CHECK_CUFFT(cufftExecC2C(hy, (cufftComplex*)ob, (cufftComplex*)ob, CUFFT_FORWARD));
+    return JPS_OK;
+  }
+  const cufftHandle h = whole ? p->fft_yz : p->fft_yz_chunk;
+  JPS_REQUIRE(whole || p->yzc_ok, "jps_slab_fft_yz_planes: no chunk plan");
   JPS_CHECK_CUFFT(cufftSetStream(h, s));
   ScopedLaunch L(K_FFT_R2C, s);
-  const size_t n = (size_t)p->n;
   JPS_CHECK_CUFFT(cufftExecR2C(h, (cufftReal*)(slab + (size_t)x_begin * n * n),
                                (cufftComplex*)((float2*)out + (size_t)x_begin * n * p->nz)));
   return JPS_OK;

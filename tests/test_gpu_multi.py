@@ -28,7 +28,7 @@ def test_slab_pipeline_over_real_ranks(world):
         pytest.skip(f"needs {world} GPUs, box has {torch.cuda.device_count()}")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tests", "helpers", "multi_rank_check.py"), "256", "2e6"]
+           os.path.join(ROOT, "tests", "helpers", "multi_rank_check.py"), "256", "4e6"]
     env = dict(os.environ)
     if world == 2:
         env["JPS_SLAB_CHUNKS"] = "4"      # 128 owned planes -> 4 pieces of 32: the TMA bulk-store peer kernel takes them
