@@ -841,10 +841,14 @@ extern "C" int jps_slab_pack_p2p_planes(jps_slab_plan_t* p, const void* yz, void
   {
     ScopedLaunch L(K_MISC, s);
     const long long nrun = (long long)x_count * p->nranks;
-    // a partial range runs next to the 2-D FFT of the following chunk: it is NVLink bound, a
-    // quarter of the SMs' worth of CTAs keeps the links busy without starving cuFFT
+    // A partial range runs NEXT TO the transform of the following piece (on a high-priority stream): it is NVLink
+    // bound, so it must leave most of every SM to cuFFT.  Round 1 launched up to 8 CTAs of 256 threads per SM for the
+    // transposing kernels -- every thread slot of the GPU -- and the "overlap" hid nothing (measured on 8 GPUs: fused
+    // stage 9.45 ms = transform 4.11 + transfer 5.46).  Now 3 CTAs per SM for a partial range (JPS_PACK_CTAS_PER_SM),
+    // 8 when the whole slab is sent in one launch (nothing to share the SMs with).
     static const int per_sm_env = [] { const char* e = getenv("JPS_PACK_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
-    const long long cap = (x_count == p->nxl) ? (long long)kNumSMs * 8 : (long long)kNumSMs * (per_sm_env > 0 ? per_sm_env : 2);
+    const long long per_sm = (x_count == p->nxl) ? 8 : (per_sm_env > 0 ? per_sm_env : 3);
+    const long long cap = (long long)kNumSMs * per_sm;
     // JPS_PACK_KERNEL=tma selects the TMA bulk-store variant.  Measured on 2 B200s (2048^3, 8.6 GB leaving each
     // rank, kernel alone): straight contiguous peer copy 12.4 ms = 692 GB/s; the plain load/store transposing kernel
     // 12.6 ms = 0.99 of it; the TMA variant 14.0 ms = 0.89 (one warp serialises 32 UBLKCP issues per 16 KB tile while
@@ -853,7 +857,7 @@ extern "C" int jps_slab_pack_p2p_planes(jps_slab_plan_t* p, const void* yz, void
     static const int tma_ctas = [] { const char* e = getenv("JPS_PACK_TMA_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
     if (p->xfast && p->pencil_ok) {
       const long long ntiles = (long long)p->nz * ((x_count + 31) / 32) * ((p->n + 31) / 32);
-      slab_pack_p2p_xfast_ykz_kernel<<<(int)std::min<long long>(ntiles, cap * 4), 256, 0, s>>>(
+      slab_pack_p2p_xfast_ykz_kernel<<<(int)std::min<long long>(ntiles, cap), 256, 0, s>>>(
           (const float2*)yz, p->peer_dev, p->n, p->nz, p->nxl, p->nyl, p->nranks, p->rank, x_begin, x_count);
     } else if (p->xfast && !no_tma && x_count % 32 == 0 && x_begin % 2 == 0 && p->nxl % 2 == 0 && p->n % 2 == 0) {
       const int tx = (x_count % 64 == 0) ? 64 : 32;
@@ -867,7 +871,7 @@ extern "C" int jps_slab_pack_p2p_planes(jps_slab_plan_t* p, const void* yz, void
                                                                  p->nranks, p->rank, x_begin, x_count);
     } else if (p->xfast) {
       const long long ntiles = (long long)p->n * ((x_count + 31) / 32) * ((p->nz + 31) / 32);
-      slab_pack_p2p_xfast_kernel<<<(int)std::min<long long>(ntiles, cap * 4), 256, 0, s>>>(
+      slab_pack_p2p_xfast_kernel<<<(int)std::min<long long>(ntiles, cap), 256, 0, s>>>(
           (const float2*)yz, p->peer_dev, p->n, p->nz, p->nxl, p->nyl, p->nranks, p->rank, x_begin, x_count);
     } else {
       slab_pack_p2p_kernel<<<(int)std::min<long long>(nrun, cap), 256, 0, s>>>(
