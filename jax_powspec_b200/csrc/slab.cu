@@ -844,10 +844,11 @@ extern "C" int jps_slab_pack_p2p_planes(jps_slab_plan_t* p, const void* yz, void
     // A partial range runs NEXT TO the transform of the following piece (on a high-priority stream): it is NVLink
     // bound, so it must leave most of every SM to cuFFT.  Round 1 launched up to 8 CTAs of 256 threads per SM for the
     // transposing kernels -- every thread slot of the GPU -- and the "overlap" hid nothing (measured on 8 GPUs: fused
-    // stage 9.45 ms = transform 4.11 + transfer 5.46).  Now 3 CTAs per SM for a partial range (JPS_PACK_CTAS_PER_SM),
-    // 8 when the whole slab is sent in one launch (nothing to share the SMs with).
+    // stage 9.45 ms = transform 4.11 + transfer 5.46).  Now 4 CTAs per SM for a partial range (JPS_PACK_CTAS_PER_SM;
+    // fused stage on 2 GPUs, 2048^3: 1 / 2 / 3 / 4 / 6 per SM -> 37.2 / 28.8 / 26.9 / 25.8 / 26.0 ms), 8 when the whole
+    // slab is sent in one launch (nothing to share the SMs with).
     static const int per_sm_env = [] { const char* e = getenv("JPS_PACK_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
-    const long long per_sm = (x_count == p->nxl) ? 8 : (per_sm_env > 0 ? per_sm_env : 3);
+    const long long per_sm = (x_count == p->nxl) ? 8 : (per_sm_env > 0 ? per_sm_env : 4);
     const long long cap = (long long)kNumSMs * per_sm;
     // JPS_PACK_KERNEL=tma selects the TMA bulk-store variant.  Measured on 2 B200s (2048^3, 8.6 GB leaving each
     // rank, kernel alone): straight contiguous peer copy 12.4 ms = 692 GB/s; the plain load/store transposing kernel
