@@ -14,8 +14,7 @@ for l in sys.stdin:
         d=json.loads(l); t=d['transpose'] or {}
         print('$1', 'step', round(d['ms_per_step'],2), 'stages', {k:round(v,2) for k,v in d['stages_ms'].items()}, 'fft_alone', t.get('fft_yz_alone_ms'), 'store_alone', t.get('store_alone_ms'), 'hidden', t.get('hidden_ms'))"; }
 python bench.py --gpus $N --quick-kernels --steps 5 --pipeline 2>/dev/null | tee gpurun_out/r2_c4_${N}gpu_pipeline.json | summ pipeline
-for v in 2 3 6; do JPS_PACK_CTAS_PER_SM=$v python bench.py --gpus $N --quick-kernels --steps 5 2>/dev/null | tee gpurun_out/r2_c4_${N}gpu_ctas$v.json | summ ctas_per_sm=$v; done
+for v in 2 6; do JPS_PACK_CTAS_PER_SM=$v python bench.py --gpus $N --quick-kernels --steps 5 2>/dev/null | tee gpurun_out/r2_c4_${N}gpu_ctas$v.json | summ ctas_per_sm=$v; done
 JPS_SLAB_FFT=cufft2d python bench.py --gpus $N --quick-kernels --steps 5 2>/dev/null | tee gpurun_out/r2_c4_${N}gpu_cufft2d.json | summ cufft2d
-JPS_SLAB_CHUNKS=4 python bench.py --gpus $N --quick-kernels --steps 5 2>/dev/null | tee gpurun_out/r2_c4_${N}gpu_4chunks.json | summ 4chunks
 $TR --master-port 29533 tools/bench_c5.py > gpurun_out/r2_c5_${N}gpu.json 2>&1; tail -1 gpurun_out/r2_c5_${N}gpu.json
 $TR --master-port 29544 tools/bench_bispec_sharded.py > gpurun_out/r2_bispec_sharded_${N}gpu.json 2>&1; tail -1 gpurun_out/r2_bispec_sharded_${N}gpu.json
