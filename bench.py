@@ -519,7 +519,7 @@ def replica_check(torch, dist, a, wl, world, rank, dev):
     ke = k_edges_for(box, n)
     x, y, z = slab_catalog(torch, rep, rank, world, dev, seed=wl["seed"] + 1000)
     pipe = SlabPipeline(n, box, ke, order=order, compat="fixed", method="sorted", transport=a.transport,
-                        overlap=not a.no_overlap, layout=a.layout, pipeline=a.pipeline)
+                        overlap=not a.no_overlap, layout=a.layout, pipeline=a.pipeline, fft=a.slab_fft)
     pipe._force_chunks = True                       # take the chunked FFT / transfer overlap path like the big mesh
     k3d, pk, nm = (t.clone() for t in pipe(x, y, z))
     out = {"mesh": n, "n_part": REPLICA["n_part"], "particles_per_cell": REPLICA["n_part"] / n ** 3}
@@ -558,7 +558,7 @@ def run_c4_arm(a, wl):
     nz = n // 2 + 1
     x, y, z = slab_catalog(torch, wl, rank, world, dev)
     pipe = SlabPipeline(n, box, k_edges_for(box, n), order=order, compat="fixed", method=a.method, transport=a.transport,
-                        overlap=not a.no_overlap, layout=a.layout, pipeline=a.pipeline)
+                        overlap=not a.no_overlap, layout=a.layout, pipeline=a.pipeline, fft=a.slab_fft)
 
     def sync():
         if world > 1:
@@ -782,6 +782,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-overlap", action="store_true", help="c4: do not overlap the 2-D FFT with the peer transfer")
     ap.add_argument("--layout", default="auto", choices=["auto", "xfast", "xslow"], help="c4: layout of the transposed shard")
+    ap.add_argument("--slab-fft", default="auto", choices=["auto", "pencil", "cufft2d"],
+                    help="c4: form of the 2-D transform of a rank's planes (auto: pencil from 6 GB of planes per rank)")
     ap.add_argument("--pipeline", action="store_true", help="c4: deposit, halo, FFT and transfer as one pipeline over pieces of planes")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the CPUs nearest its GPU")
     ap.add_argument("--quick", action="store_true", help="stop after the device-resident timed region (ncu runs)")

@@ -289,11 +289,21 @@ JPS_API int jps_slab_pack_p2p(jps_slab_plan_t* plan, const void* yz, void* const
  * that the 2-D FFT of one chunk overlaps the NVLink transfer of the previous one (two streams on
  * the host side).  x_count must be the whole slab or jps_slab_chunk_planes() (0 = no chunking). */
 JPS_API int jps_slab_chunk_planes(jps_slab_plan_t* plan);
-/* Layout of the transposed shard (default 0).  0: [n][n/nranks][n/2+1], x slowest -- what jps_slab_pack +
- * an all-to-all produce; the 1-D FFT along x is strided.  1: [n/nranks][n/2+1][n], x fastest -- produced
- * by jps_slab_pack_p2p[_planes], which then transposes 32x32 tiles on the way to the peers; the 1-D
- * FFT is contiguous and jps_slab_powspec_partial runs its lanes along kx.  Set before the first step. */
-JPS_API int jps_slab_set_layout(jps_slab_plan_t* plan, int xfast);
+/* Layout of the transposed shard and form of the 2-D transform of the owned planes (default 0).
+ * layout & JPS_SLAB_LAYOUT_XFAST == 0: shard [n][n/nranks][n/2+1], x slowest -- what jps_slab_pack + an all-to-all
+ * produce; the 1-D FFT along x is strided.  JPS_SLAB_LAYOUT_XFAST: shard [n/nranks][n/2+1][n], x fastest -- produced
+ * by jps_slab_pack_p2p[_planes], which then transposes 32x32 tiles on the way to the peers; the 1-D FFT is contiguous
+ * and jps_slab_powspec_partial runs its lanes along kx.
+ * With the x-fast layout the owned planes are transformed either by cuFFT's batched 2-D R2C plan (the planes leave
+ * jps_slab_fft_yz* as [x_local][n][n/2+1]) or in "pencil form" -- C2C of length n/2 along z on the real lines read as
+ * complex pairs, real-to-complex untangle fused with a transpose, contiguous C2C along y (the planes leave as
+ * [x_local][n/2+1][n], and the peer-store kernel transposes x <-> y).  Default: pencil form when a rank's planes hold
+ * 6 GB or more (measured crossover at 2048^3); JPS_SLAB_FFT_PENCIL / JPS_SLAB_FFT_CUFFT2D force one (even n only for
+ * the pencil form).  Set before the first step. */
+#define JPS_SLAB_LAYOUT_XFAST  1
+#define JPS_SLAB_FFT_PENCIL    2
+#define JPS_SLAB_FFT_CUFFT2D   4
+JPS_API int jps_slab_set_layout(jps_slab_plan_t* plan, int layout);
 JPS_API int jps_slab_fft_yz_planes(jps_slab_plan_t* plan, const float* slab, void* yz, int x_begin, int x_count,
                            void* stream);
 JPS_API int jps_slab_pack_p2p_planes(jps_slab_plan_t* plan, const void* yz, void* const* peer_recv, int x_begin,

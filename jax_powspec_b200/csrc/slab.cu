@@ -56,7 +56,8 @@ struct jps_slab_plan {
   // real lines read as complex pairs -> untangle + transpose (y fastest) -> contiguous C2C along y.  Three streaming
   // passes at 5-6.5 TB/s instead of cuFFT's 2-D R2C plan (24.3 ms for 1024 planes of 2048^2 on 2 GPUs = 2.3x the 2-pass
   // model).  The transformed planes are then [xl][kz][y] and the peer-store kernel transposes (xl <-> y) on the way.
-  bool pencil_ok = false;
+  bool pencil_ok = false;         // the pencil plans exist
+  bool use_pencil = false;        // ... and are used (default rule, JPS_SLAB_FFT, or jps_slab_set_layout)
   cufftHandle pz = 0, py = 0, pz_chunk = 0, py_chunk = 0;
   bool pz_ok = false, py_ok = false, pzc_ok = false, pyc_ok = false;
   float2* zbuf = nullptr;         // [nxl][n][n/2] complex: output of the z-pass
@@ -109,9 +110,21 @@ static int make_c2c_contig(int len, long long batch, cufftHandle* h, size_t* wor
   return JPS_OK;
 }
 
-static bool slab_pencil_wanted(int n, int nranks) {
-  static const bool off = [] { const char* e = getenv("JPS_SLAB_FFT"); return e && !strcmp(e, "cufft2d"); }();
-  return !off && nranks > 1 && n % 2 == 0;
+// Pencil form or cuFFT's batched 2-D R2C plan for the owned planes?  Measured at 2048^3: 1024 planes per rank (2 GPUs)
+// 16.8 ms against 24.3 ms; 256 planes per rank (8 GPUs) 4.22 ms against 4.11 ms, and the peer-store kernel that reads
+// the pencil layout is 4 % slower (its remote 256-byte runs land 16 MB apart instead of 16 KB): step 20.76 against
+// 20.38 ms.  So by default the pencil form is taken when a rank's planes hold 6 GB or more; jps_slab_set_layout (or
+// JPS_SLAB_FFT=pencil|cufft2d) forces one.  The pencil plans exist whenever the mesh size is even.
+static bool slab_pencil_possible(int n, int nranks) { return nranks > 1 && n % 2 == 0; }
+
+static bool slab_pencil_default(int n, int nranks) {
+  static const int forced = [] {
+    const char* e = getenv("JPS_SLAB_FFT");
+    return !e ? 0 : !strcmp(e, "cufft2d") ? 1 : !strcmp(e, "pencil") ? 2 : 0;
+  }();
+  if (!slab_pencil_possible(n, nranks) || forced == 1) return false;
+  if (forced == 2) return true;
+  return (double)(n / nranks) * n * n * 4.0 >= 6.0e9;
 }
 
 struct SlabPkParams {
@@ -652,7 +665,7 @@ extern "C" int jps_slab_plan_workspace_bytes(int n_mesh, int nranks, size_t* byt
   const size_t tb = tables_bytes(n_mesh);
   JPS_REQUIRE(tb > 0, "jps_slab_plan_workspace_bytes: table sizing failed");
   size_t wp = 0, pencil_bytes = 0;
-  if (slab_pencil_wanted(n_mesh, nranks)) {
+  if (slab_pencil_possible(n_mesh, nranks)) {
     const int nxl = n_mesh / nranks, nzz = n_mesh / 2 + 1;
     size_t a = 0, b = 0;
     rc = make_c2c_contig(n_mesh / 2, (long long)nxl * n_mesh, &h, &a);
@@ -713,7 +726,7 @@ extern "C" int jps_slab_plan_create(int n_mesh, int nranks, int rank, void* work
   if (rc) { jps_slab_plan_destroy(p); return rc; }
   p->xc_ok = true;
   size_t wp = 0, pencil_bytes = 0;
-  const bool want_pencil = slab_pencil_wanted(n_mesh, nranks);
+  const bool want_pencil = slab_pencil_possible(n_mesh, nranks);
   if (want_pencil) {
     size_t a = 0;
     rc = make_c2c_contig(n_mesh / 2, (long long)p->nxl * n_mesh, &p->pz, &a);
@@ -765,6 +778,7 @@ extern "C" int jps_slab_plan_create(int n_mesh, int nranks, int rank, void* work
       return JPS_ERR_CUFFT;
     }
     p->pencil_ok = true;
+    p->use_pencil = slab_pencil_default(n_mesh, nranks);
   }
   *out = p;
   return JPS_OK;
@@ -856,7 +870,7 @@ extern "C" int jps_slab_pack_p2p_planes(jps_slab_plan_t* p, const void* yz, void
     // the other seven wait at the barrier).  The link is already saturated by the plain kernel, so it stays the default.
     static const bool no_tma = [] { const char* e = getenv("JPS_PACK_KERNEL"); return !(e && !strcmp(e, "tma")); }();
     static const int tma_ctas = [] { const char* e = getenv("JPS_PACK_TMA_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
-    if (p->xfast && p->pencil_ok) {
+    if (p->xfast && p->use_pencil) {
       const long long ntiles = (long long)p->nz * ((x_count + 31) / 32) * ((p->n + 31) / 32);
       slab_pack_p2p_xfast_ykz_kernel<<<(int)std::min<long long>(ntiles, cap), 256, 0, s>>>(
           (const float2*)yz, p->peer_dev, p->n, p->nz, p->nxl, p->nyl, p->nranks, p->rank, x_begin, x_count);
@@ -890,10 +904,16 @@ extern "C" int jps_slab_pack_p2p(jps_slab_plan_t* p, const void* yz, void* const
 
 extern "C" int jps_slab_chunk_planes(jps_slab_plan_t* p) { return p ? p->chunk_planes : 0; }
 
-extern "C" int jps_slab_set_layout(jps_slab_plan_t* p, int xfast) {
+extern "C" int jps_slab_set_layout(jps_slab_plan_t* p, int layout) {
   JPS_REQUIRE(p != nullptr, "jps_slab_set_layout: NULL plan");
+  const int xfast = layout & JPS_SLAB_LAYOUT_XFAST;
   JPS_REQUIRE(!xfast || p->nranks > 1, "jps_slab_set_layout: the x-fast layout is produced by the peer-store kernel (nranks > 1)");
+  JPS_REQUIRE(!((layout & JPS_SLAB_FFT_PENCIL) && (layout & JPS_SLAB_FFT_CUFFT2D)), "jps_slab_set_layout: contradictory transform flags");
+  JPS_REQUIRE(!(layout & JPS_SLAB_FFT_PENCIL) || (xfast && p->pencil_ok), "jps_slab_set_layout: the pencil form needs the x-fast layout and an even mesh size");
   p->xfast = xfast ? 1 : 0;
+  if (layout & JPS_SLAB_FFT_PENCIL) p->use_pencil = true;
+  else if (layout & JPS_SLAB_FFT_CUFFT2D) p->use_pencil = false;
+  else p->use_pencil = p->pencil_ok && slab_pencil_default(p->n, p->nranks);
   return JPS_OK;
 }
 
@@ -911,7 +931,7 @@ extern "C" int jps_slab_fft_yz_planes(jps_slab_plan_t* p, const float* slab, voi
     return JPS_ERR_INVALID;
   }
   const size_t n = (size_t)p->n;
-  if (p->pencil_ok && p->xfast) {
+  if (p->use_pencil && p->xfast) {
     // out[xl][kz][y]: C2C of length n/2 along z (real lines read as complex pairs), untangle + transpose, C2C along y
     const cufftHandle hz = whole ? p->pz : p->pz_chunk, hy = whole ? p->py : p->py_chunk;
     const size_t M = n / 2;

@@ -123,7 +123,7 @@ class SlabPipeline:
 
     def __init__(self, n_mesh, box_size, k_edges, *, order=2, compat="fixed", method="auto", wrap=True,
                  shot_noise=0.0, rank=None, world=None, device=None, transport="auto", overlap=True,
-                 layout="auto", pipeline=False):
+                 layout="auto", pipeline=False, fft="auto"):
         """transport: how the transpose crosses GPUs -- "p2p": one fused pack + peer-store kernel
         over NVLink peer memory (receive buffers mapped into every rank with CUDA IPC); "nccl":
         pack kernel + ``all_to_all_single``; "auto": p2p when the mapping succeeds, else nccl.
@@ -132,6 +132,9 @@ class SlabPipeline:
         layout: "xfast" = the peer-store kernel transposes on the way so that the shard arrives as
         [y_local][kz][x] and the 1-D FFT along x is contiguous (p2p only); "xslow" = [x][y_local][kz]
         with a strided FFT; "auto" = xfast with p2p, xslow otherwise.
+        fft (x-fast layout only): "pencil" = the owned planes are transformed as C2C of half length along z +
+        fused untangle/transpose + contiguous C2C along y; "cufft2d" = cuFFT's batched 2-D R2C plan; "auto" = pencil
+        when a rank's planes hold 6 GB or more (the measured crossover at 2048^3).
         pipeline: run deposit, halo exchange, 2-D FFT and peer transfer as one pipeline over pieces of planes
         (p2p + overlap only; see _pipelined_paint_fft).  Off by default: measured on 2 B200s (2048^3) the pipelined
         step takes 83.3 ms against 82.7 ms staged -- the deposit (3 CTAs of 58 KB shared memory per SM) and cuFFT
@@ -212,6 +215,9 @@ class SlabPipeline:
         self._side, self._events = None, None
         self._halo_stream, self._halo_ev = None, None
         self._dep_stream = None
+        if fft not in ("auto", "pencil", "cufft2d"):
+            raise ValueError("fft must be 'auto', 'pencil' or 'cufft2d'")
+        self.fft = fft
         self._zero_stream, self._zero_ev = None, None
         self.pipeline = bool(pipeline)
         self._local_peers = False
@@ -226,7 +232,12 @@ class SlabPipeline:
             self._set_layout(self._want_xfast)
 
     def _set_layout(self, xfast):
-        check(lib.jps_slab_set_layout(self.handle, int(bool(xfast))), "jps_slab_set_layout")
+        mode = 1 if xfast else 0
+        if xfast and self.fft == "pencil" and self.n % 2 == 0:
+            mode |= 2
+        elif xfast and self.fft == "cufft2d":
+            mode |= 4
+        check(lib.jps_slab_set_layout(self.handle, mode), "jps_slab_set_layout")
         self.xfast = bool(xfast)
 
     def use_local_peers(self, pipes, xfast=True):

@@ -45,16 +45,16 @@ for order, weighted in ((4, False), (3, True), (2, False)):
         wf = torch.from_numpy(w_all).to(dev) if weighted else None
         ref = jps.PaintPowspec(n, box, ke, order=order, compat="fixed", device=dev)
         k1, pk1, nm1 = (t.clone() for t in ref(*full, wf))
-    for transport, layout, overlap, pipelined in (("p2p", "xfast", True, True), ("p2p", "xfast", True, False),
-                                                  ("p2p", "xfast", False, False), ("p2p", "xslow", True, True),
-                                                  ("nccl", "xslow", True, False)):
+    for transport, layout, overlap, pipelined, fft in (("p2p", "xfast", True, True, "pencil"), ("p2p", "xfast", True, False, "cufft2d"),
+                                                       ("p2p", "xfast", False, False, "pencil"), ("p2p", "xslow", True, True, "auto"),
+                                                       ("nccl", "xslow", True, False, "auto")):
         pipe = SlabPipeline(n, box, ke, order=order, compat="fixed", transport=transport, layout=layout, overlap=overlap,
-                            pipeline=pipelined)
+                            pipeline=pipelined, fft=fft)
         pipe._force_chunks = overlap
         for _ in range(2):                                      # twice: buffers reused across steps
             k3d, pk, nm = pipe(x, y, z, w)
         case = {"order": order, "weighted": weighted, "transport": pipe.transport, "layout": "xfast" if pipe.xfast else "xslow",
-                "overlap": overlap, "pipelined": bool(pipelined and pipe._can_pipeline(x.numel()))}
+                "overlap": overlap, "fft": fft, "pipelined": bool(pipelined and pipe._can_pipeline(x.numel()))}
         if transport == "p2p" and layout == "xfast" and overlap and pipelined and order == 4:
             # the host-buffer pipeline (what bench.py's e2e times) must give the same numbers
             host = SlabHostPipeline(pipe, x.numel(), weighted=weighted, n_chunks=3)

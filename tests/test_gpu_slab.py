@@ -64,7 +64,7 @@ def test_virtual_ranks_match_single_gpu_and_oracle(jps, world, order, method):
         q.close()
 
 
-@pytest.mark.parametrize("layout", ["xslow", "xfast"])
+@pytest.mark.parametrize("layout", ["xslow", "xfast", "xfast-pencil"])
 @pytest.mark.parametrize("world,n", [(2, 64), (4, 64), (2, 96), (8, 64)])
 def test_fused_peer_store_transpose_both_layouts(jps, world, n, layout):
     """The p2p transport on one device (peers = the other virtual ranks' receive buffers): the plain
@@ -78,7 +78,9 @@ def test_fused_peer_store_transpose_both_layouts(jps, world, n, layout):
     cats = _split_by_slab(p, box, n, world)
     ref_pipes = [SlabPipeline(n, box, ke, order=order, compat="fixed", rank=r, world=world) for r in range(world)]
     k0, pk0, nm0 = (t.cpu().numpy() for t in run_virtual_ranks(ref_pipes, cats)[0])
-    pipes = [SlabPipeline(n, box, ke, order=order, compat="fixed", rank=r, world=world) for r in range(world)]
+    fft = "pencil" if layout == "xfast-pencil" else "cufft2d"      # pencil: C2C n/2 + fused untangle/transpose + C2C along y
+    layout = layout.split("-")[0]
+    pipes = [SlabPipeline(n, box, ke, order=order, compat="fixed", rank=r, world=world, fft=fft) for r in range(world)]
     for q in pipes:
         q._force_chunks = (n == 96)                      # also the chunked FFT / transfer overlap path
     outs = run_virtual_ranks(pipes, cats, p2p=layout)

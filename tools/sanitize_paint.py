@@ -44,10 +44,10 @@ for world in (2, 4):
     cats = [tuple(torch.from_numpy(np.ascontiguousarray(p[owner == r][:, i])).cuda() for i in range(3)) + (None,) for r in range(world)]
     ref = [SlabPipeline(n, box, ke, order=3, rank=r, world=world) for r in range(world)]
     k0, pk0, nm0 = run_virtual_ranks(ref, cats)[0]
-    for layout in ("xslow", "xfast"):
-        pipes = [SlabPipeline(n, box, ke, order=3, rank=r, world=world) for r in range(world)]
+    for layout, fft in (("xslow", "auto"), ("xfast", "cufft2d"), ("xfast", "pencil")):
+        pipes = [SlabPipeline(n, box, ke, order=3, rank=r, world=world, fft=fft) for r in range(world)]
         for q in pipes:
             q._force_chunks = True
         k1, pk1, nm1 = run_virtual_ranks(pipes, cats, p2p=layout)[0]
-        assert torch.equal(nm0, nm1) and float(((pk1 - pk0).abs() / pk0[:, :1].abs()).max()) < 2e-6, (world, layout)
+        assert torch.equal(nm0, nm1) and float(((pk1 - pk0).abs() / pk0[:, :1].abs()).max()) < 2e-6, (world, layout, fft)
 print("slab peer-store ok")
