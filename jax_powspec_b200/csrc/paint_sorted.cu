@@ -420,6 +420,11 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(PaintParams p, Tile
 #ifndef JPS_FINE_UNR
 #define JPS_FINE_UNR 4
 #endif
+#ifdef JPS_FINE_LDCS
+#define JPS_FINE_LOAD(ptr) __ldcs(ptr)          // evict-first: the coarse records are read once
+#else
+#define JPS_FINE_LOAD(ptr) (*(ptr))
+#endif
 constexpr int COARSE_CHUNK = JPS_COARSE_CHUNK;     // 64 KB of staged records per CTA
 constexpr int COARSE_THREADS = JPS_COARSE_THREADS;
 constexpr int COARSE_QPT = COARSE_CHUNK / (4 * COARSE_THREADS);   // quads (4 particles) per thread
@@ -542,11 +547,15 @@ __global__ void group_bases_from_offsets_kernel(const unsigned* __restrict__ off
   if (gidx < ngroups) gcursor[gidx] = v;
 }
 
-template <int ORDER, bool REFCIC>
+// TILE_COUNTS: also build the per-tile histogram (one global red per particle into the L2-resident table) -- the
+// big-mesh path, where the pass that precedes this one then only needs the cheap shared-memory GROUP histogram.  The
+// reds ride on a kernel that is bound by its shared-memory staging, not by the L2.
+template <int ORDER, bool REFCIC, bool TILE_COUNTS>
 __global__ void __launch_bounds__(COARSE_THREADS, JPS_COARSE_MINB) coarse_scatter_kernel(PaintParams p, TileGeom g, int gshift,
                                                                         int ngroups,
                                                                         unsigned* __restrict__ gcursor,
-                                                                        float4* __restrict__ tmp) {
+                                                                        float4* __restrict__ tmp,
+                                                                        unsigned* __restrict__ tile_counts) {
   extern __shared__ __align__(16) unsigned char smraw[];
   float4* stage = reinterpret_cast<float4*>(smraw);                                   // [COARSE_CHUNK]
   unsigned short* skey = reinterpret_cast<unsigned short*>(stage + COARSE_CHUNK);     // [COARSE_CHUNK]
@@ -590,9 +599,13 @@ __global__ void __launch_bounds__(COARSE_THREADS, JPS_COARSE_MINB) coarse_scatte
         cq[k].x[u] = grid_pos(cq[k].x[u], p.xmin, p.inv);
         cq[k].y[u] = grid_pos(cq[k].y[u], p.ymin, p.inv);
         cq[k].z[u] = grid_pos(cq[k].z[u], p.zmin, p.inv);
-        const unsigned grp = (unsigned)(tile_of<ORDER, REFCIC>(cq[k].x[u], cq[k].y[u], cq[k].z[u], g, 0u) >> gshift);
+        const int tile = tile_of<ORDER, REFCIC>(cq[k].x[u], cq[k].y[u], cq[k].z[u], g, 0u);
+        const unsigned grp = (unsigned)(tile >> gshift);
         key[k][u] = 0xffffffffu;
-        if (u < cnt) key[k][u] = grp | (atomicAdd(h + grp, 1u) << 12);
+        if (u < cnt) {
+          key[k][u] = grp | (atomicAdd(h + grp, 1u) << 12);
+          if (TILE_COUNTS) atomicAdd(tile_counts + tile, 1u);
+        }
       }
     }
     __syncthreads();
@@ -683,7 +696,7 @@ __global__ void __launch_bounds__(512, JPS_FINE_MINB) fine_scatter_kernel(const 
     for (int u = 0; u < FINE_UNR; ++u) {
       const unsigned i = i0 + u * blockDim.x + threadIdx.x;
       ok[u] = i < end;
-      if (ok[u]) r[u] = tmp[i];
+      if (ok[u]) r[u] = JPS_FINE_LOAD(tmp + i);
     }
     int f[FINE_UNR];
     unsigned same[FINE_UNR], base[FINE_UNR];
@@ -703,6 +716,111 @@ __global__ void __launch_bounds__(512, JPS_FINE_MINB) fine_scatter_kernel(const 
       if (f[u] >= 0) sorted[beg + base[u] + __popc(same[u] & ((1u << lane) - 1u))] = r[u];
     }
   }
+}
+
+// ---- fine pass, staged form (big groups).  The direct form above hands every record to its tile with one lone
+// 16-byte store; with hundreds of tiles per group those stores have no neighbours in their warp and every 32-byte
+// sector is written by two separate requests.  Here one CTA per group works like the coarse pass: a chunk of
+// FS_CHUNK records is ranked by tile with shared integer atomics, laid out in tile order in shared memory and
+// written out as coalesced runs (FS_CHUNK / tiles-per-group records each).  The CTA owns its group, so the tile
+// cursors live in shared memory and no global atomic is needed.  The next chunk's loads are issued before the
+// write-out of the current one.  Needs the per-tile offsets (HAVE_OFFSETS path).
+// Two shapes (measured on a B200, 1e9 particles on 2048^3 = 2048 tiles per group: direct 26.5 ms, 4096-record chunks
+// 20.4 ms, 8192-record chunks 12.0 ms; one rank of the 8-GPU decomposition = 256 tiles per group: direct 1.57 ms,
+// 4096-record chunks 1.03 ms; C2 = 32 tiles per group: direct 0.755 ms, staged 0.778 ms): what matters is the run
+// length chunk / tiles-per-group, so big groups take the big chunk (one 1024-thread CTA per SM) and medium ones the
+// small chunk (two 512-thread CTAs per SM, which overlap each other's barriers).
+constexpr int kFineStagedMinShift = 7;             // auto rule: staged form from 128 tiles per group
+constexpr int kFineStagedBigShift = 10;            //            big chunk from 1024 tiles per group
+constexpr bool kCountInCoarseDefault = false;      // auto rule for JPS_COUNT (until measured)
+
+template <int CHUNK>
+static size_t fine_staged_smem(int gshift) {
+  return (size_t)CHUNK * (sizeof(float4) + 2) + (size_t)(3 * (1 << gshift) + 1) * 4 + 33 * 4;
+}
+
+template <int ORDER, bool REFCIC, int CHUNK, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) fine_staged_kernel(const float4* __restrict__ tmp,
+                                                                    const unsigned* __restrict__ gbase, TileGeom g,
+                                                                    int gshift, int nbuckets,
+                                                                    const unsigned* __restrict__ offsets,
+                                                                    float4* __restrict__ sorted) {
+  static_assert(CHUNK % THREADS == 0 && CHUNK <= 65536, "chunk ranks are kept in 16 bits");
+  constexpr int RPT = CHUNK / THREADS;             // records per thread and chunk
+  extern __shared__ __align__(16) unsigned char fs_raw[];
+  const int G = 1 << gshift;
+  float4* stage = reinterpret_cast<float4*>(fs_raw);                                  // [CHUNK] records in tile order
+  unsigned short* skey = reinterpret_cast<unsigned short*>(stage + CHUNK);            // [CHUNK] their local tile
+  unsigned* h = reinterpret_cast<unsigned*>(skey + CHUNK);                            // [G + 1] chunk histogram -> offsets
+  unsigned* cur = h + G + 1;                                                          // [G] next free slot of every tile
+  unsigned* wb = cur + G;                                                             // [G] cur - h: slot of staged record 0
+  unsigned* scratch = wb + G;                                                         // [33]
+  const int tid = threadIdx.x;
+  const int grp = blockIdx.x;
+  const unsigned beg = gbase[grp], end = gbase[grp + 1];
+  if (beg == end) return;
+  const int t0 = grp << gshift;
+  for (int i = tid; i < G; i += THREADS) cur[i] = offsets[min(t0 + i, nbuckets)];
+  float4 r[RPT];
+  auto fetch = [&](unsigned c0) {
+    const unsigned m = min((unsigned)CHUNK, end - c0);
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const unsigned j = (unsigned)tid + (unsigned)k * THREADS;
+      if (j < m) r[k] = JPS_FINE_LOAD(tmp + c0 + j);
+    }
+  };
+  fetch(beg);
+  for (unsigned c0 = beg; c0 < end; c0 += CHUNK) {
+    const unsigned m = min((unsigned)CHUNK, end - c0);
+    for (int i = tid; i < G; i += THREADS) h[i] = 0u;
+    if (tid == 0) h[G] = m;
+    __syncthreads();
+    unsigned key[RPT];                             // local tile | rank inside the chunk << 16
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const unsigned j = (unsigned)tid + (unsigned)k * THREADS;
+      key[k] = 0xffffffffu;
+      if (j < m) {
+        const unsigned f = (unsigned)(tile_of<ORDER, REFCIC>(r[k].x, r[k].y, r[k].z, g, 0u) - t0);
+        key[k] = f | (atomicAdd(h + f, 1u) << 16);
+      }
+    }
+    __syncthreads();
+    block_scan_inplace(h, G, scratch);             // h -> exclusive offsets inside the chunk (syncs inside)
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      if (key[k] != 0xffffffffu) {
+        const unsigned f = key[k] & 0xffffu, pos = h[f] + (key[k] >> 16);
+        stage[pos] = r[k];
+        skey[pos] = (unsigned short)f;
+      }
+    }
+    for (int i = tid; i < G; i += THREADS) {
+      const unsigned c = cur[i], o = h[i];
+      wb[i] = c - o;                               // mod 2^32: wb + (index in the chunk) is the record's slot
+      cur[i] = c + (h[i + 1] - o);
+    }
+    __syncthreads();
+    if (c0 + CHUNK < end) fetch(c0 + CHUNK);
+    for (unsigned j = tid; j < m; j += THREADS) sorted[wb[skey[j]] + j] = stage[j];   // a tile's records: consecutive slots
+    // no barrier here: the next round writes h only after its first barrier, stage / skey / wb after three more
+  }
+}
+
+template <int ORDER, bool REFCIC, int CHUNK, int THREADS, int MINB>
+static int launch_fine_staged(const float4* tmp, const unsigned* gbase, const TileGeom& g, int gshift, int ngroups, int nbuckets,
+                              const unsigned* offsets, float4* sorted, cudaStream_t s) {
+  JPS_REQUIRE(gshift <= 11, "fine_staged: 2^%d tiles per group do not fit the shared-memory tables", gshift);
+  static PerDeviceFlag attr_set;
+  if (!attr_set.get()) {
+    JPS_CHECK_CUDA(cudaFuncSetAttribute(fine_staged_kernel<ORDER, REFCIC, CHUNK, THREADS, MINB>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fine_staged_smem<CHUNK>(11)));
+    attr_set.set();
+  }
+  fine_staged_kernel<ORDER, REFCIC, CHUNK, THREADS, MINB><<<ngroups, THREADS, fine_staged_smem<CHUNK>(gshift), s>>>(
+      tmp, gbase, g, gshift, nbuckets, offsets, sorted);
+  return JPS_OK;
 }
 
 // ---------------------------------------------------------------- K2: per-tile deposit
@@ -836,6 +954,11 @@ __global__ void __launch_bounds__(256) paint_tile_kernel(const float4* __restric
 // A cleverer ordering of the particles (in-tile counting sort by cell, tried in round 1) was
 // SLOWER with float CAS: adjacent lanes then hit the same cell and every collision costs a full
 // CAS retry; with native integer atomics ordering no longer matters.
+// Fixed-point position of the tile accumulators: a contribution is quantised at 2^-JPS_FX_BITS of the tile's
+// largest weight.  31 = finest (|contribution| fills the low word; ~1 % of the updates carry into the high word).
+#ifndef JPS_FX_BITS
+#define JPS_FX_BITS 31
+#endif
 template <int ORDER>
 struct TileDims {
   static constexpr int L = TILE + ORDER - 1;
@@ -1080,7 +1203,7 @@ __global__ void __launch_bounds__(512, 3) paint_tile_fx_kernel(const float4* __r
   int e;
   frexpf(wmax, &e);
   e = max(-90, min(90, e));
-  const float scale = ldexpf(1.0f, 31 - e);
+  const float scale = ldexpf(1.0f, JPS_FX_BITS - e);
   __syncthreads();
 
   for (unsigned i = beg + threadIdx.x; i < end; i += blockDim.x) {
@@ -1093,7 +1216,7 @@ __global__ void __launch_bounds__(512, 3) paint_tile_fx_kernel(const float4* __r
   __syncthreads();
 
   // fixed point -> float32 (one rounding), in place over the low words: lo[] becomes a dense float box
-  const double inv_scale = (double)ldexpf(1.0f, e - 31);
+  const double inv_scale = (double)ldexpf(1.0f, e - JPS_FX_BITS);
   float* ftile = reinterpret_cast<float*>(lo);
   for (int i = threadIdx.x; i < NC; i += blockDim.x) {
     const unsigned l = lo[i], h = hi[i];
@@ -1289,9 +1412,18 @@ static int run_bucket_two_level(const PaintParams& p, const TileGeom& g, const S
   // shared-memory histogram when the tile table fits it, from global reds into the (L2-resident) table
   // otherwise.  JPS_FINE_TWOPASS=1 restores round 1's big-mesh path (group histogram, fine pass reads twice).
   static const bool two_pass = [] { const char* e = getenv("JPS_FINE_TWOPASS"); return e && atoi(e) != 0; }();
+  // JPS_COUNT=fused|separate: big meshes only -- tile histogram from reds issued by the coarse pass (the count pass is
+  // then the shared-memory group histogram) or by a pass of its own
+  static const int count_forced = [] {
+    const char* e = getenv("JPS_COUNT");
+    return !e ? 0 : !strcmp(e, "fused") ? 1 : !strcmp(e, "separate") ? 2 : 0;
+  }();
   const bool smem_hist = g.ntiles <= kSmemCountMaxTiles;        // tile histogram fits one SM's shared memory
   const bool have_offsets = smem_hist || !two_pass;
-  if (have_offsets) {
+  const bool count_in_coarse = !smem_hist && !two_pass && (count_forced == 1 || (count_forced == 0 && kCountInCoarseDefault));
+  const int nsb = (nbuckets + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  unsigned* block_tot = (unsigned*)(ws + L.block_tot);
+  if (have_offsets && !count_in_coarse) {
     // tile-level histogram (shared-memory privatised) + scan -> offsets[]; group bases are a sample of it
     unsigned* counts = (unsigned*)(ws + L.counts);
     unsigned* cursor = (unsigned*)(ws + L.cursor);
@@ -1319,8 +1451,6 @@ static int run_bucket_two_level(const PaintParams& p, const TileGeom& g, const S
     }
     JPS_CHECK_LAUNCH();
     {
-      const int nsb = (nbuckets + SCAN_BLOCK - 1) / SCAN_BLOCK;
-      unsigned* block_tot = (unsigned*)(ws + L.block_tot);
       { ScopedLaunch T(K_BUCKET_SCAN, s); scan_block_totals_kernel<<<nsb, SCAN_THREADS, 0, s>>>(counts, block_tot, nbuckets); }
       { ScopedLaunch T(K_BUCKET_SCAN, s); scan_of_totals_kernel<<<1, SCAN_THREADS, 0, s>>>(block_tot, nsb); }
       { ScopedLaunch T(K_BUCKET_SCAN, s); scan_write_kernel<<<nsb, SCAN_THREADS, 0, s>>>(counts, block_tot, offsets, cursor, nbuckets, nsb); }
@@ -1332,6 +1462,7 @@ static int run_bucket_two_level(const PaintParams& p, const TileGeom& g, const S
     ScopedLaunch T(K_MEMSET, s);
     JPS_CHECK_CUDA(cudaMemsetAsync(gcounts, 0, (size_t)(ngroups + 1) * 4, s));
     JPS_CHECK_CUDA(cudaMemsetAsync(wmax_bits, 0, 4, s));
+    if (count_in_coarse) JPS_CHECK_CUDA(cudaMemsetAsync(ws + L.counts, 0, (size_t)(nbuckets + 1) * 4, s));
   }
   {
     const int64_t want = (p.n_part + 256 * BUCKET_UNROLL - 1) / (256 * BUCKET_UNROLL);
@@ -1348,22 +1479,52 @@ static int run_bucket_two_level(const PaintParams& p, const TileGeom& g, const S
   }
   {
     const size_t smem = (size_t)COARSE_CHUNK * (sizeof(float4) + 2) + (size_t)ngroups * 8 + 33 * 4;
+    const int smem_max = (int)((size_t)COARSE_CHUNK * (sizeof(float4) + 2) + (size_t)kMaxGroups * 8 + 33 * 4);
     static PerDeviceFlag attr_set;
     if (!attr_set.get()) {
-      JPS_CHECK_CUDA(cudaFuncSetAttribute(coarse_scatter_kernel<ORDER, REFCIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)((size_t)COARSE_CHUNK * (sizeof(float4) + 2) + (size_t)kMaxGroups * 8 + 33 * 4)));
+      JPS_CHECK_CUDA(cudaFuncSetAttribute(coarse_scatter_kernel<ORDER, REFCIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+      JPS_CHECK_CUDA(cudaFuncSetAttribute(coarse_scatter_kernel<ORDER, REFCIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
       attr_set.set();
     }
     const int64_t nchunks = (p.n_part + COARSE_CHUNK - 1) / COARSE_CHUNK;
+    const int cblocks = (int)std::min<int64_t>(nchunks, JPS_COARSE_MINB * kNumSMs);
     ScopedLaunch T(K_BUCKET_SCATTER, s);
-    coarse_scatter_kernel<ORDER, REFCIC><<<(int)std::min<int64_t>(nchunks, JPS_COARSE_MINB * kNumSMs), COARSE_THREADS, smem, s>>>(
-        p, g, gshift, ngroups, gcursor, tmp);
+    if (count_in_coarse)
+      coarse_scatter_kernel<ORDER, REFCIC, true><<<cblocks, COARSE_THREADS, smem, s>>>(p, g, gshift, ngroups, gcursor, tmp,
+                                                                                      (unsigned*)(ws + L.counts));
+    else
+      coarse_scatter_kernel<ORDER, REFCIC, false><<<cblocks, COARSE_THREADS, smem, s>>>(p, g, gshift, ngroups, gcursor, tmp, nullptr);
   }
   JPS_CHECK_LAUNCH();
+  if (count_in_coarse) {                           // tile offsets from the counts the coarse pass left behind
+    unsigned* counts = (unsigned*)(ws + L.counts);
+    unsigned* cursor = (unsigned*)(ws + L.cursor);
+    { ScopedLaunch T(K_BUCKET_SCAN, s); scan_block_totals_kernel<<<nsb, SCAN_THREADS, 0, s>>>(counts, block_tot, nbuckets); }
+    { ScopedLaunch T(K_BUCKET_SCAN, s); scan_of_totals_kernel<<<1, SCAN_THREADS, 0, s>>>(block_tot, nsb); }
+    { ScopedLaunch T(K_BUCKET_SCAN, s); scan_write_kernel<<<nsb, SCAN_THREADS, 0, s>>>(counts, block_tot, offsets, cursor, nbuckets, nsb); }
+    JPS_CHECK_LAUNCH();
+  }
   {
     const size_t smem = (size_t)(2 << gshift) * 4 + 33 * 4;
+    // staged form: JPS_FINE=staged|direct forces one (A/B runs, tests)
+    static const int fine_forced = [] {
+      const char* e = getenv("JPS_FINE");
+      return !e ? 0 : !strcmp(e, "staged") ? 1 : !strcmp(e, "direct") ? 2 : 0;
+    }();
+    // JPS_FINE_CHUNK=big|small forces the chunk shape of the staged form
+    static const int chunk_forced = [] {
+      const char* e = getenv("JPS_FINE_CHUNK");
+      return !e ? 0 : !strcmp(e, "big") ? 1 : !strcmp(e, "small") ? 2 : 0;
+    }();
+    const bool staged = have_offsets && gshift <= 11 &&
+                        (fine_forced == 1 || (fine_forced == 0 && gshift >= kFineStagedMinShift));
+    const bool big = chunk_forced == 1 || (chunk_forced == 0 && gshift >= kFineStagedBigShift);
     ScopedLaunch T(K_BUCKET_FINE, s);
-    if (have_offsets)
+    if (staged) {
+      const int rc = big ? launch_fine_staged<ORDER, REFCIC, 8192, 1024, 1>(tmp, gbase, g, gshift, ngroups, nbuckets, offsets, sorted, s)
+                         : launch_fine_staged<ORDER, REFCIC, 4096, 512, 2>(tmp, gbase, g, gshift, ngroups, nbuckets, offsets, sorted, s);
+      if (rc) return rc;
+    } else if (have_offsets)
       fine_scatter_kernel<ORDER, REFCIC, true><<<ngroups, 512, smem, s>>>(tmp, gbase, g, gshift, ngroups, nbuckets, offsets, sorted);
     else
       fine_scatter_kernel<ORDER, REFCIC, false><<<ngroups, 512, smem, s>>>(tmp, gbase, g, gshift, ngroups, nbuckets, offsets, sorted);

@@ -1,4 +1,5 @@
-"""Run in a subprocess with JPS_BUCKET=two: the two-level partition against the atomic painter and f64 oracle."""
+"""Run in a subprocess with JPS_BUCKET=two (and, optionally, JPS_FINE / JPS_MAX_GROUPS): the two-level partition
+against the f64 oracle."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np

@@ -176,6 +176,18 @@ def test_two_level_partition_in_subprocess():
     assert r.returncode == 0 and "two-level ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("fine", ["staged", "direct"])
+def test_fine_pass_forms_in_subprocess(fine):
+    """Both forms of the fine pass (lone stores / chunks staged in shared memory), with few groups so that a group
+    holds many tiles even on a small mesh (64 groups: 128 tiles per group at 256^3)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, JPS_BUCKET="two", JPS_FINE=fine, JPS_MAX_GROUPS="64")
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "helpers", "two_level_check.py")],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "two-level ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("order", [2, 3, 4])
 def test_garbage_positions_do_not_crash_or_corrupt(jps, order):
     """NaN / inf / absurd coordinates must not fault or write out of bounds (nothing is validated, as
