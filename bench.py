@@ -290,26 +290,32 @@ ALGO_BYTES = {
 }
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-NCU_KERNEL = {"paint_tile": "paint_tile_fx_kernel", "bucket_scatter": "coarse_scatter_kernel",
-              "bucket_fine": "fine_scatter_kernel", "bucket_count": "bucket_count_smem_kernel",
-              "pk_fold_bin": "pk_fold_bin_kernel"}
+NCU_KERNEL = {"paint_tile": ("paint_tile_fx_kernel",), "bucket_scatter": ("coarse_scatter_kernel",),
+              "bucket_fine": ("fine_staged_kernel", "fine_scatter_kernel"),
+              "bucket_count": ("bucket_count_smem_kernel", "bucket_count_global_kernel"),
+              "pk_fold_bin": ("pk_fold_bin_kernel", "pk_bin_xfast_kernel")}
 
 
 def ncu_traffic(kernel, wl, world):
-    """Per-launch DRAM bytes from the committed ncu captures: C2 = profiles/r1_ncu_dram_traffic_c2.json,
-    one C4 rank of the 8-GPU decomposition = profiles/r2_ncu_dram_traffic_c4_rank.json (when present)."""
+    """Per-launch DRAM bytes from the committed ncu captures: C2 = profiles/r2_ncu_dram_traffic_c2.json, C4 on one GPU
+    = profiles/r2_ncu_dram_traffic_c4_1gpu.json, one C4 rank of the 8-GPU decomposition =
+    profiles/r2_ncu_dram_traffic_c4_rank.json (when present)."""
     name = None
     if wl["name"] == "C2" and (wl["n_part"], wl["n_mesh"], wl["order"]) == (C2["n_part"], C2["n_mesh"], C2["order"]):
         name = "r2_ncu_dram_traffic_c2.json"
         if not os.path.exists(os.path.join(ROOT, "profiles", name)):
             name = "r1_ncu_dram_traffic_c2.json"
-    elif wl["name"] == "C4" and world == 8 and (wl["n_part"], wl["n_mesh"], wl["order"]) == (C4["n_part"], C4["n_mesh"], C4["order"]):
-        name = "r2_ncu_dram_traffic_c4_rank.json"
+    elif wl["name"] == "C4" and world in (1, 8) and (wl["n_part"], wl["n_mesh"], wl["order"]) == (C4["n_part"], C4["n_mesh"], C4["order"]):
+        name = "r2_ncu_dram_traffic_c4_rank.json" if world == 8 else "r2_ncu_dram_traffic_c4_1gpu.json"
     if name is None:
         return None, None
     try:
         with open(os.path.join(ROOT, "profiles", name)) as f:
-            return json.load(f).get(NCU_KERNEL.get(kernel, "")), "profiles/" + name
+            table = json.load(f)
+        for k in NCU_KERNEL.get(kernel, ()):
+            if k in table:
+                return table[k], "profiles/" + name
+        return None, None
     except Exception:
         return None, None
 

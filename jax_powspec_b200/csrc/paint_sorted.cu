@@ -1040,6 +1040,15 @@ __device__ __forceinline__ int tile_local_axis(float pos, int n, int origin, int
   return l;
 }
 
+// The anchor alone (same arithmetic as tile_local_axis): the cell a particle's stencil starts in decides which
+// shared-memory bank its atomics hit.
+template <int ORDER>
+__device__ __forceinline__ int tile_local_anchor(float pos, int n, int origin) {
+  int l = anchor_base<ORDER>(pos) - origin;
+  if ((unsigned)l >= (unsigned)TILE) l = pymod(l, n);
+  return l;
+}
+
 template <int ORDER, bool REFCIC, bool NEG>
 __device__ __forceinline__ void fx_deposit(const float4& r, float ws, unsigned* lo, unsigned* hi,
                                            const TileGeom& g, int wrap, int variant, int ox, int oy, int oz) {
@@ -1165,7 +1174,7 @@ __global__ void __launch_bounds__(512, 3) paint_tile_fx_kernel(const float4* __r
                                                             int mesh_vec_ok, int has_w,
                                                             float* __restrict__ mesh,
                                                             const __grid_constant__ CUtensorMap tmap, int use_tma,
-                                                            int tile_offset) {
+                                                            int tile_offset, int bank_order) {
   constexpr int L = TileDims<ORDER>::L, LP = TileDims<ORDER>::LP, NC = TileDims<ORDER>::CELLS;
   extern __shared__ __align__(128) unsigned fx_smem[];
   unsigned* lo = fx_smem;
@@ -1206,22 +1215,88 @@ __global__ void __launch_bounds__(512, 3) paint_tile_fx_kernel(const float4* __r
   const float scale = ldexpf(1.0f, JPS_FX_BITS - e);
   __syncthreads();
 
-  for (unsigned i = beg + threadIdx.x; i < end; i += blockDim.x) {
-    const float4 r = sorted[i];
-    const float ws = fabsf(r.w) * scale;
-    if (has_w && !(fabsf(r.w) < 3.0e38f)) global_deposit<ORDER, REFCIC>(r.x, r.y, r.z, r.w, n, g.x0, g.nx, wrap, variant, mesh);
-    else if (r.w >= 0.0f) fx_deposit<ORDER, REFCIC, false>(r, ws, lo, hi, g, wrap, variant, ox, oy, oz);
-    else fx_deposit<ORDER, REFCIC, true>(r, ws, lo, hi, g, wrap, variant, ox, oy, oz);
+  if (!REFCIC && bank_order) {
+    // Bank-class order.  Every atomic of a warp instruction adds the SAME stencil offset to each lane's anchor cell, so
+    // the bank conflicts of all order^3 instructions are decided by the 32 anchors' word index mod 32 -- with particles
+    // in arrival order that is 32 balls in 32 bins (3.5 wavefronts per instruction: 54 % of the kernel's shared-memory
+    // wavefronts were conflict replays).  So each batch of blockDim particles is counting-sorted by that residue, and
+    // warp w takes the sorted positions w, w + nw, w + 2 nw, ... (nw = warps in the batch): its lanes walk through the
+    // classes and land on distinct banks but for the Poisson drift of the class sizes (2.0 wavefronts per instruction on
+    // C4's tiles, 1.6 on C2's), with every lane busy.  The records change hands through shared memory.
+    __shared__ unsigned s_cls[32], s_start[32];
+    float4* s_rec = reinterpret_cast<float4*>(fx_smem + 2 * NC);           // [blockDim]
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (unsigned b0 = beg; b0 < end; b0 += blockDim.x) {
+      const unsigned pb = min((unsigned)blockDim.x, end - b0);
+      const unsigned nwb = (pb + 31u) >> 5;
+      if (threadIdx.x < 32) s_cls[threadIdx.x] = 0u;
+      __syncthreads();
+      const bool valid = threadIdx.x < pb;
+      float4 r = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      unsigned cls = 0xffffu, rank = 0u;
+      if (valid) {
+        r = sorted[b0 + threadIdx.x];
+        const int lx = tile_local_anchor<ORDER>(r.x, n, g.x0 + ox), ly = tile_local_anchor<ORDER>(r.y, n, oy),
+                  lz = tile_local_anchor<ORDER>(r.z, n, oz);
+        cls = (unsigned)((lx * L + ly) * LP + lz) & 31u;
+      }
+      {
+        const unsigned same = __match_any_sync(0xffffffffu, cls);
+        const int leader = __ffs(same) - 1;
+        unsigned base = 0u;
+        if (valid && (int)lane == leader) base = atomicAdd(&s_cls[cls], (unsigned)__popc(same));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        rank = base + (unsigned)__popc(same & ((1u << lane) - 1u));
+      }
+      __syncthreads();
+      if (warp == 0) {                             // exclusive scan of the 32 class sizes
+        const unsigned c = s_cls[lane];
+        unsigned incl = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const unsigned t = __shfl_up_sync(0xffffffffu, incl, off);
+          if ((int)lane >= off) incl += t;
+        }
+        s_start[lane] = incl - c;
+      }
+      __syncthreads();
+      if (valid) {
+        const unsigned p = s_start[cls] + rank;    // sorted position -> (warp p % nwb, lane p / nwb)
+        const unsigned l = (p * (65536u / nwb + 1u)) >> 16;                // p / nwb, exact for p < 512, nwb <= 16
+        s_rec[(p - l * nwb) * 32u + l] = r;
+      }
+      __syncthreads();
+      if (warp < nwb && warp + nwb * lane < pb) {
+        r = s_rec[threadIdx.x];
+        const float ws = fabsf(r.w) * scale;
+        if (has_w && !(fabsf(r.w) < 3.0e38f)) global_deposit<ORDER, REFCIC>(r.x, r.y, r.z, r.w, n, g.x0, g.nx, wrap, variant, mesh);
+        else if (r.w >= 0.0f) fx_deposit<ORDER, REFCIC, false>(r, ws, lo, hi, g, wrap, variant, ox, oy, oz);
+        else fx_deposit<ORDER, REFCIC, true>(r, ws, lo, hi, g, wrap, variant, ox, oy, oz);
+      }
+      // no barrier: the next batch touches s_cls after its own first barrier and s_rec after three
+    }
+  } else {
+    for (unsigned i = beg + threadIdx.x; i < end; i += blockDim.x) {
+      const float4 r = sorted[i];
+      const float ws = fabsf(r.w) * scale;
+      if (has_w && !(fabsf(r.w) < 3.0e38f)) global_deposit<ORDER, REFCIC>(r.x, r.y, r.z, r.w, n, g.x0, g.nx, wrap, variant, mesh);
+      else if (r.w >= 0.0f) fx_deposit<ORDER, REFCIC, false>(r, ws, lo, hi, g, wrap, variant, ox, oy, oz);
+      else fx_deposit<ORDER, REFCIC, true>(r, ws, lo, hi, g, wrap, variant, ox, oy, oz);
+    }
   }
   __syncthreads();
 
   // fixed point -> float32 (one rounding), in place over the low words: lo[] becomes a dense float box
-  const double inv_scale = (double)ldexpf(1.0f, e - JPS_FX_BITS);
+  // A cell whose sum fits one word (high word 0: every cell of a sparse tile) takes one I2F and an exact multiply by the
+  // power of two -- the same value as the general 64-bit -> double -> float path, at a quarter of its instructions.
+  const float inv_scale_f = ldexpf(1.0f, e - JPS_FX_BITS);
+  const double inv_scale = (double)inv_scale_f;
   float* ftile = reinterpret_cast<float*>(lo);
   for (int i = threadIdx.x; i < NC; i += blockDim.x) {
     const unsigned l = lo[i], h = hi[i];
-    float v = 0.0f;
-    if ((l | h) != 0u) v = (float)((double)(long long)(((unsigned long long)h << 32) | l) * inv_scale);
+    float v;
+    if (h == 0u) v = __uint2float_rn(l) * inv_scale_f;
+    else v = (float)((double)(long long)(((unsigned long long)h << 32) | l) * inv_scale);
     ftile[i] = v;
   }
   // whole box inside the mesh along y, z (and x for a full mesh; a slab's missing planes are clipped)?
@@ -1580,7 +1655,8 @@ static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayo
       paint_tile_kernel<ORDER, REFCIC><<<g.ntiles, 256, 0, s>>>(sorted, offsets, g, p.wrap, p.variant,
                                                               mesh_vec_ok, p.mesh);
     } else {
-      constexpr int smem = 2 * TileDims<ORDER>::CELLS * (int)sizeof(unsigned);
+      // the fixed-point tile (two words per cell) + one record per thread (bank-class order of the particles)
+      constexpr int smem = 2 * TileDims<ORDER>::CELLS * (int)sizeof(unsigned) + 512 * (int)sizeof(float4);
       static PerDeviceFlag attr_set;
       if (!attr_set.get()) {
         JPS_CHECK_CUDA(cudaFuncSetAttribute(paint_tile_fx_kernel<ORDER, REFCIC>,
@@ -1590,15 +1666,17 @@ static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayo
       // CTA size (measured, C2 / a C4 rank): 256 threads 1.94 ms, 384 1.56, 512 1.61, 768 1.89 for TSC;
       // PCS on sparse tiles 9.2 (256), 6.67 (384), 6.41 (512) ms; CIC flat between 320 and 512.
       static const int tpb_env = [] { const char* e = getenv("JPS_TILE_THREADS"); return e ? atoi(e) : 0; }();
-      const int tpb = tpb_env > 0 ? std::min(tpb_env, 512) : (ORDER == 3 ? 384 : 512);
+      const int tpb = tpb_env > 0 ? std::max(32, std::min(tpb_env, 512) & ~31) : (ORDER == 3 ? 384 : 512);   // whole warps
       // JPS_TILE_FLUSH=red forces the per-thread red flush everywhere (A/B runs, tests)
       static const bool no_tma = [] { const char* e = getenv("JPS_TILE_FLUSH"); return e && !strcmp(e, "red"); }();
       CUtensorMap tmap;
       memset(&tmap, 0, sizeof(tmap));
       const int use_tma = (!no_tma && make_mesh_tensor_map(&tmap, p.mesh, g.n, g.nx, TileDims<ORDER>::L, TileDims<ORDER>::LP)) ? 1 : 0;
+      // JPS_TILE_ORDER=arrival keeps the particles of a tile in arrival order (A/B runs, tests)
+      static const bool arrival = [] { const char* e = getenv("JPS_TILE_ORDER"); return e && !strcmp(e, "arrival"); }();
       paint_tile_fx_kernel<ORDER, REFCIC><<<tile_count, tpb, smem, s>>>(sorted, offsets, g, p.wrap, p.variant,
                                                                       mesh_vec_ok, p.w ? 1 : 0, p.mesh, tmap, use_tma,
-                                                                      tile_offset);
+                                                                      tile_offset, arrival ? 0 : 1);
     }
   }
   JPS_CHECK_LAUNCH();

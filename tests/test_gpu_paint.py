@@ -176,16 +176,31 @@ def test_two_level_partition_in_subprocess():
     assert r.returncode == 0 and "two-level ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("fine", ["staged", "direct"])
-def test_fine_pass_forms_in_subprocess(fine):
-    """Both forms of the fine pass (lone stores / chunks staged in shared memory), with few groups so that a group
-    holds many tiles even on a small mesh (64 groups: 128 tiles per group at 256^3)."""
+@pytest.mark.parametrize("cfg", [{"JPS_FINE": "staged"}, {"JPS_FINE": "direct"}, {"JPS_FINE": "staged", "JPS_FINE_CHUNK": "big"},
+                                 {"JPS_TILE_ORDER": "arrival"}, {"JPS_TILE_ORDER": "arrival", "JPS_TILE_FLUSH": "red"}])
+def test_fine_pass_forms_in_subprocess(cfg):
+    """Both forms of the fine pass (lone stores / chunks staged in shared memory, both chunk shapes), with few groups
+    so that a group holds many tiles even on a small mesh (64 groups: 128 tiles per group at 256^3); and the deposit
+    with the particles of a tile in arrival order (the default is the bank-class order)."""
     import subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, JPS_BUCKET="two", JPS_FINE=fine, JPS_MAX_GROUPS="64")
+    env = dict(os.environ, JPS_BUCKET="two", JPS_MAX_GROUPS="64", **cfg)
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "helpers", "two_level_check.py")],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "two-level ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("cfg", [{"JPS_COUNT": "fused", "JPS_FINE": "staged", "JPS_FINE_CHUNK": "big"},
+                                 {"JPS_COUNT": "separate", "JPS_FINE": "staged", "JPS_FINE_CHUNK": "small"},
+                                 {"JPS_COUNT": "fused", "JPS_FINE": "direct"}, {}])
+def test_big_mesh_bucketing_options_in_subprocess(cfg):
+    """N = 592 (more tiles than the shared-memory histogram holds): tile histogram from its own pass or fused into the
+    coarse pass, both forms of the fine pass, both chunk shapes -- each against the plain atomic painter."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "helpers", "big_mesh_check.py")],
+                       env=dict(os.environ, **cfg), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "big-mesh ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 @pytest.mark.parametrize("order", [2, 3, 4])
