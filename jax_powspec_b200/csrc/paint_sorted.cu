@@ -947,18 +947,19 @@ __global__ void __launch_bounds__(256) paint_tile_kernel(const float4* __restric
 // same-address retries.  So the tile is accumulated in 64-bit fixed point held as two 32-bit words
 // per cell: lo += q (native atomic, returns the old value -> carry), hi += carry (native, only on
 // overflow of the low word: ~4% of the updates).  Each contribution is the SAME float32 product the
-// reference forms, scaled by a power of two 2^(31-e) with 2^e >= max|w| (exact in float32) and
-// rounded to an integer, i.e. quantised at 2^-31 of the largest weight -- far below float32
+// reference forms, scaled by a power of two 2^(fx_bits-e) with 2^e >= max|w| (exact in float32; fx_bits = 31 or 28,
+// below) and rounded to an integer, i.e. quantised at 2^-fx_bits of the largest weight -- far below float32
 // resolution -- and integer addition is associative, so the tile sum is independent of the order
 // in which particles arrive (the float32 path is only reproducible to ~1e-7).
 // A cleverer ordering of the particles (in-tile counting sort by cell, tried in round 1) was
 // SLOWER with float CAS: adjacent lanes then hit the same cell and every collision costs a full
 // CAS retry; with native integer atomics ordering no longer matters.
-// Fixed-point position of the tile accumulators: a contribution is quantised at 2^-JPS_FX_BITS of the tile's
-// largest weight.  31 = finest (|contribution| fills the low word; ~1 % of the updates carry into the high word).
-#ifndef JPS_FX_BITS
-#define JPS_FX_BITS 31
-#endif
+// Fixed-point position of the tile accumulators (kernel argument fx_bits, JPS_FX_BITS overrides): a contribution is
+// quantised at 2^-fx_bits of the tile's largest weight.  31 = finest: |contribution| fills the low word, and with PCS
+// 0.8 % of the updates carry into the high word -- two thirds of the warp-level rows of four then take the slow path,
+// which costs the deposit a third of its instructions.  28 (the PCS default: that kernel is bound by instruction
+// issue once its bank conflicts are gone) makes carries 8x rarer; the quantum, 3.7e-9 of the tile's largest weight, is
+// still an order of magnitude below the float32 rounding of the products being added (6e-8 relative).
 template <int ORDER>
 struct TileDims {
   static constexpr int L = TILE + ORDER - 1;
@@ -966,7 +967,7 @@ struct TileDims {
   static constexpr int CELLS = L * L * LP;
 };
 
-// v >= 0 is the magnitude of one contribution in units of 2^-31 of the weight scale (< 2^32, one
+// v >= 0 is the magnitude of one contribution in units of 2^-fx_bits of the weight scale (< 2^32, one
 // F2I); NEG selects subtraction (negative particle weight).  64-bit two's-complement arithmetic on
 // the (hi, lo) word pair: the low-word atomic returns the old value, from which carry / borrow follow.
 // K contributions at once: all K low-word atomics are issued back to back (independent, K in
@@ -985,8 +986,21 @@ __device__ __forceinline__ void fx_add_batch(unsigned* __restrict__ lo, unsigned
   // wrapped sum so that the compiler keeps the fast path to K compares (it otherwise materialises
   // both senses of every predicate before the branch).
   bool any = false;
+  if (NEG) {
 #pragma unroll
-  for (int j = 0; j < K; ++j) any |= NEG ? (old[j] < q[j]) : (q[j] > ~old[j]);
+    for (int j = 0; j < K; ++j) any |= (old[j] < q[j]);
+  } else {
+    // number of carries as the high words of 64-bit sums: one add with carry-out + one add-with-carry per update
+    // (IADD3 / IADD3.X) instead of a complement and two compares
+    // (inline PTX: from the C expression the compiler falls back to compares and selects)
+    unsigned nc = 0u;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      unsigned t;
+      asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %1, 0;" : "=r"(t), "+r"(nc) : "r"(old[j]), "r"(q[j]));
+    }
+    any = nc != 0u;
+  }
   if (any) {
 #pragma unroll
     for (int j = 0; j < K; ++j) {
@@ -1054,9 +1068,9 @@ __device__ __forceinline__ void fx_deposit(const float4& r, float ws, unsigned* 
                                            const TileGeom& g, int wrap, int variant, int ox, int oy, int oz) {
   constexpr int L = TileDims<ORDER>::L, LP = TileDims<ORDER>::LP;
   const int n = g.n;
-  // ws = |w| * 2^(31-e): the power-of-two scale is folded into the weight, which commutes exactly
+  // ws = |w| * 2^(fx_bits-e): the power-of-two scale is folded into the weight, which commutes exactly
   // with the float32 products below, so each contribution is the reference's float32 product
-  // (src/mas.py:142-151, left to right) times 2^(31-e).
+  // (src/mas.py:142-151, left to right) times 2^(fx_bits-e).
   if (REFCIC) {
     int x0, x1, y0, y1, z0, z1;
     float mdx, ddx, mdy, ddy, mdz, ddz;
@@ -1174,7 +1188,7 @@ __global__ void __launch_bounds__(512, 3) paint_tile_fx_kernel(const float4* __r
                                                             int mesh_vec_ok, int has_w,
                                                             float* __restrict__ mesh,
                                                             const __grid_constant__ CUtensorMap tmap, int use_tma,
-                                                            int tile_offset, int bank_order) {
+                                                            int tile_offset, int bank_order, int fx_bits) {
   constexpr int L = TileDims<ORDER>::L, LP = TileDims<ORDER>::LP, NC = TileDims<ORDER>::CELLS;
   extern __shared__ __align__(128) unsigned fx_smem[];
   unsigned* lo = fx_smem;
@@ -1188,7 +1202,7 @@ __global__ void __launch_bounds__(512, 3) paint_tile_fx_kernel(const float4* __r
   static_assert((2 * NC) % 4 == 0, "tile words are zeroed 16 bytes at a time");
   for (int i = threadIdx.x; i < (2 * NC) / 4; i += blockDim.x) reinterpret_cast<uint4*>(fx_smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   // Power-of-two scale of THIS tile: 2^e >= max|w| over the tile's own particles, so that
-  // |contribution| * 2^(31-e) <= 2^31 fits one 32-bit word and the quantum is 2^-31 of the tile's largest
+  // |contribution| * 2^(fx_bits-e) <= 2^31 fits one 32-bit word and the quantum is 2^-fx_bits of the tile's largest
   // weight -- one outlier weight costs precision in its own 16^3 cells only, not in the whole mesh.  With unit
   // weights (no w array) the scale is 2^31 and the extra pass over the tile's records is skipped.  Particles
   // with a non-finite weight never enter the fixed-point tile: they are deposited straight into the mesh with
@@ -1212,7 +1226,7 @@ __global__ void __launch_bounds__(512, 3) paint_tile_fx_kernel(const float4* __r
   int e;
   frexpf(wmax, &e);
   e = max(-90, min(90, e));
-  const float scale = ldexpf(1.0f, JPS_FX_BITS - e);
+  const float scale = ldexpf(1.0f, fx_bits - e);
   __syncthreads();
 
   if (!REFCIC && bank_order) {
@@ -1222,9 +1236,12 @@ __global__ void __launch_bounds__(512, 3) paint_tile_fx_kernel(const float4* __r
     // wavefronts were conflict replays).  So each batch of blockDim particles is counting-sorted by that residue, and
     // warp w takes the sorted positions w, w + nw, w + 2 nw, ... (nw = warps in the batch): its lanes walk through the
     // classes and land on distinct banks but for the Poisson drift of the class sizes (2.0 wavefronts per instruction on
-    // C4's tiles, 1.6 on C2's), with every lane busy.  The records change hands through shared memory.
+    // C4's tiles, 1.6 on C2's), with every lane busy.  Measured (ncu, one C4 rank): conflict replays 6.7e8 -> 3.4e8,
+    // shared-memory wavefronts 12.4e8 -> 9.6e8; the sort costs ~120 instructions per particle and four barriers per
+    // batch, which only the 64-update PCS stencil pays back (TSC on C2: 1.52 -> 2.13 ms), so it is the default for
+    // order 4 only.
     __shared__ unsigned s_cls[32], s_start[32];
-    float4* s_rec = reinterpret_cast<float4*>(fx_smem + 2 * NC);           // [blockDim]
+    __shared__ unsigned short s_perm[512];                                 // [warp][lane] -> particle of the batch
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (unsigned b0 = beg; b0 < end; b0 += blockDim.x) {
       const unsigned pb = min((unsigned)blockDim.x, end - b0);
@@ -1263,17 +1280,17 @@ __global__ void __launch_bounds__(512, 3) paint_tile_fx_kernel(const float4* __r
       if (valid) {
         const unsigned p = s_start[cls] + rank;    // sorted position -> (warp p % nwb, lane p / nwb)
         const unsigned l = (p * (65536u / nwb + 1u)) >> 16;                // p / nwb, exact for p < 512, nwb <= 16
-        s_rec[(p - l * nwb) * 32u + l] = r;
+        s_perm[(p - l * nwb) * 32u + l] = (unsigned short)threadIdx.x;
       }
       __syncthreads();
       if (warp < nwb && warp + nwb * lane < pb) {
-        r = s_rec[threadIdx.x];
+        r = sorted[b0 + s_perm[threadIdx.x]];      // second read of the batch's records: L1 / L2 hits
         const float ws = fabsf(r.w) * scale;
         if (has_w && !(fabsf(r.w) < 3.0e38f)) global_deposit<ORDER, REFCIC>(r.x, r.y, r.z, r.w, n, g.x0, g.nx, wrap, variant, mesh);
         else if (r.w >= 0.0f) fx_deposit<ORDER, REFCIC, false>(r, ws, lo, hi, g, wrap, variant, ox, oy, oz);
         else fx_deposit<ORDER, REFCIC, true>(r, ws, lo, hi, g, wrap, variant, ox, oy, oz);
       }
-      // no barrier: the next batch touches s_cls after its own first barrier and s_rec after three
+      // no barrier: the next batch touches s_cls after its own first barrier and s_perm after three
     }
   } else {
     for (unsigned i = beg + threadIdx.x; i < end; i += blockDim.x) {
@@ -1289,7 +1306,7 @@ __global__ void __launch_bounds__(512, 3) paint_tile_fx_kernel(const float4* __r
   // fixed point -> float32 (one rounding), in place over the low words: lo[] becomes a dense float box
   // A cell whose sum fits one word (high word 0: every cell of a sparse tile) takes one I2F and an exact multiply by the
   // power of two -- the same value as the general 64-bit -> double -> float path, at a quarter of its instructions.
-  const float inv_scale_f = ldexpf(1.0f, e - JPS_FX_BITS);
+  const float inv_scale_f = ldexpf(1.0f, e - fx_bits);
   const double inv_scale = (double)inv_scale_f;
   float* ftile = reinterpret_cast<float*>(lo);
   for (int i = threadIdx.x; i < NC; i += blockDim.x) {
@@ -1655,8 +1672,7 @@ static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayo
       paint_tile_kernel<ORDER, REFCIC><<<g.ntiles, 256, 0, s>>>(sorted, offsets, g, p.wrap, p.variant,
                                                               mesh_vec_ok, p.mesh);
     } else {
-      // the fixed-point tile (two words per cell) + one record per thread (bank-class order of the particles)
-      constexpr int smem = 2 * TileDims<ORDER>::CELLS * (int)sizeof(unsigned) + 512 * (int)sizeof(float4);
+      constexpr int smem = 2 * TileDims<ORDER>::CELLS * (int)sizeof(unsigned);
       static PerDeviceFlag attr_set;
       if (!attr_set.get()) {
         JPS_CHECK_CUDA(cudaFuncSetAttribute(paint_tile_fx_kernel<ORDER, REFCIC>,
@@ -1672,11 +1688,18 @@ static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayo
       CUtensorMap tmap;
       memset(&tmap, 0, sizeof(tmap));
       const int use_tma = (!no_tma && make_mesh_tensor_map(&tmap, p.mesh, g.n, g.nx, TileDims<ORDER>::L, TileDims<ORDER>::LP)) ? 1 : 0;
-      // JPS_TILE_ORDER=arrival keeps the particles of a tile in arrival order (A/B runs, tests)
-      static const bool arrival = [] { const char* e = getenv("JPS_TILE_ORDER"); return e && !strcmp(e, "arrival"); }();
+      // JPS_TILE_ORDER=bank|arrival: particles of a tile in bank-class order (default for PCS) or in arrival order;
+      // JPS_FX_BITS=24..31: fixed-point position (default 28 with the bank-class order, 31 otherwise)
+      static const int order_forced = [] {
+        const char* e = getenv("JPS_TILE_ORDER");
+        return !e ? 0 : !strcmp(e, "bank") ? 1 : !strcmp(e, "arrival") ? 2 : 0;
+      }();
+      static const int fx_env = [] { const char* e = getenv("JPS_FX_BITS"); const int v = e ? atoi(e) : 0; return (v >= 24 && v <= 31) ? v : 0; }();
+      const int bank_order = (!REFCIC && (order_forced == 1 || (order_forced == 0 && ORDER == 4))) ? 1 : 0;
+      const int fx_bits = fx_env ? fx_env : (bank_order ? 28 : 31);
       paint_tile_fx_kernel<ORDER, REFCIC><<<tile_count, tpb, smem, s>>>(sorted, offsets, g, p.wrap, p.variant,
                                                                       mesh_vec_ok, p.w ? 1 : 0, p.mesh, tmap, use_tma,
-                                                                      tile_offset, arrival ? 0 : 1);
+                                                                      tile_offset, bank_order, fx_bits);
     }
   }
   JPS_CHECK_LAUNCH();
