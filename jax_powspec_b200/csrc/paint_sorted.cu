@@ -954,12 +954,11 @@ __global__ void __launch_bounds__(256) paint_tile_kernel(const float4* __restric
 // A cleverer ordering of the particles (in-tile counting sort by cell, tried in round 1) was
 // SLOWER with float CAS: adjacent lanes then hit the same cell and every collision costs a full
 // CAS retry; with native integer atomics ordering no longer matters.
-// Fixed-point position of the tile accumulators (kernel argument fx_bits, JPS_FX_BITS overrides): a contribution is
-// quantised at 2^-fx_bits of the tile's largest weight.  31 = finest: |contribution| fills the low word, and with PCS
-// 0.8 % of the updates carry into the high word -- two thirds of the warp-level rows of four then take the slow path,
-// which costs the deposit a third of its instructions.  28 (the PCS default: that kernel is bound by instruction
-// issue once its bank conflicts are gone) makes carries 8x rarer; the quantum, 3.7e-9 of the tile's largest weight, is
-// still an order of magnitude below the float32 rounding of the products being added (6e-8 relative).
+// Fixed-point position of the tile accumulators (kernel argument fx_bits = 31; JPS_FX_BITS=24..31 overrides): a
+// contribution is quantised at 2^-fx_bits of the tile's largest weight.  At 31 |contribution| fills the low word and,
+// with PCS, 0.8 % of the updates carry into the high word (two thirds of the warp-level rows of four take the slow
+// path); 28 makes carries 8x rarer at a quantum of 3.7e-9 -- measured: no change in the kernel's time (5.25 ms per C4
+// rank either way: it is bound by the shared-memory atomic pipe, not by instruction issue), so the finest position stays.
 template <int ORDER>
 struct TileDims {
   static constexpr int L = TILE + ORDER - 1;
@@ -1236,10 +1235,12 @@ __global__ void __launch_bounds__(512, 3) paint_tile_fx_kernel(const float4* __r
     // wavefronts were conflict replays).  So each batch of blockDim particles is counting-sorted by that residue, and
     // warp w takes the sorted positions w, w + nw, w + 2 nw, ... (nw = warps in the batch): its lanes walk through the
     // classes and land on distinct banks but for the Poisson drift of the class sizes (2.0 wavefronts per instruction on
-    // C4's tiles, 1.6 on C2's), with every lane busy.  Measured (ncu, one C4 rank): conflict replays 6.7e8 -> 3.4e8,
-    // shared-memory wavefronts 12.4e8 -> 9.6e8; the sort costs ~120 instructions per particle and four barriers per
-    // batch, which only the 64-update PCS stencil pays back (TSC on C2: 1.52 -> 2.13 ms), so it is the default for
-    // order 4 only.
+    // C4's tiles, 1.6 on C2's), with every lane busy.  MEASURED AND NOT THE DEFAULT (JPS_TILE_ORDER=bank enables it):
+    // on one C4 rank (ncu) the conflict replays fall from 6.7e8 to 3.2e8 and the shared-memory wavefronts from 12.4e8
+    // to 9.1e8 (l1tex 85 % -> 64 % busy) exactly as the model says -- tools/microbench_atoms.cu: an ATOMS costs its
+    // conflict degree + 0.3 clocks, 1.33 with 32 distinct banks, 3.84 with random words -- but the sort adds 10 % to the
+    // instruction count and four barriers per batch, and the kernel, already issuing 69 % of the time, ends up bound by
+    // issue and barriers instead: PCS 5.25 -> 5.49 ms per C4 rank, TSC on C2 1.40 -> 1.89 ms, CIC 0.38 -> 0.44 ms.
     __shared__ unsigned s_cls[32], s_start[32];
     __shared__ unsigned short s_perm[512];                                 // [warp][lane] -> particle of the batch
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -1688,15 +1689,15 @@ static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayo
       CUtensorMap tmap;
       memset(&tmap, 0, sizeof(tmap));
       const int use_tma = (!no_tma && make_mesh_tensor_map(&tmap, p.mesh, g.n, g.nx, TileDims<ORDER>::L, TileDims<ORDER>::LP)) ? 1 : 0;
-      // JPS_TILE_ORDER=bank|arrival: particles of a tile in bank-class order (default for PCS) or in arrival order;
-      // JPS_FX_BITS=24..31: fixed-point position (default 28 with the bank-class order, 31 otherwise)
+      // JPS_TILE_ORDER=bank: particles of a tile in bank-class order instead of arrival order (measured slower, see
+      // the kernel); JPS_FX_BITS=24..31: fixed-point position (default 31)
       static const int order_forced = [] {
         const char* e = getenv("JPS_TILE_ORDER");
         return !e ? 0 : !strcmp(e, "bank") ? 1 : !strcmp(e, "arrival") ? 2 : 0;
       }();
       static const int fx_env = [] { const char* e = getenv("JPS_FX_BITS"); const int v = e ? atoi(e) : 0; return (v >= 24 && v <= 31) ? v : 0; }();
-      const int bank_order = (!REFCIC && (order_forced == 1 || (order_forced == 0 && ORDER == 4))) ? 1 : 0;
-      const int fx_bits = fx_env ? fx_env : (bank_order ? 28 : 31);
+      const int bank_order = (!REFCIC && order_forced == 1) ? 1 : 0;
+      const int fx_bits = fx_env ? fx_env : 31;
       paint_tile_fx_kernel<ORDER, REFCIC><<<tile_count, tpb, smem, s>>>(sorted, offsets, g, p.wrap, p.variant,
                                                                       mesh_vec_ok, p.w ? 1 : 0, p.mesh, tmap, use_tma,
                                                                       tile_offset, bank_order, fx_bits);

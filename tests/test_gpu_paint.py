@@ -177,11 +177,11 @@ def test_two_level_partition_in_subprocess():
 
 
 @pytest.mark.parametrize("cfg", [{"JPS_FINE": "staged"}, {"JPS_FINE": "direct"}, {"JPS_FINE": "staged", "JPS_FINE_CHUNK": "big"},
-                                 {"JPS_TILE_ORDER": "arrival"}, {"JPS_TILE_ORDER": "arrival", "JPS_TILE_FLUSH": "red"}])
+                                 {"JPS_TILE_ORDER": "bank"}, {"JPS_TILE_ORDER": "bank", "JPS_TILE_FLUSH": "red", "JPS_FX_BITS": "28"}])
 def test_fine_pass_forms_in_subprocess(cfg):
     """Both forms of the fine pass (lone stores / chunks staged in shared memory, both chunk shapes), with few groups
     so that a group holds many tiles even on a small mesh (64 groups: 128 tiles per group at 256^3); and the deposit
-    with the particles of a tile in arrival order (the default is the bank-class order)."""
+    with the particles of a tile in bank-class order (an option: the default is arrival order)."""
     import subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, JPS_BUCKET="two", JPS_MAX_GROUPS="64", **cfg)

@@ -14,9 +14,10 @@ for tool in memcheck racecheck; do
   echo "$tool exit code $?" >> gpurun_out/sanitize_paint_$tool.log
   tail -6 gpurun_out/sanitize_paint_$tool.log
 done
-# both shapes of the staged fine pass and the tile histogram fused into the coarse pass (128 tiles per group at 256^3)
+# both shapes of the staged fine pass (128 tiles per group at 256^3), the bank-class order of the deposit, and the tile
+# histogram fused into the coarse pass (N = 592)
 for tool in memcheck racecheck; do
-  for cfg in "JPS_FINE_CHUNK=small JPS_COUNT=separate" "JPS_FINE_CHUNK=big JPS_COUNT=fused"; do
+  for cfg in "JPS_FINE_CHUNK=small JPS_COUNT=separate" "JPS_FINE_CHUNK=big JPS_TILE_ORDER=bank"; do
     env JPS_BUCKET=two JPS_FINE=staged JPS_MAX_GROUPS=64 $cfg timeout 600 $SAN --tool $tool --error-exitcode 99 --print-limit 20 \
         python tests/helpers/two_level_check.py --quick >> gpurun_out/sanitize_fine_$tool.log 2>&1
     echo "[$cfg] $tool exit code $?" >> gpurun_out/sanitize_fine_$tool.log
