@@ -1,6 +1,10 @@
 #!/bin/bash
 # Round-2b probe (ONE GPU): bucketing passes of the painter at C4's full size on one GPU -- group count, staged fine
 # pass, streaming loads, fixed-point position of the deposit -- plus a limited-section ncu capture of the three passes.
+# Variant libraries (not kept in the tree; build them first):
+#   bash tools/build_variant.sh fx28 -DJPS_FX_BITS=28      (before fx_bits became a kernel argument: now JPS_FX_BITS=28 in the environment)
+#   bash tools/build_variant.sh ldcs -DJPS_FINE_LDCS
+#   bash tools/build_variant.sh fs8k -DJPS_FS_CHUNK=8192 -DJPS_FS_THREADS=1024 -DJPS_FS_MINB=1   (now JPS_FINE_CHUNK=big)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 LOG=gpurun_out/r2b_probe.log

@@ -2,6 +2,8 @@
 # Round-2b probe 2 (ONE GPU): auto rule of the staged fine pass, tile histogram fused into the coarse pass, 8192-record
 # coarse chunks; on the painter alone (full 2048^3 mesh, one rank of the 8-GPU and of the 2-GPU decomposition), C2, and
 # the default bench's per-kernel pass.
+# Variant library (not kept in the tree; build it first):
+#   bash tools/build_variant.sh coarse8k -DJPS_COARSE_CHUNK=8192 -DJPS_COARSE_THREADS=1024 -DJPS_COARSE_MINB=1
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 LOG=gpurun_out/r2b_probe2.log
