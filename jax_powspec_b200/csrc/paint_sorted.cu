@@ -954,6 +954,25 @@ __global__ void __launch_bounds__(256) paint_tile_kernel(const float4* __restric
 // A cleverer ordering of the particles (in-tile counting sort by cell, tried in round 1) was
 // SLOWER with float CAS: adjacent lanes then hit the same cell and every collision costs a full
 // CAS retry; with native integer atomics ordering no longer matters.
+// Heavy tiles.  One CTA deposits at most kTileSplit particles of a tile; a tile that holds more is finished by further
+// CTAs (a second launch over the list of (tile, part) pairs built here), each with its own shared-memory copy of the
+// tile -- the flush is additive, so nothing else changes.  Measured on a B200 (1e8 particles, TSC, 512^3,
+// tools/clustered_paint.py, before / after): half of the particles in 40 blobs (2.3e5 in the densest tile, 74x the
+// mean) 2.15 ms against 1.35 ms for a uniform catalogue; half in 4 blobs of 1 % of the box (7.6e6 in one tile)
+// 31.4 ms -- one CTA working through millions of particles while the GPU idles.
+constexpr int kTileSplit = 16384;
+
+__global__ void __launch_bounds__(256) tile_parts_kernel(const unsigned* __restrict__ offsets, int ntiles, int rep,
+                                                         uint2* __restrict__ parts, unsigned* __restrict__ nparts, int cap) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  const unsigned c = offsets[(t + 1) * rep] - offsets[t * rep];
+  if (c <= (unsigned)kTileSplit) return;
+  const unsigned k = (c - 1u) / (unsigned)kTileSplit;         // parts beyond the first
+  const unsigned base = atomicAdd(nparts, k);
+  for (unsigned i = 0; i < k && base + i < (unsigned)cap; ++i) parts[base + i] = make_uint2((unsigned)t, i + 1u);
+}
+
 // Fixed-point position of the tile accumulators (kernel argument fx_bits = 31; JPS_FX_BITS=24..31 overrides): a
 // contribution is quantised at 2^-fx_bits of the tile's largest weight.  At 31 |contribution| fills the low word and,
 // with PCS, 0.8 % of the updates carry into the high word (two thirds of the warp-level rows of four take the slow
@@ -1187,14 +1206,31 @@ __global__ void __launch_bounds__(512, 3) paint_tile_fx_kernel(const float4* __r
                                                             int mesh_vec_ok, int has_w,
                                                             float* __restrict__ mesh,
                                                             const __grid_constant__ CUtensorMap tmap, int use_tma,
-                                                            int tile_offset, int bank_order, int fx_bits) {
+                                                            int tile_offset, int bank_order, int fx_bits,
+                                                            const uint2* __restrict__ parts,
+                                                            const unsigned* __restrict__ nparts, int tile_count) {
   constexpr int L = TileDims<ORDER>::L, LP = TileDims<ORDER>::LP, NC = TileDims<ORDER>::CELLS;
   extern __shared__ __align__(128) unsigned fx_smem[];
   unsigned* lo = fx_smem;
   unsigned* hi = fx_smem + NC;
-  const int t = blockIdx.x + tile_offset;
-  const unsigned beg = offsets[t * g.rep], end = offsets[(t + 1) * g.rep];
-  if (beg == end) return;
+  // first launch: CTA b takes the first kTileSplit particles of tile b; second launch (parts != nullptr): CTA b takes
+  // entry b of the list of further parts of heavy tiles
+  int t;
+  unsigned beg, end;
+  if (parts == nullptr) {
+    t = blockIdx.x + tile_offset;
+    beg = offsets[t * g.rep];
+    end = offsets[(t + 1) * g.rep];
+  } else {
+    if (blockIdx.x >= *nparts) return;
+    const uint2 e = parts[blockIdx.x];
+    t = (int)e.x;
+    if (t < tile_offset || t >= tile_offset + tile_count) return;      // deposit of a range of tile rows
+    beg = offsets[t * g.rep] + e.y * (unsigned)kTileSplit;        // < offsets[(t + 1) * rep]: the list holds existing parts only
+    end = offsets[(t + 1) * g.rep];
+  }
+  if (beg >= end) return;
+  if (end - beg > (unsigned)kTileSplit) end = beg + (unsigned)kTileSplit;
   const int tz = t % g.nt, ty = (t / g.nt) % g.nt, tx = t / (g.nt * g.nt);
   const int ox = tx * TILE, oy = ty * TILE, oz = tz * TILE;
   const int n = g.n;
@@ -1394,7 +1430,8 @@ __global__ void __launch_bounds__(256) paint_outliers_kernel(const float4* __res
 
 // ---------------------------------------------------------------- host side
 struct SortedLayout {
-  size_t sorted, tmp, counts, offsets, cursor, block_tot, wmax, gcounts, gbase, gcursor, total;
+  size_t sorted, tmp, counts, offsets, cursor, block_tot, wmax, gcounts, gbase, gcursor, parts, nparts, total;
+  int parts_cap;
   int nbuckets;
 };
 
@@ -1422,6 +1459,9 @@ static SortedLayout sorted_layout(int n, int nx, int64_t n_part) {
   L.gcounts = take((size_t)(kMaxGroups + 1) * 4);
   L.gbase = take((size_t)(kMaxGroups + 1) * 4);
   L.gcursor = take((size_t)(kMaxGroups + 1) * 4);
+  L.parts_cap = (int)((n_part > 0 ? n_part : 0) / kTileSplit) + 1;        // sum over tiles of floor((count - 1) / split) <= n_part / split
+  L.parts = take((size_t)L.parts_cap * sizeof(uint2));
+  L.nparts = take(256);
   L.total = off;
   return L;
 }
@@ -1700,7 +1740,13 @@ static int run_deposit(const PaintParams& p, const TileGeom& g, const SortedLayo
       const int fx_bits = fx_env ? fx_env : 31;
       paint_tile_fx_kernel<ORDER, REFCIC><<<tile_count, tpb, smem, s>>>(sorted, offsets, g, p.wrap, p.variant,
                                                                       mesh_vec_ok, p.w ? 1 : 0, p.mesh, tmap, use_tma,
-                                                                      tile_offset, bank_order, fx_bits);
+                                                                      tile_offset, bank_order, fx_bits, nullptr, nullptr, tile_count);
+      // further parts of heavy tiles: at most parts_cap list entries, CTAs beyond the list's length return at once
+      paint_tile_fx_kernel<ORDER, REFCIC><<<L.parts_cap, tpb, smem, s>>>(sorted, offsets, g, p.wrap, p.variant,
+                                                                       mesh_vec_ok, p.w ? 1 : 0, p.mesh, tmap, use_tma,
+                                                                       tile_offset, bank_order, fx_bits,
+                                                                       (const uint2*)(ws + L.parts), (const unsigned*)(ws + L.nparts),
+                                                                       tile_count);
     }
   }
   JPS_CHECK_LAUNCH();
@@ -1727,6 +1773,13 @@ static int run_sorted(const PaintParams& p, const TileGeom& g, char* ws, size_t 
   if (phase != 2) {
     int rc = g.two_level ? run_bucket_two_level<ORDER, REFCIC>(p, g, L, ws, s) : run_bucket<ORDER, REFCIC>(p, g, L, ws, s);
     if (rc) return rc;
+    {                                              // list of the further parts of heavy tiles (usually empty)
+      ScopedLaunch T(K_BUCKET_SCAN, s);
+      JPS_CHECK_CUDA(cudaMemsetAsync(ws + L.nparts, 0, 4, s));
+      tile_parts_kernel<<<(g.ntiles + 255) / 256, 256, 0, s>>>((const unsigned*)(ws + L.offsets), g.ntiles, g.rep,
+                                                                (uint2*)(ws + L.parts), (unsigned*)(ws + L.nparts), L.parts_cap);
+    }
+    JPS_CHECK_LAUNCH();
   }
   if (phase == 1) return JPS_OK;
   if (phase == 0) { tx_begin = 0; tx_end = g.ntx; }

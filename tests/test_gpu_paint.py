@@ -278,6 +278,35 @@ def test_one_outlier_weight_costs_precision_in_its_own_tile_only(jps, order):
     assert np.abs(got - want)[near].max() <= 3e-7 * 1e9
 
 
+@pytest.mark.parametrize("order,compat", [(2, "reference"), (2, "fixed"), (3, "fixed"), (4, "fixed")])
+def test_heavy_tiles_are_split_over_ctas(jps, order, compat):
+    """One CTA deposits at most 16384 particles of a tile; the rest of a heavy tile is taken by further CTAs, each
+    with its own shared-memory copy of the tile (the flush is additive).  60 % of the catalogue sits in a blob narrower
+    than a tile (~1.7e5 particles in one tile: 11 parts) and 20 % in a blob around the box corner (periodic wrap,
+    boundary tiles that flush with per-thread reds): the mesh must agree with the f64 oracle like any other."""
+    n, box, npart = 64, 1000.0, 300_000
+    rng = np.random.default_rng(5)
+    p = rng.random((npart, 3)) * box
+    p[:180_000] = np.array([625.0, 635.0, 645.0]) + rng.normal(size=(180_000, 3)) * 20.0      # sigma = 1.3 cells, mid-tile
+    p[180_000:240_000] = rng.normal(size=(60_000, 3)) * 15.0                                   # around the origin
+    p = (p % box).astype(F32)
+    p[p >= F32(box)] = 0.0
+    w = rng.uniform(-0.5, 1.5, npart).astype(F32)
+    tiles = (np.floor(p * F32(n / box)).astype(np.int64) % n) // 16
+    assert np.bincount((tiles[:, 0] * 4 + tiles[:, 1]) * 4 + tiles[:, 2]).max() > 5 * 16384
+    for wt in (None, w):
+        want = om.paint(np.zeros((n, n, n)), p[:, 0], p[:, 1], p[:, 2], wt, 0., 0., 0., box, n, True,
+                        order=order, compat=compat, precision="f64")
+        per_cell = want if wt is None else om.paint(np.zeros((n, n, n)), p[:, 0], p[:, 1], p[:, 2], np.abs(wt), 0., 0., 0.,
+                                                    box, n, True, order=order, compat=compat, precision="f64")
+        got = jps.paint(np.zeros((n, n, n), F32), p[:, 0], p[:, 1], p[:, 2], wt, 0., 0., 0., box, n, True,
+                        order=order, compat=compat, method="sorted").astype(np.float64)
+        tol = 3e-7 * np.abs(per_cell) + 2e-7
+        bad = np.abs(got - want) > tol
+        assert not bad.any(), f"{bad.sum()} cells off, worst {np.max(np.abs(got - want) / tol):.2f}x tol (weights: {wt is not None})"
+        assert abs(got.sum() - want.sum()) <= 1e-6 * np.abs(per_cell).sum()
+
+
 @pytest.mark.parametrize("bad", [np.inf, -np.inf, np.nan])
 def test_non_finite_weight_propagates_like_a_float_scatter(jps, bad):
     """inf / NaN weights never enter the fixed-point tile: the particle is deposited with float atomics, so its
