@@ -307,6 +307,29 @@ def test_heavy_tiles_are_split_over_ctas(jps, order, compat):
         assert abs(got.sum() - want.sum()) <= 1e-6 * np.abs(per_cell).sum()
 
 
+def test_heavy_group_is_sliced_over_ctas(jps):
+    """The fine pass gives a group of tiles to one CTA; a group above 2^22 records is left to fine_heavy_kernel, which
+    cuts it into slices placed through the global tile cursors.  5e6 of 6e6 particles sit in one tile of a 64^3 mesh
+    (one tile per group there): mesh against the float64 C oracle, and mass conservation."""
+    from oracle import cport
+    n, box, npart, nb = 64, 1000.0, 6_000_000, 5_000_000
+    rng = np.random.default_rng(8)
+    p = rng.random((npart, 3)) * box
+    p[:nb] = np.array([625.0, 635.0, 645.0]) + rng.normal(size=(nb, 3)) * 20.0
+    p = (p % box).astype(F32)
+    p[p >= F32(box)] = 0.0
+    rng.shuffle(p, axis=0)
+    x, y, z = (np.ascontiguousarray(p[:, i]) for i in range(3))
+    for order in (3, 4):
+        want = cport.paint_f64(np.zeros((n, n, n)), x, y, z, None, 0., 0., 0., box, n, True, order=order, compat="fixed")
+        got = jps.paint(np.zeros((n, n, n), F32), x, y, z, None, 0., 0., 0., box, n, True, order=order, compat="fixed",
+                        method="sorted").astype(np.float64)
+        err = np.abs(got - want) / np.maximum(np.abs(want), 1.0)
+        # ~300 parts of the heavy tile are added to the mesh in float32 (reduce-add in L2, any order)
+        assert err.max() < 3e-6, f"order {order}: max error relative to max(|cell|,1): {err.max():.3e}"
+        assert abs(got.sum() / npart - 1.0) < 1e-7
+
+
 @pytest.mark.parametrize("bad", [np.inf, -np.inf, np.nan])
 def test_non_finite_weight_propagates_like_a_float_scatter(jps, bad):
     """inf / NaN weights never enter the fixed-point tile: the particle is deposited with float atomics, so its
